@@ -1,0 +1,313 @@
+// One pass of the multi-pass NTT: a CTA owns a tile of R = 2^log_r rows x ZKB_NTT_C columns held in
+// shared memory, runs a radix-2^log_r decimation-in-frequency sub-NTT down the rows (radix-4 steps,
+// 2 butterfly levels per shared-memory round trip), and writes the tile back multiplied by the
+// inter-pass twiddles.  Columns are independent transforms, laid out so that every global access is
+// a contiguous run (ZKB_NTT_C elements = 256 B along the column axis, or R elements when the row
+// axis is the contiguous one) and every shared-memory access of a quarter-warp hits distinct banks.
+//
+// Device replacement for crypto3-math `basic_radix2_domain::fft / inverse_fft`
+// (call sites: zk/snark/reductions/r1cs_to_qap.hpp:250-310,
+//  zk/commitments/detail/polynomial/basic_fri.hpp:453) - same DFT, natural order in and out.
+//
+// The body is written as per-thread "phase" functions (load / step / store) that are
+// __host__ __device__: the kernel calls them between __syncthreads(), and the CPU test harness
+// (host_selftest.cpp) replays them thread by thread over a host buffer, which is how the index
+// logic is validated in the GPU-less build container.
+#pragma once
+#include "zkb_field.cuh"
+
+namespace zkb {
+
+#define ZKB_NTT_C 8            // columns per tile
+#ifndef ZKB_NTT_MAX_LOG_R
+#define ZKB_NTT_MAX_LOG_R 8    // rows per tile <= 256 (overridable so the CPU replay can exercise 3-4 pass plans at small sizes)
+#endif
+#define ZKB_NTT_TW_LOG 10      // master in-tile twiddle table: w_{1024}^j, j < 512
+#define ZKB_NTT_THREADS 256
+#define ZKB_NTT_MAX_PASSES 4
+
+struct alignas(16) u128 {
+    uint32_t x, y, z, w;
+};
+
+enum { NTT_MODE_SINGLE = 0, NTT_MODE_STRIDED = 1, NTT_MODE_FINAL = 2 };
+
+struct NttPassParams {
+    const u128 *in;
+    u128 *out;
+    uint64_t in_poly_stride, out_poly_stride;  // elements between consecutive polynomials
+    uint64_t tiles_per_poly;                   // SINGLE: tiles cover the batch, tiles_per_poly = 0
+    uint32_t batch;
+    int mode;
+    int log_r;             // this pass' radix
+    int log_n;             // full transform size
+    int log_m;             // STRIDED: log2 M_i (row stride); FINAL: log2 M_1 (column stride)
+    int log_mprev;         // STRIDED: log2 M_{i-1}
+    int n_passes;
+    int lr[ZKB_NTT_MAX_PASSES];   // log radix of every pass (for the FINAL digit reversal)
+    uint64_t in_valid_elems;      // input indices (within the polynomial) >= this read as zero (zero-padded LDE)
+    const void *load_tab;         // optional: in[i] *= load_tab[i & load_mask]   (Montgomery form)
+    uint64_t load_mask;
+    const void *store_tab;        // optional: out[o] *= store_tab[o & store_mask]
+    uint64_t store_mask;
+    const void *tw;               // master twiddles w_{2^ZKB_NTT_TW_LOG}^j (direction specific)
+};
+
+// shared-memory layout: two planes (low/high 16 bytes of every element), [row][C+1] 16-byte slots,
+// second plane offset by 4 extra slots so the planes fall in different bank groups.
+ZKB_HD constexpr uint32_t ntt_plane_slots(int log_r) { return (1u << log_r) * (ZKB_NTT_C + 1) + 4; }
+ZKB_HD constexpr uint32_t ntt_smem_bytes(int log_r) { return 2u * ntt_plane_slots(log_r) * 16u; }
+ZKB_HD uint32_t ntt_slot(int log_r, int plane, uint32_t r, uint32_t c) {
+    return plane * ntt_plane_slots(log_r) + r * (ZKB_NTT_C + 1) + c;
+}
+
+ZKB_HD uint32_t brev(uint32_t v, int bits) {
+#if defined(__CUDA_ARCH__)
+    return bits ? (__brev(v) >> (32 - bits)) : 0;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+struct NttTile {
+    uint64_t in_base, out_base;                 // element offsets (including the polynomial offset)
+    uint64_t in_row_stride, in_col_stride, out_row_stride, out_col_stride;
+    uint64_t in_tab_base, out_tab_base;         // offsets within the polynomial (for the tables)
+    uint32_t ncols;                             // valid columns
+};
+
+ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
+    NttTile t;
+    const uint32_t C = ZKB_NTT_C;
+    if (p.mode == NTT_MODE_SINGLE) {
+        // columns = polynomials of the batch
+        uint64_t b0 = tile * C;
+        t.in_base = b0 * p.in_poly_stride;
+        t.out_base = b0 * p.out_poly_stride;
+        t.in_row_stride = 1; t.in_col_stride = p.in_poly_stride;
+        t.out_row_stride = 1; t.out_col_stride = p.out_poly_stride;
+        t.in_tab_base = 0; t.out_tab_base = 0;
+        uint64_t left = p.batch - b0;
+        t.ncols = left < C ? (uint32_t)left : C;
+        return t;
+    }
+    uint64_t poly = tile / p.tiles_per_poly;
+    uint64_t tt = tile % p.tiles_per_poly;
+    t.ncols = C;
+    if (p.mode == NTT_MODE_STRIDED) {
+        uint64_t blocks = (1ull << p.log_m) / C;       // column blocks per row group
+        uint64_t q = tt / blocks, cb = tt % blocks;
+        uint64_t off = (q << p.log_mprev) + cb * C;
+        t.in_tab_base = off; t.out_tab_base = off;
+        t.in_base = poly * p.in_poly_stride + off;
+        t.out_base = poly * p.out_poly_stride + off;
+        t.in_row_stride = 1ull << p.log_m; t.in_col_stride = 1;
+        t.out_row_stride = 1ull << p.log_m; t.out_col_stride = 1;
+    } else {  // FINAL: rows contiguous on input, columns (k_1) contiguous on output
+        uint64_t kblocks = (1ull << p.lr[0]) / C;
+        uint64_t kb = tt % kblocks, q = tt / kblocks;  // q = (k_2 .. k_{p-1}) mixed radix, k_2 major
+        uint64_t in_off = ((kb * C) << p.log_m) + (q << p.log_r);
+        uint64_t rev = 0, qq = q;
+        for (int i = p.n_passes - 2; i >= 1; i--) {
+            uint64_t d = qq & ((1ull << p.lr[i]) - 1);
+            qq >>= p.lr[i];
+            rev = (rev << p.lr[i]) | d;
+        }
+        uint64_t out_off = kb * C + (rev << p.lr[0]);
+        t.in_tab_base = in_off; t.out_tab_base = out_off;
+        t.in_base = poly * p.in_poly_stride + in_off;
+        t.out_base = poly * p.out_poly_stride + out_off;
+        t.in_row_stride = 1; t.in_col_stride = 1ull << p.log_m;
+        t.out_row_stride = 1ull << (p.log_n - p.log_r); t.out_col_stride = 1;
+    }
+    return t;
+}
+
+template <class F>
+ZKB_HD F ntt_ld_elem(const u128 *s, int log_r, uint32_t r, uint32_t c) {
+    u128 lo = s[ntt_slot(log_r, 0, r, c)], hi = s[ntt_slot(log_r, 1, r, c)];
+    F v;
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+    return v;
+}
+template <class F>
+ZKB_HD void ntt_st_elem(u128 *s, int log_r, uint32_t r, uint32_t c, const F &v) {
+    u128 lo = {v.l[0], v.l[1], v.l[2], v.l[3]}, hi = {v.l[4], v.l[5], v.l[6], v.l[7]};
+    s[ntt_slot(log_r, 0, r, c)] = lo;
+    s[ntt_slot(log_r, 1, r, c)] = hi;
+}
+template <class F>
+ZKB_HD F ntt_ld_tab(const void *tab, uint64_t idx) {
+    const u128 *t = (const u128 *)tab + 2 * idx;
+    u128 lo = t[0], hi = t[1];
+    F v;
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+    v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------ load phase
+// Copies the tile global -> shared (16-byte units, coalesced along whichever axis is contiguous).
+template <class F>
+ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem, uint32_t tid,
+                                  uint32_t nthreads) {
+    const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r;
+    const uint32_t total = R * C * 2;  // 16-byte units
+    const u128 zero = {0, 0, 0, 0};
+    for (uint32_t u = tid; u < total; u += nthreads) {
+        uint32_t half, r, c;
+        if (t.in_col_stride == 1) {      // runs of C elements along the column axis
+            half = u & 1; c = (u >> 1) % C; r = u / (2 * C);
+        } else {                         // runs of R elements along the row axis
+            half = u & 1; r = (u >> 1) % R; c = u / (2 * R);
+        }
+        u128 v = zero;
+        uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
+        if (c < t.ncols && widx < p.in_valid_elems)
+            v = p.in[2 * (t.in_base + r * t.in_row_stride + c * t.in_col_stride) + half];
+        smem[ntt_slot(p.log_r, half, r, c)] = v;
+    }
+}
+
+// optional pre-multiplication (coset shift) - separate phase so that it works on whole elements
+template <class F>
+ZKB_HD void ntt_phase_premul(const NttPassParams &p, const NttTile &t, u128 *smem, uint32_t tid,
+                                    uint32_t nthreads) {
+    const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r;
+    for (uint32_t e = tid; e < R * C; e += nthreads) {
+        uint32_t c = e % C, r = e / C;
+        uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
+        if (c >= t.ncols || widx >= p.in_valid_elems) continue;
+        uint64_t idx = widx & p.load_mask;
+        F v = ntt_ld_elem<F>(smem, p.log_r, r, c);
+        v = v * ntt_ld_tab<F>(p.load_tab, idx);
+        ntt_st_elem<F>(smem, p.log_r, r, c, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------ butterflies
+template <class F>
+ZKB_HD F ntt_tw(const NttPassParams &p, uint32_t e, int log_size) {
+    // w_{2^log_size}^e from the master table
+    return ntt_ld_tab<F>(p.tw, (uint64_t)e << (ZKB_NTT_TW_LOG - log_size));
+}
+
+// radix-2 DIF level with half-distance h = 2^log_h
+template <class F>
+ZKB_HD void ntt_phase_radix2(const NttPassParams &p, u128 *smem, int log_h, uint32_t tid,
+                                    uint32_t nthreads) {
+    const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r, h = 1u << log_h;
+    for (uint32_t task = tid; task < (R / 2) * C; task += nthreads) {
+        uint32_t c = task % C, g = task / C;
+        uint32_t j = g & (h - 1);
+        uint32_t i = ((g >> log_h) << (log_h + 1)) + j;
+        F a = ntt_ld_elem<F>(smem, p.log_r, i, c), b = ntt_ld_elem<F>(smem, p.log_r, i + h, c);
+        F s = a + b, d = a - b;
+        if (h > 1) d = d * ntt_tw<F>(p, j, log_h + 1);
+        ntt_st_elem<F>(smem, p.log_r, i, c, s);
+        ntt_st_elem<F>(smem, p.log_r, i + h, c, d);
+    }
+}
+
+// two fused DIF levels with half-distances h = 2^log_h and h/2
+template <class F>
+ZKB_HD void ntt_phase_radix4(const NttPassParams &p, u128 *smem, int log_h, uint32_t tid,
+                                    uint32_t nthreads) {
+    const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r, h = 1u << log_h, q = h >> 1;
+    const int log_q = log_h - 1;
+    for (uint32_t task = tid; task < (R / 4) * C; task += nthreads) {
+        uint32_t c = task % C, g = task / C;
+        uint32_t j = g & (q - 1);
+        uint32_t i = ((g >> log_q) << (log_h + 1)) + j;
+        F x0 = ntt_ld_elem<F>(smem, p.log_r, i, c), x2 = ntt_ld_elem<F>(smem, p.log_r, i + h, c);
+        F y0 = x0 + x2, y2 = x0 - x2;
+        F x1 = ntt_ld_elem<F>(smem, p.log_r, i + q, c), x3 = ntt_ld_elem<F>(smem, p.log_r, i + h + q, c);
+        F y1 = x1 + x3, y3 = x1 - x3;
+        if (q > 1) y2 = y2 * ntt_tw<F>(p, j, log_h + 1);      // j == 0 is the only exponent when q == 1
+        y3 = y3 * ntt_tw<F>(p, j + q, log_h + 1);
+        F z0 = y0 + y1, z1 = y0 - y1, z2 = y2 + y3, z3 = y2 - y3;
+        if (q > 1) {
+            F w = ntt_tw<F>(p, j, log_h);
+            z1 = z1 * w;
+            z3 = z3 * w;
+        }
+        ntt_st_elem<F>(smem, p.log_r, i, c, z0);
+        ntt_st_elem<F>(smem, p.log_r, i + q, c, z1);
+        ntt_st_elem<F>(smem, p.log_r, i + h, c, z2);
+        ntt_st_elem<F>(smem, p.log_r, i + h + q, c, z3);
+    }
+}
+
+// ------------------------------------------------------------------------------------ store phase
+// Output row k lives in shared row bitrev(k) (DIF leaves the sub-transform bit-reversed).
+template <class F>
+ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128 *smem, uint32_t tid,
+                                   uint32_t nthreads) {
+    const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r;
+    if (p.store_tab == nullptr) {
+        const uint32_t total = R * C * 2;
+        for (uint32_t u = tid; u < total; u += nthreads) {
+            uint32_t half, k, c;
+            if (t.out_col_stride == 1) {
+                half = u & 1; c = (u >> 1) % C; k = u / (2 * C);
+            } else {
+                half = u & 1; k = (u >> 1) % R; c = u / (2 * R);
+            }
+            if (c >= t.ncols) continue;
+            p.out[2 * (t.out_base + k * t.out_row_stride + c * t.out_col_stride) + half] =
+                smem[ntt_slot(p.log_r, half, brev(k, p.log_r), c)];
+        }
+        return;
+    }
+    for (uint32_t e = tid; e < R * C; e += nthreads) {
+        uint32_t k, c;
+        if (t.out_col_stride == 1) { c = e % C; k = e / C; } else { k = e % R; c = e / R; }
+        if (c >= t.ncols) continue;
+        uint64_t off = k * t.out_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.out_col_stride);
+        F v = ntt_ld_elem<F>(smem, p.log_r, brev(k, p.log_r), c);
+        v = v * ntt_ld_tab<F>(p.store_tab, (t.out_tab_base + off) & p.store_mask);
+        u128 lo = {v.l[0], v.l[1], v.l[2], v.l[3]}, hi = {v.l[4], v.l[5], v.l[6], v.l[7]};
+        u128 *dst = p.out + 2 * (t.out_base + k * t.out_row_stride + c * t.out_col_stride);
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+}
+
+// Sequence of phases shared by the kernel and the host replay.  `sync` is __syncthreads() on the
+// device and a no-op marker on the host (the host replays a phase for all threads before moving on).
+#define ZKB_NTT_FOR_EACH_PHASE(PHASE_LOAD, PHASE_PREMUL, PHASE_R2, PHASE_R4, PHASE_STORE, log_r, has_load_tab) \
+    {                                                                                                   \
+        PHASE_LOAD;                                                                                     \
+        if (has_load_tab) { PHASE_PREMUL; }                                                             \
+        int _lh = (log_r)-1;                                                                            \
+        if ((log_r)&1) { PHASE_R2(_lh); _lh -= 1; }                                                     \
+        for (; _lh >= 1; _lh -= 2) { PHASE_R4(_lh); }                                                   \
+        PHASE_STORE;                                                                                    \
+    }
+
+#if defined(__CUDACC__)
+template <class P>
+__global__ void __launch_bounds__(ZKB_NTT_THREADS, 3) ntt_pass_kernel(const NttPassParams p) {
+    typedef Fp<P> F;
+    extern __shared__ uint4 ntt_smem_raw[];
+    u128 *smem = reinterpret_cast<u128 *>(ntt_smem_raw);
+    const NttTile t = ntt_tile(p, blockIdx.x);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+#define ZKB_L ntt_phase_load<F>(p, t, smem, tid, nt); __syncthreads()
+#define ZKB_PM ntt_phase_premul<F>(p, t, smem, tid, nt); __syncthreads()
+#define ZKB_R2(lh) ntt_phase_radix2<F>(p, smem, lh, tid, nt); __syncthreads()
+#define ZKB_R4(lh) ntt_phase_radix4<F>(p, smem, lh, tid, nt); __syncthreads()
+#define ZKB_S ntt_phase_store<F>(p, t, smem, tid, nt)
+    ZKB_NTT_FOR_EACH_PHASE(ZKB_L, ZKB_PM, ZKB_R2, ZKB_R4, ZKB_S, p.log_r, p.load_tab != nullptr)
+#undef ZKB_L
+#undef ZKB_PM
+#undef ZKB_R2
+#undef ZKB_R4
+#undef ZKB_S
+}
+#endif
+
+}  // namespace zkb
