@@ -41,7 +41,7 @@ struct XYZZ {
     }
 
     // 2 * (affine p)   (mdbl-2008-s-1)
-    ZKB_HD static XYZZ dbl_affine(const Affine<F> &p) {
+    ZKB_HD_NOINLINE static XYZZ dbl_affine(const Affine<F> p) {
         if (p.is_infinity() || p.y.is_zero()) return infinity();
         XYZZ r;
         F U = p.y.dbl();
@@ -58,7 +58,7 @@ struct XYZZ {
     }
 
     // dbl-2008-s-1
-    ZKB_HD XYZZ dbl() const {
+    ZKB_HD_NOINLINE XYZZ dbl() const {
         if (is_infinity() || Y.is_zero()) return infinity();
         XYZZ r;
         F U = Y.dbl();
@@ -101,7 +101,7 @@ struct XYZZ {
     }
 
     // this += q   (add-2008-s)
-    ZKB_HD void add(const XYZZ &q) {
+    ZKB_HD_NOINLINE void add(const XYZZ &q) {
         if (q.is_infinity()) return;
         if (is_infinity()) { *this = q; return; }
         F U1 = X * q.ZZ;

@@ -1,0 +1,54 @@
+// Internal (non-ABI) declarations shared by the translation units of libzkb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/zkb200.h"
+
+struct zkb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string last_error;
+    uint64_t launches = 0;
+    uint64_t scratch_limit = 6ull << 30;
+    // grow-only scratch buffers, keyed by role
+    struct Buf {
+        void *p = nullptr;
+        size_t cap = 0;
+    };
+    std::map<std::string, Buf> scratch;
+    // cached device tables (twiddles, coset powers), keyed by a descriptive string
+    std::map<std::string, Buf> tables;
+};
+
+namespace zkb {
+
+int ctx_fail(zkb_ctx *ctx, int status, const std::string &msg);
+// returns a device buffer of at least `bytes` (reallocates when too small)
+int ctx_scratch(zkb_ctx *ctx, const char *role, size_t bytes, void **out);
+// looks a table up; *created is set when the caller has to fill it
+int ctx_table(zkb_ctx *ctx, const std::string &key, size_t bytes, void **out, bool *created);
+
+#define ZKB_CUDA_OK(ctx, expr)                                                                       \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return zkb::ctx_fail(ctx, _e == cudaErrorMemoryAllocation ? ZKB_ERR_OUT_OF_MEMORY : ZKB_ERR_CUDA, \
+                                 std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+#define ZKB_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != ZKB_OK) return _s;  \
+    } while (0)
+
+// device-pointer level entry points used across translation units
+int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
+               const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st);
+int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
+               cudaStream_t st);
+
+}  // namespace zkb

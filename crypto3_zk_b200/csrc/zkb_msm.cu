@@ -1,0 +1,552 @@
+// Pippenger multi-scalar multiplication on G1 (BLS12-381, BN254, Pallas) for sm_100a.
+//
+// Device replacement for `algebra::multiexp<Method>` / `multiexp_with_mixed_addition<Method>`
+// (call sites: zk/commitments/polynomial/kzg.hpp:146, zk/snark/systems/ppzksnark/r1cs_gg_ppzksnark/
+// prover.hpp:108-139, zk/commitments/polynomial/knowledge_commitment_multiexp.hpp:107).  The result is
+// the same group element whatever the method; parity is checked in affine form.
+//
+// Pipeline (W = ceil((bits+1)/c) signed c-bit windows, 2^(c-1) buckets per window):
+//   1 digits      scalar -> W signed digits; key = (bucket << 1 | sign); histogram of bucket sizes
+//   2 scan        bucket offsets; split buckets longer than MSM_TASK_CAP into tasks (0/1-heavy
+//                 Groth16 assignments put most points into one bucket - the reference pre-filters
+//                 them on the CPU, knowledge_commitment_multiexp.hpp:88-101)
+//   3 scatter     counting sort of (point index, sign) by bucket
+//   4 accumulate  one thread per task: XYZZ += affine point (mixed add, 8M+2S)
+//   5 reduce      per window S_w = sum_k (k+1) B_k via radix-32 digit sums of the bucket index
+//                 (every level is a flat, short-chain parallel sum; no serial running sum over 2^(c-1))
+//   6 combine     sum_w 2^(c w) S_w on the host (c W doublings; zkb_msm_host.cpp)
+#include <stdio.h>
+#include <string.h>
+#include "zkb_curve.cuh"
+#include "zkb_internal.h"
+
+using namespace zkb;
+
+namespace zkb {
+int msm_window_combine(int curve, int c, int W, const uint32_t *sums, uint32_t *out);
+}
+
+struct zkb_msm_bases {
+    zkb_ctx *ctx;
+    int curve;
+    uint64_t n;
+    void *d_points;  // Affine<F>, Montgomery form
+};
+
+#define MSM_TASK_CAP 256u
+#define MSM_SENTINEL 0xffffffffu
+#define MSM_LEVEL_BITS 5
+
+// ------------------------------------------------------------------------------------ small kernels
+template <class P>
+__global__ void __launch_bounds__(256) points_to_mont_kernel(uint64_t n, Affine<Fp<P>> *pts) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pts[i] = pts[i].to_mont();
+}
+
+// scalars: 8 canonical limbs each.  keys[w * n + i]
+__global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint32_t *__restrict__ scalars, int c, int W,
+                                                         uint32_t *__restrict__ keys, uint32_t *__restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars) + 2 * (uint64_t)i;
+    uint4 lo = sp[0], hi = sp[1];
+    uint32_t l[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+        uint64_t two = limb < 8 ? ((uint64_t)l[limb] | ((uint64_t)l[limb + 1] << 32)) : 0;
+        uint32_t raw = ((uint32_t)(two >> sh) & mask) + carry;
+        uint32_t key = MSM_SENTINEL;
+        carry = 0;
+        if (raw != 0) {
+            uint32_t mag = raw, neg = 0;
+            if (raw > half && w < W - 1) {  // recode into [-2^(c-1), 2^(c-1)]
+                mag = (1u << c) - raw;
+                neg = 1;
+                carry = 1;
+            }
+            if (mag != 0) {
+                uint32_t bucket = (uint32_t)w * half + (mag - 1);
+                key = (bucket << 1) | neg;
+                atomicAdd(counts + bucket, 1u);
+            }
+        }
+        keys[(uint64_t)w * n + i] = key;
+    }
+}
+
+// tasks per bucket from the bucket sizes
+__global__ void __launch_bounds__(256) msm_ntasks_kernel(uint32_t nb, const uint32_t *__restrict__ counts,
+                                                         uint32_t *__restrict__ ntasks) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) ntasks[b] = (counts[b] + MSM_TASK_CAP - 1) / MSM_TASK_CAP;
+}
+
+// ---- exclusive scan over uint32 (three launches, 1024 items per block) --------------------------
+__global__ void __launch_bounds__(256) scan_block_kernel(uint32_t n, const uint32_t *__restrict__ in,
+                                                         uint32_t *__restrict__ out, uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[8];
+    uint32_t base = blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t k = 0; k < wid; k++) woff += warp_sums[k];
+    uint32_t excl = woff + incl - s;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) out[base + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + incl;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t nblocks, uint32_t *block_sums, uint32_t *total) {
+    // single block: serial over chunks of 1024 block sums
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nblocks ? block_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t d = 1; d < 1024; d <<= 1) {
+            uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t r = running;
+        if (i < nblocks) block_sums[i] = r + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = r + sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = running;
+}
+__global__ void __launch_bounds__(256) scan_add_kernel(uint32_t n, uint32_t *__restrict__ out,
+                                                       const uint32_t *__restrict__ block_sums) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += block_sums[i >> 10];
+}
+
+static int exclusive_scan(zkb_ctx *ctx, uint32_t n, const uint32_t *in, uint32_t *out, uint32_t *block_sums,
+                          uint32_t *total, cudaStream_t st) {
+    uint32_t nblocks = (n + 1023) / 1024;
+    scan_block_kernel<<<nblocks, 256, 0, st>>>(n, in, out, block_sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(nblocks, block_sums, total);
+    scan_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, out, block_sums);
+    ctx->launches += 3;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+struct MsmTask {
+    uint32_t start;   // offset into the sorted index array
+    uint32_t len;
+};
+
+// one thread per bucket: emit its tasks
+__global__ void __launch_bounds__(256) msm_fill_tasks_kernel(uint32_t nb, const uint32_t *__restrict__ counts,
+                                                             const uint32_t *__restrict__ offsets,
+                                                             const uint32_t *__restrict__ task_offsets, MsmTask *tasks) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t cnt = counts[b], off = offsets[b], t = task_offsets[b];
+    for (uint32_t s = 0; s < cnt; s += MSM_TASK_CAP, t++) {
+        MsmTask k;
+        k.start = off + s;
+        k.len = cnt - s < MSM_TASK_CAP ? cnt - s : MSM_TASK_CAP;
+        tasks[t] = k;
+    }
+}
+
+__global__ void __launch_bounds__(256) msm_scatter_kernel(uint64_t total, uint32_t n, const uint32_t *__restrict__ keys,
+                                                          const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
+                                                          uint32_t *__restrict__ sorted) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    uint32_t key = keys[idx];
+    if (key == MSM_SENTINEL) return;
+    uint32_t bucket = key >> 1;
+    uint32_t i = (uint32_t)(idx % n);
+    uint32_t pos = atomicAdd(cursor + bucket, 1u);
+    sorted[offsets[bucket] + pos] = (i << 1) | (key & 1);
+}
+
+// ------------------------------------------------------------------------------------ accumulate
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F> *p) {
+    // 2*N limbs, 16-byte aligned (N = 8 or 12): vector loads
+    Affine<F> r;
+    const uint4 *s = reinterpret_cast<const uint4 *>(p);
+    uint32_t *d = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < (2 * F::N) / 4; k++) {
+        uint4 v = __ldg(s + k);
+        d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+    }
+    return r;
+}
+
+template <class P>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ n_tasks, const MsmTask *__restrict__ tasks,
+                                                             const uint32_t *__restrict__ sorted,
+                                                             const Affine<Fp<P>> *__restrict__ points,
+                                                             XYZZ<Fp<P>> *__restrict__ out) {
+    typedef Fp<P> F;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tasks) return;
+    MsmTask task = tasks[t];
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (uint32_t k = 0; k < task.len; k++) {
+        uint32_t e = sorted[task.start + k];
+        Affine<F> p = load_affine<F>(points + (e >> 1));
+        if (e & 1) p.y = p.y.neg();
+        acc.add_mixed(p);
+    }
+    out[t] = acc;
+}
+
+// ------------------------------------------------------------------------------------ reduce
+// Geometry of the radix-32 digit decomposition of the bucket index k in [0, 2^(c-1)).
+struct MsmLevels {
+    int n_levels;
+    int bits[8];      // bits of level l
+    int shift[8];     // bit offset of level l
+    int log_per;      // unused
+};
+__host__ __device__ inline MsmLevels msm_levels(int c) {
+    MsmLevels L;
+    int rem = c - 1, l = 0, sh = 0;
+    while (rem > 0) {
+        int b = rem < MSM_LEVEL_BITS ? rem : MSM_LEVEL_BITS;
+        L.bits[l] = b;
+        L.shift[l] = sh;
+        sh += b;
+        rem -= b;
+        l++;
+    }
+    if (l == 0) {  // c == 1: a single bucket
+        L.bits[0] = 0; L.shift[0] = 0; l = 1;
+    }
+    L.n_levels = l;
+    L.log_per = 0;
+    return L;
+}
+
+// R1: thread per (window, level, digit, chunk): sum of `chunk_len` buckets sharing that digit.
+// A bucket's value is the sum of its tasks' partial results.
+template <class P>
+__global__ void __launch_bounds__(128) msm_reduce_gather_kernel(int c, int W, int level, int log_chunk,
+                                                                const uint32_t *__restrict__ task_offsets,
+                                                                const uint32_t *__restrict__ ntasks,
+                                                                const XYZZ<Fp<P>> *__restrict__ task_out,
+                                                                XYZZ<Fp<P>> *__restrict__ tmp) {
+    typedef Fp<P> F;
+    const MsmLevels L = msm_levels(c);
+    const int b = L.bits[level], s = L.shift[level];
+    const uint32_t M = 1u << (c - 1);
+    const uint32_t per_digit = M >> b;                 // buckets sharing one digit value
+    const uint32_t nchunks = (per_digit + (1u << log_chunk) - 1) >> log_chunk;
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total = (uint32_t)W * (1u << b) * nchunks;
+    if (tid >= total) return;
+    uint32_t chunk = tid % nchunks;
+    uint32_t D = (tid / nchunks) & ((1u << b) - 1);
+    uint32_t w = tid / (nchunks << b);
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    uint32_t j0 = chunk << log_chunk, j1 = j0 + (1u << log_chunk);
+    if (j1 > per_digit) j1 = per_digit;
+    for (uint32_t j = j0; j < j1; j++) {
+        uint32_t low = j & ((1u << s) - 1), high = j >> s;
+        uint32_t k = (high << (s + b)) | (D << s) | low;
+        uint32_t bucket = w * M + k;
+        uint32_t t0 = task_offsets[bucket], nt = ntasks[bucket];
+        for (uint32_t t = 0; t < nt; t++) acc.add(task_out[t0 + t]);
+    }
+    tmp[tid] = acc;
+}
+
+// R2: thread per (window, level-slot, digit): sums its chunks.  Output layout P[w][slot][32].
+template <class P>
+__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(int W, int bits, int slot, int n_slots, uint32_t nchunks,
+                                                                const XYZZ<Fp<P>> *__restrict__ tmp,
+                                                                XYZZ<Fp<P>> *__restrict__ Pout) {
+    typedef Fp<P> F;
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total = (uint32_t)W << bits;
+    if (tid >= total) return;
+    uint32_t D = tid & ((1u << bits) - 1), w = tid >> bits;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    const XYZZ<F> *src = tmp + (uint64_t)tid * nchunks;
+    for (uint32_t k = 0; k < nchunks; k++) acc.add(src[k]);
+    Pout[((uint64_t)w * n_slots + slot) * 32 + D] = acc;
+}
+
+// R3: thread per (window, slot): slot < n_levels -> Q = sum_D D * P[D] (running sum from the top);
+// slot == n_levels -> plain sum of level 0 (= sum of all buckets).
+template <class P>
+__global__ void __launch_bounds__(64) msm_reduce_weighted_kernel(int c, int W, const XYZZ<Fp<P>> *__restrict__ Pin,
+                                                                 XYZZ<Fp<P>> *__restrict__ Q) {
+    typedef Fp<P> F;
+    const MsmLevels L = msm_levels(c);
+    const int n_slots = L.n_levels;
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (uint32_t)W * (n_slots + 1)) return;
+    uint32_t slot = tid % (n_slots + 1), w = tid / (n_slots + 1);
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    if (slot == (uint32_t)n_slots) {
+        const XYZZ<F> *p = Pin + ((uint64_t)w * n_slots) * 32;
+        for (int D = 0; D < (1 << L.bits[0]); D++) acc.add(p[D]);
+    } else {
+        const XYZZ<F> *p = Pin + ((uint64_t)w * n_slots + slot) * 32;
+        XYZZ<F> run = XYZZ<F>::infinity();
+        for (int D = (1 << L.bits[slot]) - 1; D >= 1; D--) {
+            run.add(p[D]);
+            acc.add(run);
+        }
+    }
+    Q[tid] = acc;
+}
+
+// R4: thread per window: S_w = plain + sum_l 2^shift[l] Q[l]
+template <class P>
+__global__ void __launch_bounds__(32) msm_reduce_window_kernel(int c, int W, const XYZZ<Fp<P>> *__restrict__ Q,
+                                                               XYZZ<Fp<P>> *__restrict__ S) {
+    typedef Fp<P> F;
+    const MsmLevels L = msm_levels(c);
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (uint32_t)W) return;
+    const XYZZ<F> *q = Q + (uint64_t)w * (L.n_levels + 1);
+    XYZZ<F> acc = q[L.n_levels - 1];
+    for (int l = L.n_levels - 2; l >= 0; l--) {
+        for (int i = 0; i < L.bits[l]; i++) acc = acc.dbl();
+        acc.add(q[l]);
+    }
+    acc.add(q[L.n_levels]);
+    S[w] = acc;
+}
+
+// ------------------------------------------------------------------------------------ host driver
+static int msm_pick_c(uint64_t n) {
+    int lg = 0;
+    while ((1ull << lg) < n) lg++;
+    int c = lg - 4;
+    if (c < 2) c = 2;
+    if (c > 20) c = 20;
+    return c;
+}
+
+template <class P, int SCALAR_BITS>
+static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
+                     uint32_t *partial_host, cudaStream_t st) {
+    typedef Fp<P> F;
+    typedef XYZZ<F> Pt;
+    const int c = msm_pick_c(n);
+    const int W = (SCALAR_BITS + 1 + c - 1) / c;
+    const uint32_t M = 1u << (c - 1);
+    const uint32_t nb = (uint32_t)W * M;
+    const MsmLevels L = msm_levels(c);
+    const uint64_t total_keys = (uint64_t)W * n;
+    if (n >= (1ull << 31) || total_keys >= (1ull << 32))
+        return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "MSM: W*n must be < 2^32 (split the range across calls/GPUs)");
+    const uint64_t max_tasks = (uint64_t)nb + total_keys / MSM_TASK_CAP + 1;
+
+    // ---- scratch carve-up
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_keys = carve(total_keys * 4), o_sorted = carve(total_keys * 4);
+    size_t o_counts = carve((size_t)nb * 4), o_offsets = carve((size_t)nb * 4), o_cursor = carve((size_t)nb * 4);
+    size_t o_ntasks = carve((size_t)nb * 4), o_toffs = carve((size_t)nb * 4);
+    size_t o_bsums = carve(((size_t)nb / 1024 + 2) * 4), o_totals = carve(16);
+    size_t o_tasks = carve(max_tasks * sizeof(MsmTask)), o_tout = carve(max_tasks * sizeof(Pt));
+    // reduce temporaries: per level W * 2^bits * nchunks partial sums
+    uint32_t max_tmp = 0, nchunks_l[8], logchunk_l[8];
+    for (int l = 0; l < L.n_levels; l++) {
+        uint32_t per_digit = M >> L.bits[l];
+        int lg = 0;
+        while ((1u << lg) < per_digit) lg++;
+        logchunk_l[l] = (lg + 1) / 2;
+        nchunks_l[l] = (per_digit + (1u << logchunk_l[l]) - 1) >> logchunk_l[l];
+        uint32_t cnt = (uint32_t)W * (1u << L.bits[l]) * nchunks_l[l];
+        if (cnt > max_tmp) max_tmp = cnt;
+    }
+    size_t o_tmp = carve((size_t)max_tmp * sizeof(Pt));
+    size_t o_P = carve((size_t)W * L.n_levels * 32 * sizeof(Pt));
+    size_t o_Q = carve((size_t)W * (L.n_levels + 1) * sizeof(Pt));
+    size_t o_S = carve((size_t)W * sizeof(Pt));
+    void *base;
+    ZKB_TRY(ctx_scratch(ctx, "msm", off, &base));
+    char *B = (char *)base;
+    uint32_t *keys = (uint32_t *)(B + o_keys), *sorted = (uint32_t *)(B + o_sorted);
+    uint32_t *counts = (uint32_t *)(B + o_counts), *offsets = (uint32_t *)(B + o_offsets), *cursor = (uint32_t *)(B + o_cursor);
+    uint32_t *ntasks = (uint32_t *)(B + o_ntasks), *toffs = (uint32_t *)(B + o_toffs);
+    uint32_t *bsums = (uint32_t *)(B + o_bsums), *totals = (uint32_t *)(B + o_totals);
+    MsmTask *tasks = (MsmTask *)(B + o_tasks);
+    Pt *tout = (Pt *)(B + o_tout), *tmp = (Pt *)(B + o_tmp), *Pl = (Pt *)(B + o_P), *Q = (Pt *)(B + o_Q), *S = (Pt *)(B + o_S);
+
+    // counts and cursor are adjacent carve-outs: one memset
+    ZKB_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
+    ZKB_CUDA_OK(ctx, cudaMemsetAsync(cursor, 0, (size_t)nb * 4, st));
+    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, (const uint32_t *)d_scalars, c, W, keys, counts);
+    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, ntasks);
+    ctx->launches += 2;
+    ZKB_TRY(exclusive_scan(ctx, nb, counts, offsets, bsums, totals, st));
+    ZKB_TRY(exclusive_scan(ctx, nb, ntasks, toffs, bsums, totals + 1, st));
+    msm_fill_tasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, offsets, toffs, tasks);
+    msm_scatter_kernel<<<(unsigned)((total_keys + 255) / 256), 256, 0, st>>>(total_keys, (uint32_t)n, keys, offsets, cursor, sorted);
+    const Affine<F> *pts = (const Affine<F> *)bases->d_points + offset;
+    msm_accumulate_kernel<P><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(totals + 1, tasks, sorted, pts, tout);
+    ctx->launches += 3;
+    for (int l = 0; l < L.n_levels; l++) {
+        uint32_t cnt = (uint32_t)W * (1u << L.bits[l]) * nchunks_l[l];
+        msm_reduce_gather_kernel<P><<<(cnt + 127) / 128, 128, 0, st>>>(c, W, l, (int)logchunk_l[l], toffs, ntasks, tout, tmp);
+        uint32_t cnt2 = (uint32_t)W << L.bits[l];
+        msm_reduce_chunks_kernel<P><<<(cnt2 + 127) / 128, 128, 0, st>>>(W, L.bits[l], l, L.n_levels, nchunks_l[l], tmp, Pl);
+        ctx->launches += 2;
+    }
+    uint32_t cnt3 = (uint32_t)W * (L.n_levels + 1);
+    msm_reduce_weighted_kernel<P><<<(cnt3 + 63) / 64, 64, 0, st>>>(c, W, Pl, Q);
+    msm_reduce_window_kernel<P><<<(W + 31) / 32, 32, 0, st>>>(c, W, Q, S);
+    ctx->launches += 2;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    std::vector<uint32_t> hs((size_t)W * 4 * F::N);
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(hs.data(), S, hs.size() * 4, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return msm_window_combine(bases->curve, c, W, hs.data(), partial_host);
+}
+
+static int msm_run(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
+                   uint32_t *partial_host, cudaStream_t st) {
+    switch (bases->curve) {
+        case ZKB_CURVE_BLS12_381_G1:
+            return msm_run_t<params::Bls12381Fq, params::Bls12381Fr::BITS>(ctx, bases, offset, n, d_scalars, partial_host, st);
+        case ZKB_CURVE_BN254_G1:
+            return msm_run_t<params::Bn254Fq, params::Bn254Fr::BITS>(ctx, bases, offset, n, d_scalars, partial_host, st);
+        case ZKB_CURVE_PALLAS:
+            return msm_run_t<params::PallasFp, params::PallasFq::BITS>(ctx, bases, offset, n, d_scalars, partial_host, st);
+    }
+    return ZKB_ERR_INVALID_ARGUMENT;
+}
+
+static int curve_coord_limbs(int curve) {
+    switch (curve) {
+        case ZKB_CURVE_BLS12_381_G1: return 12;
+        case ZKB_CURVE_BN254_G1: case ZKB_CURVE_PALLAS: return 8;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, int mem, void *stream,
+                         zkb_msm_bases **out) {
+    if (!ctx || !out) return ZKB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int cl = curve_coord_limbs(curve);
+    if (!cl || (n && !points_affine)) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_msm_bases_create: bad curve/pointer");
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = (size_t)n * 2 * cl * 4;
+    void *d = nullptr;
+    if (n) {
+        cudaError_t e = cudaMalloc(&d, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, "cudaMalloc MSM bases");
+        }
+        cudaError_t ce = cudaMemcpyAsync(d, points_affine, bytes, mem == ZKB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) {
+            cudaFree(d);
+            return ctx_fail(ctx, ZKB_ERR_CUDA, std::string("copy MSM bases: ") + cudaGetErrorString(ce));
+        }
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        switch (curve) {
+            case ZKB_CURVE_BLS12_381_G1: points_to_mont_kernel<params::Bls12381Fq><<<blocks, 256, 0, st>>>(n, (Affine<Fp<params::Bls12381Fq>> *)d); break;
+            case ZKB_CURVE_BN254_G1: points_to_mont_kernel<params::Bn254Fq><<<blocks, 256, 0, st>>>(n, (Affine<Fp<params::Bn254Fq>> *)d); break;
+            default: points_to_mont_kernel<params::PallasFp><<<blocks, 256, 0, st>>>(n, (Affine<Fp<params::PallasFp>> *)d); break;
+        }
+        ctx->launches++;
+        cudaError_t ke = cudaStreamSynchronize(st);
+        if (ke != cudaSuccess) {
+            cudaFree(d);
+            return ctx_fail(ctx, ZKB_ERR_CUDA, std::string("points_to_mont: ") + cudaGetErrorString(ke));
+        }
+    }
+    zkb_msm_bases *b = new zkb_msm_bases();
+    b->ctx = ctx;
+    b->curve = curve;
+    b->n = n;
+    b->d_points = d;
+    *out = b;
+    return ZKB_OK;
+}
+
+void zkb_msm_bases_free(zkb_msm_bases *b) {
+    if (!b) return;
+    if (b->d_points) {
+        cudaSetDevice(b->ctx->device);
+        cudaFree(b->d_points);
+    }
+    delete b;
+}
+
+uint64_t zkb_msm_bases_size(const zkb_msm_bases *b) { return b ? b->n : 0; }
+
+int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
+                    uint32_t *partial_xyzz_host, void *stream) {
+    if (!ctx || !bases || !partial_xyzz_host) return ZKB_ERR_INVALID_ARGUMENT;
+    if (bases->ctx != ctx || offset > bases->n || n > bases->n - offset || (n && !scalars))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_msm: range outside the bases / null scalars");
+    int cl = curve_coord_limbs(bases->curve);
+    if (n == 0) {  // empty sum = infinity (XYZZ all zero)
+        memset(partial_xyzz_host, 0, (size_t)4 * cl * 4);
+        return ZKB_OK;
+    }
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const void *ds = scalars;
+    if (mem != ZKB_MEM_DEVICE) {
+        void *d;
+        ZKB_TRY(ctx_scratch(ctx, "msm_scalars", (size_t)n * 32, &d));
+        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d, scalars, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        ds = d;
+    }
+    return msm_run(ctx, bases, offset, n, ds, partial_xyzz_host, st);
+}
+
+int zkb_msm(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
+            uint32_t *result_affine, void *stream) {
+    if (!ctx || !bases || !result_affine) return ZKB_ERR_INVALID_ARGUMENT;
+    uint32_t partial[4 * 12];
+    ZKB_TRY(zkb_msm_partial(ctx, bases, offset, n, scalars, mem, partial, stream));
+    return zkb_msm_combine(bases->curve, 1, partial, result_affine);
+}
+
+int zkb_msm_g1(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, const void *scalars, int mem,
+               uint32_t *result_affine, void *stream) {
+    zkb_msm_bases *b = nullptr;
+    ZKB_TRY(zkb_msm_bases_create(ctx, curve, n, points_affine, mem, stream, &b));
+    int s = zkb_msm(ctx, b, 0, n, scalars, mem, result_affine, stream);
+    zkb_msm_bases_free(b);
+    return s;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+// NTT / LDE / pointwise / FRI-fold runtime of libzkb200.so: table caches, pass launches, C ABI.
+// Kernel bodies are in zkb_ntt_pass.cuh; the plan and table definitions in zkb_ntt_plan.h /
+// zkb_ntt_tables.cuh.  See include/zkb200.h for the reference call sites each entry point serves.
+#include <stdio.h>
+#include <string.h>
+#include "zkb_internal.h"
+#include "zkb_ntt_plan.h"
+#include "zkb_ntt_tables.cuh"
+
+using namespace zkb;
+
+// ------------------------------------------------------------------------------------ table kernels
+template <class P>
+__global__ void __launch_bounds__(256) powtab_kernel(Fp<P> base, Fp<P> scale, int two_d, int log_m, uint64_t count,
+                                                     Fp<P> *out) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) out[idx] = powtab_value<Fp<P>>(base, scale, two_d, log_m, idx);
+}
+
+template <class P>
+static int fill_powtab(zkb_ctx *ctx, const Fp<P> &base, const Fp<P> &scale, int two_d, int log_m, uint64_t count,
+                       void *out, cudaStream_t st) {
+    uint64_t blocks = (count + 255) / 256;
+    powtab_kernel<P><<<(unsigned)blocks, 256, 0, st>>>(base, scale, two_d, log_m, count, (Fp<P> *)out);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+static std::string hexkey(const uint32_t *l, int n) {
+    char buf[16];
+    std::string s;
+    for (int i = n - 1; i >= 0; i--) {
+        snprintf(buf, sizeof buf, "%08x", l[i]);
+        s += buf;
+    }
+    return s;
+}
+
+// Collects (building on first use) every table one transform needs.
+template <class P>
+static int ntt_tables(zkb_ctx *ctx, const NttPlan &pl, int inverse, const uint32_t *shift, NttTables *tb,
+                      cudaStream_t st) {
+    typedef Fp<P> F;
+    const int log_n = pl.log_n;
+    const uint64_t N = 1ull << log_n;
+    memset(tb, 0, sizeof(*tb));
+    char key[160];
+    bool created;
+    void *p;
+    // master in-tile twiddles
+    snprintf(key, sizeof key, "tw:%d:%d", P::ID, inverse);
+    ZKB_TRY(ctx_table(ctx, key, sizeof(F) << (ZKB_NTT_TW_LOG - 1), &p, &created));
+    if (created) ZKB_TRY(fill_powtab<P>(ctx, ntt_omega<F, P>(ZKB_NTT_TW_LOG, inverse), F::one(), 0, 0,
+                                        1ull << (ZKB_NTT_TW_LOG - 1), p, st));
+    tb->tw = p;
+    // inter-pass twiddles
+    F ninv = ntt_n_inv<F>(log_n);
+    for (int i = 0; i + 1 < pl.n_passes; i++) {
+        int lmp = pl.log_m(i), lm = pl.log_m(i + 1);
+        bool scaled = (i == 0 && inverse);
+        snprintf(key, sizeof key, "inter:%d:%d:%d:%d:%d", P::ID, inverse, lmp, lm, scaled ? log_n : -1);
+        ZKB_TRY(ctx_table(ctx, key, sizeof(F) << lmp, &p, &created));
+        if (created)
+            ZKB_TRY(fill_powtab<P>(ctx, ntt_omega<F, P>(lmp, inverse), scaled ? ninv : F::one(), 1, lm, 1ull << lmp, p, st));
+        tb->inter[i] = p;
+    }
+    if (shift) {
+        F g;
+        memcpy(g.l, shift, sizeof(g.l));
+        for (int i = F::N - 1; i >= 0; i--) {  // must be canonical
+            if (g.l[i] < P::mod(i)) break;
+            if (g.l[i] > P::mod(i) || i == 0) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "coset shift >= modulus");
+        }
+        if (g.is_zero()) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "coset shift is zero");
+        bool scaled = inverse && pl.n_passes == 1;
+        snprintf(key, sizeof key, "coset:%d:%d:%d:%d:%s", P::ID, log_n, inverse, (int)scaled, hexkey(shift, F::N).c_str());
+        ZKB_TRY(ctx_table(ctx, key, sizeof(F) << log_n, &p, &created));
+        if (created) {
+            F gm = g.to_mont();
+            if (inverse) gm = gm.inverse();
+            ZKB_TRY(fill_powtab<P>(ctx, gm, scaled ? ninv : F::one(), 0, 0, N, p, st));
+        }
+        if (!inverse) { tb->load_tab = p; tb->load_mask = N - 1; }
+        else { tb->store_tab = p; tb->store_mask = N - 1; }
+    } else if (inverse && pl.n_passes == 1) {
+        snprintf(key, sizeof key, "ninv:%d:%d", P::ID, log_n);
+        ZKB_TRY(ctx_table(ctx, key, sizeof(F), &p, &created));
+        if (created) ZKB_CUDA_OK(ctx, cudaMemcpyAsync(p, &ninv, sizeof(F), cudaMemcpyHostToDevice, st));
+        tb->store_tab = p;
+        tb->store_mask = 0;
+    }
+    return ZKB_OK;
+}
+
+template <class P>
+static int ntt_launch(zkb_ctx *ctx, const NttPassParams &q, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZKB_CUDA_OK(ctx, cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)ntt_smem_bytes(ZKB_NTT_MAX_LOG_R)));
+        attr_set = true;
+    }
+    uint64_t tiles = ntt_pass_tiles(q);
+    if (tiles == 0) return ZKB_OK;
+    if (tiles > 0x7fffffffull) return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "too many tiles for one launch");
+    ntt_pass_kernel<P><<<(unsigned)tiles, ZKB_NTT_THREADS, ntt_smem_bytes(q.log_r), st>>>(q);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+template <class P>
+static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
+                        const uint32_t *shift, uint64_t in_poly_stride, uint64_t in_valid, cudaStream_t st) {
+    typedef Fp<P> F;
+    if (log_n > P::TWO_ADICITY) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n exceeds the two-adicity");
+    const uint64_t N = 1ull << log_n;
+    NttPlan pl = ntt_make_plan(log_n);
+    if (pl.n_passes < 1) return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "no pass plan");
+    NttTables tb;
+    ZKB_TRY(ntt_tables<P>(ctx, pl, inverse, shift, &tb, st));
+    // chunk the batch so the work buffer respects the scratch limit
+    uint64_t poly_bytes = N * sizeof(F);
+    uint32_t chunk = batch;
+    if (pl.n_passes > 1) {
+        uint64_t fit = ctx->scratch_limit / poly_bytes;
+        if (fit < 1) fit = 1;
+        if (fit < chunk) chunk = (uint32_t)fit;
+    }
+    void *work = nullptr;
+    if (pl.n_passes > 1) ZKB_TRY(ctx_scratch(ctx, "ntt_work", (size_t)chunk * poly_bytes, &work));
+    for (uint32_t b0 = 0; b0 < batch; b0 += chunk) {
+        uint32_t nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const char *cin = (const char *)d_in + (size_t)b0 * in_poly_stride * sizeof(F);
+        char *cout = (char *)d_out + (size_t)b0 * poly_bytes;
+        auto passes = ntt_build_passes(pl, tb, cin, cout, work, nb, in_poly_stride, N, in_valid);
+        for (auto &q : passes) ZKB_TRY(ntt_launch<P>(ctx, q, st));
+    }
+    return ZKB_OK;
+}
+
+#define ZKB_DISPATCH_NTT_FIELD(field, FN, ...)                                   \
+    switch (field) {                                                             \
+        case ZKB_FIELD_BLS12_381_FR: return FN<params::Bls12381Fr>(__VA_ARGS__); \
+        case ZKB_FIELD_BN254_FR: return FN<params::Bn254Fr>(__VA_ARGS__);        \
+        case ZKB_FIELD_PALLAS_FP: return FN<params::PallasFp>(__VA_ARGS__);      \
+        case ZKB_FIELD_PALLAS_FQ: return FN<params::PallasFq>(__VA_ARGS__);      \
+        default: return ZKB_ERR_INVALID_ARGUMENT;                                \
+    }
+
+namespace zkb {
+
+int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
+               const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st) {
+    if (batch == 0) return ZKB_OK;
+    if (log_n == 0) {  // size-1 transform is the identity (a coset shift g^0 = 1, 1/n = 1)
+        if (d_in != d_out)
+            ZKB_CUDA_OK(ctx, cudaMemcpy2DAsync(d_out, 32, d_in, in_poly_stride * 32, 32, batch, cudaMemcpyDeviceToDevice, st));
+        return ZKB_OK;
+    }
+    ZKB_DISPATCH_NTT_FIELD(field, ntt_device_t, ctx, log_n, batch, d_in, d_out, inverse, coset_shift, in_poly_stride,
+                           in_valid_elems, st)
+}
+
+int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
+               cudaStream_t st) {
+    if (batch == 0) return ZKB_OK;
+    const uint64_t Nin = 1ull << log_n_in, Nout = 1ull << log_n_out;
+    if (log_n_in == log_n_out) {
+        if (d_in != d_out) ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d_out, d_in, (size_t)batch * Nin * 32, cudaMemcpyDeviceToDevice, st));
+        return ZKB_OK;
+    }
+    // coefficients of a chunk of polynomials, then the zero-padded forward transform
+    uint64_t per_poly = (Nin + Nout) * 32;   // coefficient buffer + ntt work buffer
+    uint32_t chunk = batch;
+    uint64_t fit = ctx->scratch_limit / per_poly;
+    if (fit < 1) fit = 1;
+    if (fit < chunk) chunk = (uint32_t)fit;
+    void *coef;
+    ZKB_TRY(ctx_scratch(ctx, "lde_coef", (size_t)chunk * Nin * 32, &coef));
+    for (uint32_t b0 = 0; b0 < batch; b0 += chunk) {
+        uint32_t nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const char *cin = (const char *)d_in + (size_t)b0 * Nin * 32;
+        char *cout = (char *)d_out + (size_t)b0 * Nout * 32;
+        ZKB_TRY(ntt_device(ctx, field, log_n_in, nb, cin, coef, 1, nullptr, Nin, Nin, st));
+        ZKB_TRY(ntt_device(ctx, field, log_n_out, nb, coef, cout, 0, nullptr, Nin, Nin, st));
+    }
+    return ZKB_OK;
+}
+
+}  // namespace zkb
+
+// ------------------------------------------------------------------------------------ pointwise ops
+template <class P>
+__global__ void __launch_bounds__(256) vec_kernel(int op, uint64_t n, const Fp<P> *a, const Fp<P> *b, const Fp<P> *c,
+                                                  Fp<P> s_mont, Fp<P> *out) {
+    typedef Fp<P> F;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y = b[i], r;
+    switch (op) {
+        case ZKB_VEC_MUL: r = (x * y) * F::r2(); break;            // canonical in/out: (xy/R) * R^2 / R
+        case ZKB_VEC_SUB: r = x - y; break;
+        case ZKB_VEC_ADD: r = x + y; break;
+        default: {                                                  // (a*b - c) * s
+            F ab = (x * y) * F::r2();
+            r = (ab - c[i]) * s_mont;
+        }
+    }
+    out[i] = r;
+}
+
+template <class P>
+static int vec_t(zkb_ctx *ctx, int op, uint64_t n, const void *a, const void *b, const void *c, const uint32_t *scalar,
+                 void *out, cudaStream_t st) {
+    typedef Fp<P> F;
+    F s = F::one();
+    if (op == ZKB_VEC_MUL_SUB_SCALE) {
+        if (!scalar || !c) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "MUL_SUB_SCALE needs c and scalar");
+        memcpy(s.l, scalar, sizeof(s.l));
+        s = s.to_mont();
+    }
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks == 0) return ZKB_OK;
+    vec_kernel<P><<<(unsigned)blocks, 256, 0, st>>>(op, n, (const F *)a, (const F *)b, (const F *)c, s, (F *)out);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------------------------ FRI fold
+// out[i] = 1/2 ((1 + alpha w^-i) f[i] + (1 - alpha w^-i) f[i + n/2]); w^-i comes from a cached power
+// table instead of the reference's serial acc *= w^-1 (fold_polynomial.hpp:87-90).
+template <class P>
+__global__ void __launch_bounds__(256) fold_kernel(uint64_t half, const Fp<P> *f, const Fp<P> *winv_pow, Fp<P> alpha_mont,
+                                                   Fp<P> *out) {
+    typedef Fp<P> F;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    F acc = alpha_mont * winv_pow[i];                 // alpha * w^-i, Montgomery form
+    F a = f[i], b = f[i + half];                      // canonical
+    // 1/2 ((a + b) + acc (a - b)) ; mont_mul(canonical, montgomery) = canonical product
+    F s = a + b, d = (a - b) * acc;
+    out[i] = (s + d) * F::two_inv();
+}
+
+template <class P>
+static int fold_t(zkb_ctx *ctx, int log_n, const void *f, const uint32_t *alpha, void *out, cudaStream_t st) {
+    typedef Fp<P> F;
+    if (log_n < 1) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "fold needs log_n >= 1");
+    if (log_n > P::TWO_ADICITY) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n exceeds the two-adicity");
+    uint64_t half = 1ull << (log_n - 1);
+    char key[64];
+    snprintf(key, sizeof key, "foldw:%d:%d", P::ID, log_n);
+    void *tab;
+    bool created;
+    ZKB_TRY(ctx_table(ctx, key, sizeof(F) * half, &tab, &created));
+    if (created) ZKB_TRY(fill_powtab<P>(ctx, ntt_omega<F, P>(log_n, true), F::one(), 0, 0, half, tab, st));
+    F a;
+    memcpy(a.l, alpha, sizeof(a.l));
+    a = a.to_mont();
+    uint64_t blocks = (half + 255) / 256;
+    fold_kernel<P><<<(unsigned)blocks, 256, 0, st>>>(half, (const F *)f, (const F *)tab, a, (F *)out);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+namespace {
+struct Staged {  // host<->device staging for ZKB_MEM_HOST callers
+    zkb_ctx *ctx;
+    cudaStream_t st;
+    int mem;
+    Staged(zkb_ctx *c, cudaStream_t s, int m) : ctx(c), st(s), mem(m) {}
+    int in(const char *role, const void *src, size_t bytes, const void **dev) {
+        if (mem == ZKB_MEM_DEVICE || !src) { *dev = src; return ZKB_OK; }
+        void *d;
+        ZKB_TRY(ctx_scratch(ctx, role, bytes, &d));
+        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+        *dev = d;
+        return ZKB_OK;
+    }
+    int out_buf(const char *role, void *dst, size_t bytes, void **dev) {
+        if (mem == ZKB_MEM_DEVICE) { *dev = dst; return ZKB_OK; }
+        return ctx_scratch(ctx, role, bytes, dev);
+    }
+    int out(void *dst, const void *dev, size_t bytes) {
+        if (mem == ZKB_MEM_DEVICE) return ZKB_OK;
+        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        return ZKB_OK;
+    }
+};
+bool is_ntt_field(int f) { return f >= ZKB_FIELD_BLS12_381_FR && f <= ZKB_FIELD_PALLAS_FQ; }
+}  // namespace
+
+extern "C" {
+
+int zkb_ntt(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *in, void *out, int inverse,
+            const uint32_t *coset_shift, int mem, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!is_ntt_field(field) || log_n < 0 || (batch && (!in || !out)))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_ntt: bad field/log_n/pointers");
+    if (log_n > zkb_field_two_adicity(field)) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n exceeds the two-adicity");
+    if (batch == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = ((size_t)batch << log_n) * 32;
+    Staged sg(ctx, st, mem);
+    const void *din;
+    void *dout;
+    ZKB_TRY(sg.in("io_in", in, bytes, &din));
+    ZKB_TRY(sg.out_buf("io_in", out, bytes, &dout));   // in place on the staging buffer
+    ZKB_TRY(ntt_device(ctx, field, log_n, batch, din, dout, inverse, coset_shift, 1ull << log_n, 1ull << log_n, st));
+    return sg.out(out, dout, bytes);
+}
+
+int zkb_lde(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *in, void *out, int mem,
+            void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!is_ntt_field(field) || log_n_in < 1 || log_n_out < log_n_in || (batch && (!in || !out)))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_lde: need 1 <= log_n_in <= log_n_out");
+    if (log_n_out > zkb_field_two_adicity(field)) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n_out exceeds the two-adicity");
+    if (batch == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t ib = ((size_t)batch << log_n_in) * 32, ob = ((size_t)batch << log_n_out) * 32;
+    Staged sg(ctx, st, mem);
+    const void *din;
+    void *dout;
+    ZKB_TRY(sg.in("io_in", in, ib, &din));
+    ZKB_TRY(sg.out_buf("io_out", out, ob, &dout));
+    ZKB_TRY(lde_device(ctx, field, log_n_in, log_n_out, batch, din, dout, st));
+    return sg.out(out, dout, ob);
+}
+
+int zkb_vec(zkb_ctx *ctx, int field, int op, uint64_t n, const void *a, const void *b, const void *c,
+            const uint32_t *scalar, void *out, int mem, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!is_ntt_field(field) || op < 0 || op > ZKB_VEC_MUL_SUB_SCALE || (n && (!a || !b || !out)))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_vec: bad arguments");
+    if (n == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = (size_t)n * 32;
+    Staged sg(ctx, st, mem);
+    const void *da, *db, *dc;
+    void *dout;
+    ZKB_TRY(sg.in("vec_a", a, bytes, &da));
+    ZKB_TRY(sg.in("vec_b", b, bytes, &db));
+    ZKB_TRY(sg.in("vec_c", c, bytes, &dc));
+    ZKB_TRY(sg.out_buf("vec_a", out, bytes, &dout));
+    int s;
+    switch (field) {
+        case ZKB_FIELD_BLS12_381_FR: s = vec_t<params::Bls12381Fr>(ctx, op, n, da, db, dc, scalar, dout, st); break;
+        case ZKB_FIELD_BN254_FR: s = vec_t<params::Bn254Fr>(ctx, op, n, da, db, dc, scalar, dout, st); break;
+        case ZKB_FIELD_PALLAS_FP: s = vec_t<params::PallasFp>(ctx, op, n, da, db, dc, scalar, dout, st); break;
+        default: s = vec_t<params::PallasFq>(ctx, op, n, da, db, dc, scalar, dout, st); break;
+    }
+    ZKB_TRY(s);
+    return sg.out(out, dout, bytes);
+}
+
+int zkb_fri_fold(zkb_ctx *ctx, int field, int log_n, const void *f, const uint32_t *alpha, void *out, int mem,
+                 void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!is_ntt_field(field) || !f || !alpha || !out || log_n < 1)
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_fri_fold: bad arguments");
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t ib = ((size_t)1 << log_n) * 32, ob = ib / 2;
+    Staged sg(ctx, st, mem);
+    const void *df;
+    void *dout;
+    ZKB_TRY(sg.in("io_in", f, ib, &df));
+    ZKB_TRY(sg.out_buf("io_out", out, ob, &dout));
+    int s;
+    switch (field) {
+        case ZKB_FIELD_BLS12_381_FR: s = fold_t<params::Bls12381Fr>(ctx, log_n, df, alpha, dout, st); break;
+        case ZKB_FIELD_BN254_FR: s = fold_t<params::Bn254Fr>(ctx, log_n, df, alpha, dout, st); break;
+        case ZKB_FIELD_PALLAS_FP: s = fold_t<params::PallasFp>(ctx, log_n, df, alpha, dout, st); break;
+        default: s = fold_t<params::PallasFq>(ctx, log_n, df, alpha, dout, st); break;
+    }
+    ZKB_TRY(s);
+    return sg.out(out, dout, ob);
+}
+
+}  // extern "C"

@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define ZKB_HD __host__ __device__ __forceinline__
 #define ZKB_D __device__ __forceinline__
+#define ZKB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define ZKB_HD inline
 #define ZKB_D inline
+#define ZKB_HD_NOINLINE inline
 #endif
 
 namespace zkb {

@@ -1,0 +1,172 @@
+/* zkb200.h - C ABI of libzkb200.so: B200-native (sm_100a) NTT/LDE/FRI-commit and MSM kernels that
+ * sit behind the call sites crypto3-zk uses for its two data-parallel proving hot paths.
+ *
+ * The reference (NilFoundation/crypto3-zk, header-only C++) has no FFI/plugin layer: it reaches these
+ * operations through C++ template entities of un-vendored sibling libraries.  Each entry point below
+ * names the reference call site (file:line under /root/reference/include/nil/crypto3/) it serves and
+ * the upstream entity it replaces; the C++ host templates in crypto3_zk_b200/host/ re-create those
+ * entities on top of this ABI.
+ *
+ * Conventions
+ *   - every function returns a zkb_status; nothing throws across the ABI;
+ *   - field elements: canonical (non-Montgomery) integers < p as little-endian uint32 limbs,
+ *     8 limbs (32 B) for the 254/255-bit fields, 12 limbs (48 B) for BLS12-381 Fq;
+ *   - G1 points: affine (x || y), canonical limbs; the all-zero encoding is the point at infinity;
+ *   - `mem` says where caller buffers live (ZKB_MEM_HOST / ZKB_MEM_DEVICE); host buffers are copied
+ *     with cudaMemcpyAsync on the given stream (pin them for full PCIe rate);
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  Calls are stream-ordered;
+ *     functions that return a result to host memory synchronise the stream before returning;
+ *   - a context owns per-device caches (twiddle tables, scratch) and is not thread-safe: use one
+ *     context per thread/GPU, like the reference's lazily cached evaluation_domain objects.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns ZKB_ERR_NO_DEVICE.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ZKB_OK = 0,
+    ZKB_ERR_INVALID_ARGUMENT = 1, /* maps to std::invalid_argument in the host templates */
+    ZKB_ERR_DOMAIN_TOO_LARGE = 2, /* 2^log_n exceeds the field's two-adicity */
+    ZKB_ERR_CUDA = 3,             /* maps to std::runtime_error */
+    ZKB_ERR_OUT_OF_MEMORY = 4,
+    ZKB_ERR_NO_DEVICE = 5,
+    ZKB_ERR_UNSUPPORTED = 6
+} zkb_status;
+
+/* arithmetic_params<F> of the fields on the hot path (ids shared with crypto3_zk_b200/fields.py) */
+typedef enum {
+    ZKB_FIELD_BLS12_381_FR = 0,
+    ZKB_FIELD_BN254_FR = 1,
+    ZKB_FIELD_PALLAS_FP = 2, /* Pallas base field (= Vesta scalar field) */
+    ZKB_FIELD_PALLAS_FQ = 3, /* Pallas scalar field */
+    ZKB_FIELD_BLS12_381_FQ = 4, /* coordinate field, no NTT */
+    ZKB_FIELD_BN254_FQ = 5      /* coordinate field, no NTT */
+} zkb_field;
+
+typedef enum { ZKB_CURVE_BLS12_381_G1 = 0, ZKB_CURVE_BN254_G1 = 1, ZKB_CURVE_PALLAS = 2 } zkb_curve;
+
+typedef enum { ZKB_HASH_KECCAK_256 = 0, ZKB_HASH_SHA2_256 = 1, ZKB_HASH_KECCAK_512 = 2 } zkb_hash;
+
+typedef enum { ZKB_MEM_HOST = 0, ZKB_MEM_DEVICE = 1 } zkb_mem;
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_msm_bases zkb_msm_bases;
+typedef struct zkb_merkle_tree zkb_merkle_tree;
+
+/* ---- library / context ------------------------------------------------------------------- */
+const char *zkb_version(void);
+const char *zkb_status_string(int status);
+int zkb_device_count(void);
+int zkb_ctx_create(int device, zkb_ctx **out);
+void zkb_ctx_destroy(zkb_ctx *ctx);
+const char *zkb_ctx_last_error(const zkb_ctx *ctx);
+/* upper bound for internal scratch (bytes; default 6 GiB): batches are processed in chunks */
+int zkb_ctx_set_scratch_limit(zkb_ctx *ctx, uint64_t bytes);
+/* drops cached twiddle tables and scratch */
+int zkb_ctx_release_caches(zkb_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py reports the delta) */
+uint64_t zkb_ctx_kernel_launches(const zkb_ctx *ctx);
+
+/* ---- field descriptors (host only, no device needed) --------------------------------------- */
+int zkb_field_limbs(int field);        /* uint32 limbs per element, 0 if unknown */
+int zkb_field_two_adicity(int field);
+/* writes arithmetic_params<F>::multiplicative_generator (canonical limbs) */
+int zkb_field_generator(int field, uint32_t *out);
+/* math::unity_root<F>(2^log_n): the omega of make_evaluation_domain<F>(2^log_n) (canonical limbs).
+ * Serves evaluation_domain::get_domain_element (basic_fri.hpp:783, fold_polynomial.hpp:83). */
+int zkb_field_unity_root(int field, int log_n, uint32_t *out);
+
+/* ---- NTT: math::evaluation_domain<F>::fft / inverse_fft + math::multiply_by_coset ------------- */
+/* Replaces basic_radix2_domain<F>::fft / inverse_fft as called from
+ *   zk/snark/reductions/r1cs_to_qap.hpp:250,252,270,276,293,299,310
+ *   zk/commitments/detail/polynomial/basic_fri.hpp:453 (through polynomial_dfs::resize)
+ *   zk/snark/arithmetization/plonk/detail/column_polynomial.hpp:53
+ * `batch` independent vectors of 2^log_n elements, contiguous ([batch][2^log_n]); natural order in and
+ * out; out may equal in.  inverse != 0: inverse transform including the 1/n factor.
+ * coset_shift (host pointer, canonical limbs, or NULL):
+ *   forward: a[i] *= g^i first   == multiply_by_coset(a, g); fft(a)       (r1cs_to_qap.hpp:266-270)
+ *   inverse: a[i] *= g^-i after  == inverse_fft(a); multiply_by_coset(a, g^-1) (r1cs_to_qap.hpp:310-315)
+ */
+int zkb_ntt(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *in, void *out, int inverse,
+            const uint32_t *coset_shift, int mem, void *stream);
+
+/* ---- LDE: math::polynomial_dfs<V>::resize(2^log_n_out, nullptr, D) ---------------------------- */
+/* = inverse_fft on the 2^log_n_in subgroup, zero-pad, fft on the 2^log_n_out subgroup
+ * (basic_fri.hpp:369-371,451-455; gates_argument.hpp:120).  in: [batch][2^log_n_in],
+ * out: [batch][2^log_n_out]; log_n_out >= log_n_in >= 1. */
+int zkb_lde(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *in, void *out,
+            int mem, void *stream);
+
+/* ---- pointwise helpers of the QAP witness map (r1cs_to_qap.hpp:256-262,280-285,301-321) -------- */
+typedef enum {
+    ZKB_VEC_MUL = 0,      /* out[i] = a[i] * b[i]                       (:283-285) */
+    ZKB_VEC_SUB = 1,      /* out[i] = a[i] - b[i]                       (:304-306) */
+    ZKB_VEC_ADD = 2,      /* out[i] = a[i] + b[i]                       (:319-321) */
+    ZKB_VEC_MUL_SUB_SCALE = 3 /* out[i] = (a[i]*b[i] - c[i]) * s  (s = 1/Z(g): divide_by_z_on_coset, :283-308) */
+} zkb_vec_op;
+int zkb_vec(zkb_ctx *ctx, int field, int op, uint64_t n, const void *a, const void *b, const void *c,
+            const uint32_t *scalar, void *out, int mem, void *stream);
+
+/* ---- FRI fold: commitments::detail::fold_polynomial (dfs form) -------------------------------- */
+/* zk/commitments/detail/polynomial/fold_polynomial.hpp:68-93:
+ * out[i] = 1/2 * ((1 + alpha w^-i) f[i] + (1 - alpha w^-i) f[i + n/2]),  i < n/2, n = 2^log_n,
+ * w = unity_root(2^log_n).  alpha: host pointer, canonical limbs. */
+int zkb_fri_fold(zkb_ctx *ctx, int field, int log_n, const void *f, const uint32_t *alpha, void *out, int mem,
+                 void *stream);
+
+/* ---- LPC commit: zk::algorithms::precommit<FRI>(container<polynomial_dfs>, D, fri_step) -------- */
+/* zk/commitments/detail/polynomial/basic_fri.hpp:445-496 + lpc.hpp:101-106.
+ * polys: [batch][2^log_n_in] evaluations; every polynomial is resized to |D| = 2^log_n_out, leaves are
+ * packed as in :466-492 (big-endian 32-byte elements, polynomial-major inside a leaf) and hashed into a
+ * binary Merkle tree (containers::make_merkle_tree<Hash,2>).  The tree stays on the device behind
+ * `tree_out` (may be NULL to discard); root_out (host, digest bytes) receives lpc::commit's result. */
+int zkb_lpc_commit(zkb_ctx *ctx, int field, int hash, int log_n_in, int log_n_out, int fri_step, uint32_t batch,
+                   const void *polys, int mem, uint8_t *root_out, zkb_merkle_tree **tree_out, void *stream);
+/* Merkle tree only, over already extended evaluations [batch][2^log_n] (basic_fri.hpp:732 path) */
+int zkb_merkle_commit(zkb_ctx *ctx, int field, int hash, int log_n, int fri_step, uint32_t batch,
+                      const void *evals, int mem, uint8_t *root_out, zkb_merkle_tree **tree_out, void *stream);
+int zkb_merkle_digest_bytes(int hash);
+uint64_t zkb_merkle_leaves(const zkb_merkle_tree *tree);
+/* authentication path of leaf `index`: `depth` sibling digests, leaf level first
+ * (containers::merkle_proof<Hash,2>(tree, index), basic_fri.hpp:526-531) */
+int zkb_merkle_path(zkb_ctx *ctx, const zkb_merkle_tree *tree, uint64_t index, uint8_t *path_out);
+void zkb_merkle_free(zkb_merkle_tree *tree);
+
+/* ---- MSM: algebra::multiexp<Method> / multiexp_with_mixed_addition<Method> --------------------- */
+/* Call sites: zk/commitments/polynomial/kzg.hpp:146,414,433 ; kzg_v2.hpp:215 ;
+ * zk/snark/systems/ppzksnark/r1cs_gg_ppzksnark/prover.hpp:108-139 ;
+ * zk/commitments/polynomial/knowledge_commitment_multiexp.hpp:107.
+ * Bases are uploaded once (an SRS / proving-key query vector is long-lived) ... */
+int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, int mem, void *stream,
+                         zkb_msm_bases **out);
+void zkb_msm_bases_free(zkb_msm_bases *bases);
+uint64_t zkb_msm_bases_size(const zkb_msm_bases *bases);
+/* result = sum_{i<n} scalars[i] * bases[offset+i]; scalars canonical limbs of the curve's scalar field;
+ * result_affine: host buffer, (x||y) canonical limbs, all-zero for infinity.  Zero scalars are skipped and
+ * unit scalars cost one mixed addition, so multiexp and multiexp_with_mixed_addition map to the same call. */
+int zkb_msm(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
+            uint32_t *result_affine, void *stream);
+/* same, but leaves the result (XYZZ, Montgomery form, 4 coordinates) on the device without synchronising;
+ * zkb_msm_combine adds `count` such partial results (e.g. one per GPU) on the host into an affine point */
+int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars,
+                    int mem, uint32_t *partial_xyzz_host, void *stream);
+int zkb_msm_combine(int curve, uint32_t count, const uint32_t *partials_xyzz, uint32_t *result_affine);
+/* one-shot convenience (uploads bases every call) */
+int zkb_msm_g1(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, const void *scalars, int mem,
+               uint32_t *result_affine, void *stream);
+
+/* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ------------------ */
+/* runs `iters` dependent Montgomery multiplications per thread on `threads` threads; returns field-mul/s */
+int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threads, uint32_t iters, double *muls_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */
