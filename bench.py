@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark (contract in the task statement).
+
+Step  = one batched LDE (polynomial_dfs::resize as in LPC commit, basic_fri.hpp:451-455) of
+        BASELINE.json configs[1]: 64 Pallas-Fq polynomials, 2^20 -> 2^23 (blow-up 8), per GPU
+        (weak scaling: every rank owns its own 64 polynomials; no data-path collective).
+value = extended field elements produced per second, inputs resident in HBM.
+e2e   = the same metric through the C-ABI call zkb_lde with HOST (pinned) buffers: H2D of the 2 GiB
+        input and D2H of the 16 GiB result inside the timed region.
+extra = the other two parts of BASELINE.json's metric measured in the same run at N=1:
+        coset NTT 2^24 BLS12-381 Fr (elem/s), G1 MSM 2^20 BLS12-381 (ms), LPC commit of config #2 (ms),
+        each with its roofline fraction and CPU baseline.
+--impl reference : the reference's CPU algorithm (the oracle port, all host threads) on the same config,
+        each step a bounded sample (a few whole polynomials), same metric/unit.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched coset-NTT/LDE throughput, Fr elements/s (BASELINE: G1 MSM 2^20 BLS12-381 ms; coset NTT 2^24 Fr elem/s; LPC commit ms - see extra)"
+UNIT = "elem/s"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def rand_elems(torch, shape, seed, device):
+    """Synthetic canonical field elements on the device: uniform 252-bit integers (< every modulus)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randint(-2**31, 2**31 - 1, shape, dtype=torch.int32, device=device, generator=g)
+    x[..., 7] &= 0x0FFFFFFF
+    return x
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    import numpy as np
+    from oracle import cref
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = cref.threads_available()
+    sample_polys = max(1, min(threads, 32, args.batch))
+    rng = np.random.Generator(np.random.PCG64(0))
+    a = rng.integers(0, 1 << 32, size=(sample_polys, 1 << args.log_in, 8), dtype=np.uint64).astype(np.uint32)
+    a[..., 7] &= 0x0FFFFFFF
+    times = []
+    for it in range(args.warmup + args.steps):
+        _, t = cref.lde(3, a, args.log_in, args.log_out, threads=threads)
+        if it >= args.warmup:
+            times.append(t)
+    tot = sum(times)
+    value = sample_polys * (1 << args.log_out) * len(times) / tot
+    sample = "%d of %d polynomials per step (whole 2^%d->2^%d LDEs, one per thread)" % (sample_polys, args.batch, args.log_in, args.log_out)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times) * args.batch / sample_polys, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit prime field, exact)", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be compiled here (Boost + un-vendored crypto3 libs): timed code is oracle/c, a C port of its CPU algorithm; ms_per_step extrapolated from the sample to the full batch",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "BASELINE configs[1]: batched LDE (iNTT 2^%d, zero-pad, NTT 2^%d) of %d Pallas-Fq polynomials per GPU, blow-up %d, as in LPC commit"
+            % (args.log_in, args.log_out, args.batch, 1 << (args.log_out - args.log_in)),
+            "field": "pallas_fq", "polys_per_gpu": args.batch, "log_n_in": args.log_in, "log_n_out": args.log_out,
+            "sharding": "by polynomial, %d GPU(s), no collective" % n_gpus,
+            "l2": "inputs (%.1f GiB) and outputs (%.1f GiB) exceed the 126 MB L2; no explicit flush"
+                  % (args.batch * (32 << args.log_in) / 2**30, args.batch * (32 << args.log_out) / 2**30)}
+
+
+# ------------------------------------------------------------------------------------------ extras (N=1)
+def time_cuda(torch, fn, iters, warmup=1):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters   # ms
+
+
+def extras(args, torch, ctx, dev, hbm_peak):
+    import numpy as np
+    from crypto3_zk_b200 import capi
+    from crypto3_zk_b200.fields import CURVE_BY_NAME, FIELD_BY_NAME
+    ex = {}
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cref
+        cpu = cref
+    threads = cpu.threads_available() if cpu else 0
+    # ---- integer-pipe peak (field-mul/s), the MSM/NTT compute roofline denominator
+    peak_fr = ctx.bench_field_mul("bls12_381_fr", 148 * 8, 256, 2048)
+    peak_fq = ctx.bench_field_mul("bls12_381_fq", 148 * 8, 256, 1024)
+    ex["int_pipe_peak"] = {"fr8_mul_per_s": peak_fr, "fq12_mul_per_s": peak_fq,
+                           "how": "register-resident dependent Montgomery products, 4 chains/thread, 148*8 CTAs x 256 thr"}
+    # ---- coset NTT 2^24, BLS12-381 Fr
+    log_n = args.ntt_log
+    x = rand_elems(torch, (1, 1 << log_n, 8), 11, dev)
+    g = FIELD_BY_NAME["bls12_381_fr"].generator
+    ms = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n, coset_shift=g), 5, warmup=2)
+    ms_plain = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n), 5, warmup=2)
+    n = 1 << log_n
+    alg = 2 * n * 32
+    muls = n * (log_n / 2.0 + 2)      # butterflies + 2 inter-pass twiddles + coset scale (approx.)
+    ex["coset_ntt_2p%d_bls12_381_fr" % log_n] = {
+        "elem_per_s": n / (ms * 1e-3), "ms": ms, "ms_without_coset": ms_plain,
+        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg},
+        "int_pipe": {"field_mul_per_s": muls / (ms * 1e-3), "frac_of_peak": muls / (ms * 1e-3) / peak_fr}}
+    if cpu:
+        ls = min(log_n, 22)
+        a = np.random.Generator(np.random.PCG64(1)).integers(0, 1 << 32, size=(1, 1 << ls, 8), dtype=np.uint64).astype(np.uint32)
+        a[..., 7] &= 0x0FFFFFFF
+        t = cpu.ntt(0, a, ls, shift=g, threads=1)
+        ex["coset_ntt_2p%d_bls12_381_fr" % log_n]["cpu_baseline"] = {
+            "value": (1 << ls) / t, "unit": "elem/s", "cores": 1, "kind": "port", "sample": "one 2^%d coset FFT, 1 thread (a single transform is serial in the reference)" % ls}
+    del x
+    # ---- G1 MSM 2^20, BLS12-381
+    log_m = args.msm_log
+    nm = 1 << log_m
+    C = CURVE_BY_NAME["bls12_381_g1"]
+    gen = np.array([[(C.gen_x >> (32 * i)) & 0xFFFFFFFF for i in range(12)], [(C.gen_y >> (32 * i)) & 0xFFFFFFFF for i in range(12)]],
+                   dtype=np.uint32).reshape(1, 2, 12)
+    gb = ctx.msm_bases("bls12_381_g1", gen)
+    rng = np.random.Generator(np.random.PCG64(7))
+    m = 1024
+    nbt = (nm + m - 1) // m
+    ks = rng.integers(0, 1 << 32, size=(m + nbt, 8), dtype=np.uint64).astype(np.uint32)
+    ks[:, 7] &= 0x0FFFFFFF
+    tabs = np.zeros((m + nbt, 2, 12), dtype=np.uint32)
+    for i in range(m + nbt):          # k_i * G through the product's own MSM entry point
+        pt = ctx.multiexp(gb, ks[i:i + 1])
+        tabs[i, 0] = [(pt[0] >> (32 * k)) & 0xFFFFFFFF for k in range(12)]
+        tabs[i, 1] = [(pt[1] >> (32 * k)) & 0xFFFFFFFF for k in range(12)]
+    pts = ctx.grid_points("bls12_381_g1", nm, tabs[:m], tabs[m:])
+    bases = ctx.msm_bases("bls12_381_g1", pts)
+    sc = rand_elems(torch, (nm, 8), 13, dev)
+    msm_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 5, warmup=2)
+    sc_host = sc.cpu().numpy().view(np.uint32)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.multiexp(bases, sc_host)
+    msm_e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+    c = max(2, min(20, log_m - 4))
+    W = (255 + 1 + c - 1) // c
+    fq_mults = nm * W * 10 + W * (1 << (c - 1)) * 3 * 14 + 255 * 8
+    ex["msm_g1_2p%d_bls12_381" % log_m] = {
+        "ms": msm_ms, "e2e_ms_host_scalars": msm_e2e_ms, "window_bits": c, "windows": W,
+        "work_model_fq_mults": fq_mults,
+        "int_pipe": {"fq_mul_per_s": fq_mults / (msm_ms * 1e-3), "peak_fq_mul_per_s": peak_fq,
+                     "frac_of_peak": fq_mults / (msm_ms * 1e-3) / peak_fq},
+        "hbm_traffic_model_bytes": nm * (96 + 32)}
+    if cpu:
+        ns = min(nm, 1 << 16)
+        ph = pts[:ns].cpu().numpy().view(np.uint32)
+        _, t = cpu.msm(0, ph, sc_host[:ns], threads=threads)
+        ex["msm_g1_2p%d_bls12_381" % log_m]["cpu_baseline"] = {
+            "value": t * 1e3 * nm / ns, "unit": "ms (extrapolated linearly from the sample to 2^%d)" % log_m, "cores": threads,
+            "kind": "port", "sample": "2^%d of the 2^%d points, BDLO12 bucket MSM, chunks = threads" % (ns.bit_length() - 1, log_m)}
+    bases.free()
+    del pts, sc
+    return ex
+
+
+def lpc_extra(args, torch, ctx, x, hbm_peak):
+    from crypto3_zk_b200 import capi
+    res = {}
+    for name, hid in (("keccak256", capi.HASH_KECCAK_256), ("sha256", capi.HASH_SHA2_256)):
+        ms = time_cuda(torch, lambda: ctx.lpc_commit("pallas_fq", hid, x, args.log_in, args.log_out, 1), 2, warmup=1)
+        leaf_bytes = args.batch * (32 << args.log_out)
+        res[name] = {"ms": ms, "leaf_bytes_hashed": leaf_bytes, "hash_GBps_incl_lde": leaf_bytes / (ms * 1e-3) / 1e9}
+    return res
+
+
+# ------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--log-in", type=int, default=20)
+    ap.add_argument("--log-out", type=int, default=23)
+    ap.add_argument("--ntt-log", type=int, default=24)
+    ap.add_argument("--msm-log", type=int, default=20)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from crypto3_zk_b200 import Context, build
+    if rank == 0:
+        build.build()
+    if dist:
+        dist.barrier()
+    ctx = Context(local)
+    hbm_peak, peak_src = peaks()
+    n_in, n_out = 1 << args.log_in, 1 << args.log_out
+
+    x = rand_elems(torch, (args.batch, n_in, 8), 1000 + rank, dev)
+    y = torch.empty((args.batch, n_out, 8), dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.lde("pallas_fq", x, args.log_in, args.log_out, out=y)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.kernel_launches()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - l0
+    if dist:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms_total / args.steps
+    value = world * args.batch * n_out / (ms_per_step * 1e-3)
+    # sanity of the timed output: evaluations on the small subgroup reappear at stride 2^e
+    ok = bool(torch.equal(y[:, ::(1 << (args.log_out - args.log_in)), :], x))
+    assert ok, "LDE output failed the subgroup-restriction check"
+
+    # ---- end to end through the C ABI with host buffers (pinned): H2D + LDE + D2H per step
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((args.batch, n_in, 8), dtype=torch.int32, pin_memory=True)
+        hy = torch.empty((args.batch, n_out, 8), dtype=torch.int32, pin_memory=True)
+        hx.copy_(x)
+        hxn, hyn = hx.numpy().view(np.uint32), hy.numpy().view(np.uint32)
+        e2e_steps = max(1, min(args.steps, 3))
+        ctx.lde("pallas_fq", hxn, args.log_in, args.log_out, out=hyn)   # warm-up (allocates staging)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.lde("pallas_fq", hxn, args.log_in, args.log_out, out=hyn)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert torch.equal(hy[:2].to(dev), y[:2]), "e2e result differs from the device-resident result"
+        e2e = {"value": world * args.batch * n_out * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": args.batch * n_in * 32, "d2h_bytes_per_step": args.batch * n_out * 32,
+               "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps, "api": "zkb_lde(mem=ZKB_MEM_HOST), pinned host buffers"}
+        del hx, hy
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32x8 (255-bit prime field, exact integer arithmetic)", "data": "synthetic",
+        "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+    # ---- roofline of the dominant kernel (ntt_pass_kernel: every launch of the step is this kernel)
+    alg_bytes = args.batch * (n_in + n_out) * 32           # read the 2 GiB input once, write the 16 GiB result once
+    per_launch = alg_bytes / max(launches / args.steps, 1)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
+    except Exception:
+        pass
+    ach = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": traffic, "peak_source": peak_src, "kernel": "ntt_pass_kernel<PallasFq>",
+                        "algorithmic_bytes_per_launch": per_launch, "launches_per_step": launches / args.steps,
+                        "avg_launch_ms": ms_per_step / max(launches / args.steps, 1)}
+
+    if rank == 0 and world == 1:
+        if not args.no_cpu:
+            from oracle import cref
+            th = cref.threads_available()
+            sp = max(1, min(th, 32, args.batch))
+            a = x[:sp].cpu().numpy().view(np.uint32)
+            _, t = cref.lde(3, a, args.log_in, args.log_out, threads=th)
+            line["cpu_baseline"] = {"value": sp * n_out / t, "unit": UNIT, "cores": th, "kind": "port",
+                                    "sample": "%d of the %d polynomials (whole 2^%d->2^%d LDEs, one per thread), oracle/c port of the reference CPU algorithm" % (sp, args.batch, args.log_in, args.log_out)}
+        if not args.no_extras:
+            ex = {}
+            try:
+                ex["lpc_commit_config2"] = lpc_extra(args, torch, ctx, x, hbm_peak)
+            except Exception as e:   # extras must never lose the headline
+                ex["lpc_commit_config2"] = {"error": repr(e)}
+            del y
+            torch.cuda.empty_cache()
+            try:
+                ex.update(extras(args, torch, ctx, dev, hbm_peak))
+            except Exception as e:
+                ex["error"] = repr(e)
+            line["extra"] = ex
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

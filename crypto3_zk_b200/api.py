@@ -266,6 +266,21 @@ class Context:
                                               _stream_ptr(scalars, stream)), self._h)
         return res
 
+    def grid_points(self, curve, n, table_a, table_b, stream=None):
+        """Synthetic bases on the device: out[i] = table_a[i % m] + table_b[i // m] (torch int32 [n,2,cl])."""
+        import torch
+        c = _curve(curve)
+        cl = FIELD_BY_NAME[c.base_field].limbs32
+        ta = np.ascontiguousarray(table_a, dtype=np.uint32)
+        tb = np.ascontiguousarray(table_b, dtype=np.uint32)
+        m = ta.size // (2 * cl)
+        if tb.size // (2 * cl) < (n + m - 1) // m:
+            raise ValueError("table_b too small")
+        out = torch.empty((n, 2, cl), dtype=torch.int32, device="cuda:%d" % self.device)
+        capi.check(capi.lib().zkb_g1_grid_points(self._h, c.cid, n, m, ta.ctypes.data, tb.ctypes.data, out.data_ptr(),
+                                                 _stream_ptr(out, stream)), self._h)
+        return out
+
     def bench_field_mul(self, field, blocks, threads=256, iters=4096):
         r = ctypes.c_double()
         capi.check(capi.lib().zkb_bench_field_mul(self._h, _field_id(field), blocks, threads, iters, ctypes.byref(r)), self._h)

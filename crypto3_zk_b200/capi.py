@@ -19,7 +19,7 @@ SYMBOLS = [
     "zkb_ntt", "zkb_lde", "zkb_vec", "zkb_fri_fold", "zkb_lpc_commit", "zkb_merkle_commit",
     "zkb_merkle_digest_bytes", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm", "zkb_msm_partial",
-    "zkb_msm_combine", "zkb_msm_g1", "zkb_bench_field_mul",
+    "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
     L.zkb_msm_partial.argtypes = [vp, vp, u64, u64, vp, i, u32p, vp]
     L.zkb_msm_combine.argtypes = [i, u32, u32p, u32p]
     L.zkb_msm_g1.argtypes = [vp, i, u64, vp, vp, i, u32p, vp]
+    L.zkb_g1_grid_points.argtypes = [vp, i, u64, u32, vp, vp, vp, vp]
     L.zkb_bench_field_mul.argtypes = [vp, i, u32, u32, u32, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L

@@ -453,8 +453,58 @@ static int curve_coord_limbs(int curve) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ synthetic points
+// out[i] = A[i % m] + B[i / m] (affine, canonical): lets benchmarks and tests build millions of valid,
+// distinct curve points from two small host-made tables ("generate on GPU").
+template <class P>
+__global__ void __launch_bounds__(128) grid_points_kernel(uint64_t n, uint32_t m, const Affine<Fp<P>> *__restrict__ A,
+                                                          const Affine<Fp<P>> *__restrict__ Bt, Affine<Fp<P>> *__restrict__ out) {
+    typedef Fp<P> F;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> acc = XYZZ<F>::from_affine(A[i % m].to_mont());
+    acc.add_mixed(Bt[i / m].to_mont());
+    out[i] = acc.to_affine().from_mont();
+}
+
+template <class P>
+static int grid_points_t(zkb_ctx *ctx, uint64_t n, uint32_t m, const void *dA, const void *dB, void *dout, cudaStream_t st) {
+    typedef Affine<Fp<P>> A;
+    grid_points_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, m, (const A *)dA, (const A *)dB, (A *)dout);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" {
+
+int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const void *table_a, const void *table_b,
+                       void *out_device, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    int cl = curve_coord_limbs(curve);
+    if (!cl || !m || !table_a || !table_b || (n && !out_device))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_g1_grid_points: bad arguments");
+    if (n == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t pb = (size_t)2 * cl * 4;
+    uint64_t nb = (n + m - 1) / m;
+    void *dA, *dB;
+    ZKB_TRY(ctx_scratch(ctx, "grid_a", m * pb, &dA));
+    ZKB_TRY(ctx_scratch(ctx, "grid_b", nb * pb, &dB));
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(dA, table_a, m * pb, cudaMemcpyHostToDevice, st));
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(dB, table_b, nb * pb, cudaMemcpyHostToDevice, st));
+    int s;
+    switch (curve) {
+        case ZKB_CURVE_BLS12_381_G1: s = grid_points_t<params::Bls12381Fq>(ctx, n, m, dA, dB, out_device, st); break;
+        case ZKB_CURVE_BN254_G1: s = grid_points_t<params::Bn254Fq>(ctx, n, m, dA, dB, out_device, st); break;
+        default: s = grid_points_t<params::PallasFp>(ctx, n, m, dA, dB, out_device, st); break;
+    }
+    ZKB_TRY(s);
+    ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return ZKB_OK;
+}
 
 int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, int mem, void *stream,
                          zkb_msm_bases **out) {

@@ -162,6 +162,12 @@ int zkb_msm_combine(int curve, uint32_t count, const uint32_t *partials_xyzz, ui
 int zkb_msm_g1(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, const void *scalars, int mem,
                uint32_t *result_affine, void *stream);
 
+/* ---- synthetic inputs (benchmarks/tests; SURVEY.md 8(d) "generate on GPU") ------------------------ */
+/* out_device[i] = table_a[i % m] + table_b[i / m]: n valid affine points from two small host tables
+ * (m and ceil(n/m) affine points, canonical limbs).  out_device is DEVICE memory, n * 2 * coord limbs. */
+int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const void *table_a, const void *table_b,
+                       void *out_device, void *stream);
+
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ------------------ */
 /* runs `iters` dependent Montgomery multiplications per thread on `threads` threads; returns field-mul/s */
 int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threads, uint32_t iters, double *muls_per_s);
