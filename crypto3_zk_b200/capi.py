@@ -15,7 +15,7 @@ VEC_MUL, VEC_SUB, VEC_ADD, VEC_MUL_SUB_SCALE = 0, 1, 2, 3
 SYMBOLS = [
     "zkb_version", "zkb_status_string", "zkb_device_count", "zkb_ctx_create", "zkb_ctx_destroy",
     "zkb_ctx_last_error", "zkb_ctx_set_scratch_limit", "zkb_ctx_release_caches", "zkb_ctx_kernel_launches",
-    "zkb_field_limbs", "zkb_field_two_adicity", "zkb_field_generator", "zkb_field_unity_root",
+    "zkb_field_limbs", "zkb_field_two_adicity", "zkb_field_generator", "zkb_field_unity_root", "zkb_curve_generator",
     "zkb_ntt", "zkb_lde", "zkb_vec", "zkb_fri_fold", "zkb_lpc_commit", "zkb_merkle_commit",
     "zkb_merkle_digest_bytes", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm", "zkb_msm_partial",
@@ -64,6 +64,7 @@ def lib():
     L.zkb_field_two_adicity.argtypes = [i]
     L.zkb_field_generator.argtypes = [i, u32p]
     L.zkb_field_unity_root.argtypes = [i, i, u32p]
+    L.zkb_curve_generator.argtypes = [i, u32p]
     L.zkb_ntt.argtypes = [vp, i, i, u32, vp, vp, i, u32p, i, vp]
     L.zkb_lde.argtypes = [vp, i, i, i, u32, vp, vp, i, vp]
     L.zkb_vec.argtypes = [vp, i, i, u64, vp, vp, vp, u32p, vp, i, vp]

@@ -66,3 +66,18 @@ extern "C" int zkb_msm_combine(int curve, uint32_t count, const uint32_t *partia
     }
     return ZKB_ERR_INVALID_ARGUMENT;
 }
+
+template <class G, int N>
+static void write_gen(uint32_t *out) {
+    for (int i = 0; i < N; i++) { out[i] = G::x(i); out[N + i] = G::y(i); }
+}
+// curve_type::g1_type<>::value_type::one() of the reference (affine x || y, canonical limbs)
+extern "C" int zkb_curve_generator(int curve, uint32_t *out_affine) {
+    if (!out_affine) return ZKB_ERR_INVALID_ARGUMENT;
+    switch (curve) {
+        case ZKB_CURVE_BLS12_381_G1: write_gen<params::GenBls12381G1, 12>(out_affine); return ZKB_OK;
+        case ZKB_CURVE_BN254_G1: write_gen<params::GenBn254G1, 8>(out_affine); return ZKB_OK;
+        case ZKB_CURVE_PALLAS: write_gen<params::GenPallas, 8>(out_affine); return ZKB_OK;
+    }
+    return ZKB_ERR_INVALID_ARGUMENT;
+}

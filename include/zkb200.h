@@ -83,6 +83,9 @@ int zkb_field_generator(int field, uint32_t *out);
  * Serves evaluation_domain::get_domain_element (basic_fri.hpp:783, fold_polynomial.hpp:83). */
 int zkb_field_unity_root(int field, int log_n, uint32_t *out);
 
+/* curve_type::g1_type<>::value_type::one(): the generator (affine x || y, canonical limbs); host only */
+int zkb_curve_generator(int curve, uint32_t *out_affine);
+
 /* ---- NTT: math::evaluation_domain<F>::fft / inverse_fft + math::multiply_by_coset ------------- */
 /* Replaces basic_radix2_domain<F>::fft / inverse_fft as called from
  *   zk/snark/reductions/r1cs_to_qap.hpp:250,252,270,276,293,299,310

@@ -1,0 +1,168 @@
+// C++ host-template tests, written after the reference's own tests for the hot-path entities:
+//   test/commitment/kzg.cpp:75-101      (kzg_basic_test: commit == 3209 * G)
+//   test/commitment/fri.cpp:83-124      (domain set structure)
+//   test/commitment/fold_polynomial.cpp (fold identity, dfs form)
+// plus resize / coset round trips.  Needs a GPU (run by tests/test_cpp_host.py under -m gpu); with
+// argument "compile-only" it just proves the headers instantiate.  Prints one "ROOT <hex>" line that the
+// Python wrapper compares with the oracle's Merkle root for the same inputs.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "../../crypto3_zk_b200/host/zkb_crypto3.hpp"
+
+using namespace nil::crypto3;
+
+static int failures = 0;
+#define CHECK(cond)                                                          \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            failures++;                                                      \
+        }                                                                    \
+    } while (0)
+
+template <class Curve>
+static void kzg_basic_test() {
+    typedef typename Curve::template g1_type<> g1_type;
+    typedef typename Curve::scalar_field_type::value_type scalar_value_type;
+    typedef typename g1_type::value_type g1_value_type;
+    scalar_value_type alpha = 10u;
+    std::size_t n = 16;
+    // params_type(d, alpha): commitment_key[i] = alpha^i * G   (kzg.hpp:110-118)
+    std::vector<g1_value_type> gen = {g1_value_type::one()};
+    algebra::multiexp_bases<g1_type> G(gen.begin(), gen.end());
+    std::vector<g1_value_type> commitment_key(n);
+    scalar_value_type acc = scalar_value_type::one();
+    for (std::size_t i = 0; i < n; i++) {
+        std::vector<scalar_value_type> s = {acc};
+        commitment_key[i] = G.multiexp(0, s.begin(), s.end());
+        acc *= alpha;
+    }
+    CHECK(g1_value_type::one() == commitment_key[0]);
+    // f = {-1, 1, 2, 3}: commit == 3209 * G   (kzg.cpp:86,97)
+    std::vector<scalar_value_type> f = {-scalar_value_type(1u), 1u, 2u, 3u};
+    g1_value_type commit = algebra::multiexp<algebra::policies::multiexp_method_BDLO12>(
+        commitment_key.begin(), commitment_key.begin() + f.size(), f.begin(), f.end(), 1);
+    std::vector<scalar_value_type> k = {scalar_value_type(3209u)};
+    CHECK(G.multiexp(0, k.begin(), k.end()) == commit);
+    g1_value_type commit2 = algebra::multiexp_with_mixed_addition<algebra::policies::multiexp_method_BDLO12>(
+        commitment_key.begin(), commitment_key.begin() + f.size(), f.begin(), f.end(), 1);
+    CHECK(commit2 == commit);
+    // mismatching ranges are rejected
+    bool threw = false;
+    try {
+        algebra::multiexp<algebra::policies::multiexp_method_BDLO12>(commitment_key.begin(), commitment_key.begin() + 3, f.begin(), f.end(), 1);
+    } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+}
+
+template <class FieldType>
+static void domain_and_fold_test() {
+    typedef typename FieldType::value_type V;
+    // fri.cpp:122-123
+    auto D = math::calculate_domain_set<FieldType>(7, 3);
+    CHECK(D[1]->m == D[0]->m / 2);
+    CHECK(D[1]->get_domain_element(1) == D[0]->get_domain_element(1).squared());
+    // fft / inverse_fft round trip, zero padding of short inputs, size errors
+    std::size_t n = D[0]->m;
+    std::vector<V> a(n);
+    for (std::size_t i = 0; i < n; i++) a[i] = V(1000003u * (i + 1)) * V(i + 7).pow(5);
+    std::vector<V> b(a);
+    D[0]->fft(b);
+    V s = V::zero();   // b[0] = sum a[i]
+    for (auto &x : a) s += x;
+    CHECK(b[0] == s);
+    // b[1] = sum a[i] w^i
+    V w = D[0]->get_domain_element(1), wi = V::one(), e = V::zero();
+    for (std::size_t i = 0; i < n; i++) { e += a[i] * wi; wi *= w; }
+    CHECK(b[1] == e);
+    D[0]->inverse_fft(b);
+    CHECK(b == a);
+    std::vector<V> shortv(a.begin(), a.begin() + 5);
+    D[0]->fft(shortv);
+    CHECK(shortv.size() == n);
+    std::vector<V> longv(n + 1);
+    bool threw = false;
+    try { D[0]->fft(longv); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+    threw = false;
+    try { math::make_evaluation_domain<FieldType>(24); } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+    // coset: multiply_by_coset + fft == fused coset_fft; inverse undoes it (r1cs_to_qap.hpp:266-315)
+    V g = algebra::fields::arithmetic_params<FieldType>::multiplicative_generator_value();
+    std::vector<V> c1(a), c2(a);
+    math::multiply_by_coset(c1, g);
+    D[0]->fft(c1);
+    math::basic_radix2_domain<FieldType> dom(n);
+    dom.coset_fft(c2, g);
+    CHECK(c1 == c2);
+    dom.inverse_coset_fft(c2, g);
+    CHECK(c2 == a);
+    // polynomial_dfs: from_coefficients / coefficients / evaluate / resize
+    math::polynomial_dfs<V> p;
+    std::vector<V> coeffs(a.begin(), a.begin() + 32);
+    p.from_coefficients(coeffs);
+    CHECK(p.size() == 32);
+    CHECK(p.coefficients() == coeffs);
+    V x = V(123456789u), hv = V::zero();
+    for (std::size_t i = coeffs.size(); i-- > 0;) hv = hv * x + coeffs[i];
+    CHECK(p.evaluate(x) == hv);
+    math::polynomial_dfs<V> q = p;
+    q.resize(256);
+    CHECK(q.size() == 256);
+    for (std::size_t i = 0; i < 32; i++) CHECK(q[8 * i] == p[i]);
+    CHECK(q.evaluate(x) == hv);
+    // fold (fold_polynomial.cpp): dfs fold == coefficient fold evaluated on the squared domain
+    V alpha = V(987654321u);
+    auto d32 = math::make_evaluation_domain<FieldType>(32);
+    auto folded = zk::commitments::detail::fold_polynomial<FieldType>(p, alpha, d32);
+    std::vector<V> fc(16);
+    for (std::size_t i = 0; i < 16; i++) fc[i] = coeffs[2 * i] + alpha * coeffs[2 * i + 1];
+    math::polynomial_dfs<V> pf;
+    pf.from_coefficients(fc);
+    CHECK(folded.size() == 16);
+    for (std::size_t i = 0; i < 16; i++) CHECK(folded[i] == pf[i]);
+}
+
+static void precommit_root() {
+    typedef algebra::fields::pallas_base_field F;
+    typedef F::value_type V;
+    // 3 polynomials of size 16 with values (p+1)*1000 + i, committed on |D| = 64, fri_step = 2, keccak-256
+    std::vector<math::polynomial_dfs<V>> polys;
+    for (int p = 0; p < 3; p++) {
+        std::vector<V> v(16);
+        for (int i = 0; i < 16; i++) v[i] = V((std::uint64_t)(p + 1) * 1000 + i);
+        polys.emplace_back(15, v);
+    }
+    auto D = math::make_evaluation_domain<F>(64);
+    auto tree = zk::algorithms::precommit<F, ZKB_HASH_KECCAK_256>(polys, D, 2);
+    std::printf("ROOT ");
+    for (auto b : tree.root()) std::printf("%02x", b);
+    std::printf("\n");
+    CHECK(tree.leaves() == 16);
+    CHECK(tree.path(3).size() == 4);
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && !std::strcmp(argv[1], "compile-only")) {
+        std::printf("compiled\n");
+        return 0;
+    }
+    try {
+        kzg_basic_test<algebra::curves::bls12<381>>();
+        kzg_basic_test<algebra::curves::alt_bn128<254>>();
+        kzg_basic_test<algebra::curves::pallas>();
+        domain_and_fold_test<algebra::fields::bls12_fr<381>>();
+        domain_and_fold_test<algebra::fields::alt_bn128_fr<254>>();
+        domain_and_fold_test<algebra::fields::pallas_base_field>();
+        domain_and_fold_test<algebra::fields::pallas_scalar_field>();
+        precommit_root();
+    } catch (const std::exception &e) {
+        std::printf("EXCEPTION %s\n", e.what());
+        return 2;
+    }
+    std::printf(failures ? "FAILED %d checks\n" : "ALL OK\n", failures);
+    return failures ? 1 : 0;
+}
