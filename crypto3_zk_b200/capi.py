@@ -4,7 +4,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzkb200.so")
+# ZKB200_LIB selects another build of the same library (A/B experiments under profiles/); never a fallback
+LIB_PATH = os.environ.get("ZKB200_LIB") or os.path.join(HERE, "libzkb200.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_DOMAIN_TOO_LARGE, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(7)
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -134,79 +134,90 @@ struct Fp {
     ZKB_HD Fp dbl() const { return *this + *this; }
 
     // ------------------------------------------------------------------ Montgomery multiplication
+    // Operand scanning, one b-limb per row, with the running total split into two accumulators of
+    // 64-bit words: `lo` holds limb positions (k, k+1), (k+2, k+3), .. and `hi` positions (k+1, k+2), ..
+    // so every 32x32 partial product lands on one aligned word and each half-row is one carry chain of
+    // IMAD.WIDE.U32.X.  After a row the lowest limb is zero, the roles of the accumulators swap (that is
+    // the >> 32), and the surviving half of the dropped word is folded in with one 32-bit add whose
+    // carry starts the next chain.
    private:
-    // acc[j], acc[j+1] = a[j] * bi  for j = 0, 2, ..  (a points at the even- or odd-indexed limbs)
-    ZKB_HD static void mul_row(uint32_t *acc, const uint32_t *a, uint32_t bi) {
-#pragma unroll
-        for (int j = 0; j < N; j += 2) {
-            acc[j] = ptx::mul_lo(a[j], bi);
-            acc[j + 1] = ptx::mul_hi(a[j], bi);
+    static constexpr int H = N / 2;
+    ZKB_HD static uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+    ZKB_HD static uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+    ZKB_HD static constexpr bool is_pow2(uint32_t v) { return v > 1 && (v & (v - 1)) == 0; }
+    ZKB_HD static constexpr int log2u(uint32_t v) { return v <= 1 ? 0 : 1 + log2u(v >> 1); }
+
+    // acc[j] += p[OFF + 2j] * mi over one carry chain.  The modulus limbs are compile-time constants:
+    // limbs 0, 1, 2^32-1 and 2^s (Pallas/Vesta p = 2^254 + t, t < 2^126; BLS12-381 Fr p = ..ffffffff00000001)
+    // need no multiplier - their products are formed on the ALU pipe, which idles while an IMAD.WIDE
+    // occupies the fma pipe for four issue cycles.  That leaves 3 (Pallas) or 6 (BLS12-381 Fr) wide
+    // multiply-adds per row for the reduction instead of 8.
+    template <int OFF, int J>
+    ZKB_HD static void mad_row_mod_step(uint64_t *acc, uint32_t mi) {
+        if constexpr (J < H) {
+            constexpr uint32_t v = P::mod(OFF + 2 * J);
+            if constexpr (v == 0u || v == 1u || v == 0xffffffffu || is_pow2(v)) {
+                uint64_t t;
+                if constexpr (v == 0u) t = 0;
+                else if constexpr (v == 1u) t = ptx::pack64(mi, 0);
+                else if constexpr (v == 0xffffffffu) t = ptx::pack64(0u - mi, mi - (mi != 0u ? 1u : 0u));
+                else t = ptx::pack64(mi << log2u(v), mi >> (32 - log2u(v)));
+                acc[J] = J == 0 ? ptx::add_cc64(acc[J], t) : ptx::addc_cc64(acc[J], t);
+            } else {
+                acc[J] = J == 0 ? ptx::mad_wide_cc(mi, v, acc[J]) : ptx::madc_wide_cc(mi, v, acc[J]);
+            }
+            mad_row_mod_step<OFF, J + 1>(acc, mi);
         }
     }
-    // acc += {a[j] * bi}, one carry chain over the whole row; carry-out stays in CC
-    ZKB_HD static void mad_row(uint32_t *acc, const uint32_t *a, uint32_t bi) {
-        acc[0] = ptx::mad_lo_cc(a[0], bi, acc[0]);
-        acc[1] = ptx::madc_hi_cc(a[0], bi, acc[1]);
-#pragma unroll
-        for (int j = 2; j < N; j += 2) {
-            acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
-            acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
-        }
-    }
-    // same with the modulus as the multiplicand (compile-time constants -> immediates)
-    template <int OFF>
-    ZKB_HD static void mad_row_mod(uint32_t *acc, uint32_t mi) {
-        acc[0] = ptx::mad_lo_cc(P::mod(OFF), mi, acc[0]);
-        acc[1] = ptx::madc_hi_cc(P::mod(OFF), mi, acc[1]);
-#pragma unroll
-        for (int j = 2; j < N; j += 2) {
-            acc[j] = ptx::madc_lo_cc(P::mod(OFF + j), mi, acc[j]);
-            acc[j + 1] = ptx::madc_hi_cc(P::mod(OFF + j), mi, acc[j + 1]);
-        }
-    }
-    // acc = (acc >> 64) + {a[j] * bi}, continuing the carry chain already in CC
-    ZKB_HD static void mad_row_shift2(uint32_t *acc, const uint32_t *a, uint32_t bi) {
-#pragma unroll
-        for (int j = 0; j < N - 2; j += 2) {
-            acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j + 2]);
-            acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 3]);
-        }
-        acc[N - 2] = ptx::madc_lo_cc(a[N - 2], bi, 0);
-        acc[N - 1] = ptx::madc_hi(a[N - 2], bi, 0);
-    }
-    // One outer iteration: T += a*bi; T += m*p; (the >>32 is realised by swapping lo/hi roles)
-    // `lo` holds limb positions k, `hi` holds positions k+1.
-    ZKB_HD static void mad_redc(uint32_t *lo, uint32_t *hi, const uint32_t *a, uint32_t bi, bool first) {
+    // one row: T += a * bi; T += mi * p with mi chosen so that the lowest limb cancels
+    ZKB_HD static void mad_redc(uint64_t *lo, uint64_t *hi, const uint32_t *a, uint32_t bi, bool first) {
         if (first) {
-            mul_row(hi, a + 1, bi);
-            mul_row(lo, a, bi);
+#pragma unroll
+            for (int j = 0; j < H; j++) hi[j] = ptx::mul_wide(a[2 * j + 1], bi);
+#pragma unroll
+            for (int j = 0; j < H; j++) lo[j] = ptx::mul_wide(a[2 * j], bi);
         } else {
-            lo[0] = ptx::add_cc(lo[0], hi[1]);
-            mad_row_shift2(hi, a + 1, bi);
-            mad_row(lo, a, bi);
-            hi[N - 1] = ptx::addc(hi[N - 1], 0);
+            lo[0] = ptx::pack64(ptx::add_cc(lo32(lo[0]), hi32(hi[0])), hi32(lo[0]));
+#pragma unroll
+            for (int j = 0; j < H - 1; j++) hi[j] = ptx::madc_wide_cc(a[2 * j + 1], bi, hi[j + 1]);
+            hi[H - 1] = ptx::madc_wide(a[N - 1], bi, 0);
+            lo[0] = ptx::mad_wide_cc(a[0], bi, lo[0]);
+#pragma unroll
+            for (int j = 1; j < H; j++) lo[j] = ptx::madc_wide_cc(a[2 * j], bi, lo[j]);
+            hi[H - 1] = ptx::pack64(lo32(hi[H - 1]), ptx::addc(hi32(hi[H - 1]), 0));
         }
-        uint32_t mi = lo[0] * P::NINV;
-        mad_row_mod<1>(hi, mi);
-        mad_row_mod<0>(lo, mi);
-        hi[N - 1] = ptx::addc(hi[N - 1], 0);
+        uint32_t mi = lo32(lo[0]) * P::NINV;
+        mad_row_mod_step<1, 0>(hi, mi);
+        mad_row_mod_step<0, 0>(lo, mi);
+        hi[H - 1] = ptx::pack64(lo32(hi[H - 1]), ptx::addc(hi32(hi[H - 1]), 0));
     }
 
    public:
-    ZKB_HD friend Fp operator*(const Fp &a, const Fp &b) {
-        uint32_t even[N], odd[N];
+    // Translation units whose kernels chain dozens of multiplications per loop iteration (MSM bucket
+    // accumulation: ~10 per point) define ZKB_MUL_OUTLINE: one shared out-of-line copy of the body keeps
+    // the loop inside the instruction cache instead of streaming ~70 KB of unrolled code per iteration.
+#if defined(ZKB_MUL_OUTLINE) && defined(__CUDA_ARCH__)
+    __device__ __noinline__ static Fp mul_outlined(const Fp a, const Fp b) { return mul_inline(a, b); }
+    __device__ __forceinline__ friend Fp operator*(const Fp &a, const Fp &b) { return mul_outlined(a, b); }
+#else
+    ZKB_HD friend Fp operator*(const Fp &a, const Fp &b) { return mul_inline(a, b); }
+#endif
+    ZKB_HD static Fp mul_inline(const Fp &a, const Fp &b) {
+        uint64_t even[H], odd[H];
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
             mad_redc(even, odd, a.l, b.l[i], i == 0);
             mad_redc(odd, even, a.l, b.l[i + 1], false);
         }
-        // N is even, so the last row left T = odd + (even << 32) with odd[0] == 0:
+        // N is even, so the last row left T = odd + (even << 32) with the lowest limb of odd zero:
         // result = T >> 32 = even + (odd >> 32)
         Fp r;
-        r.l[0] = ptx::add_cc(even[0], odd[1]);
+        r.l[0] = ptx::add_cc(lo32(even[0]), hi32(odd[0]));
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(even[i], odd[i + 1]);
-        r.l[N - 1] = ptx::addc(even[N - 1], 0);
+        for (int i = 1; i < N - 1; i++)
+            r.l[i] = ptx::addc_cc((i & 1) ? hi32(even[i / 2]) : lo32(even[i / 2]),
+                                  (i & 1) ? lo32(odd[(i + 1) / 2]) : hi32(odd[(i + 1) / 2]));
+        r.l[N - 1] = ptx::addc(hi32(even[H - 1]), 0);
         return reduce_once(r);
     }
     ZKB_HD Fp sqr() const { return *this * *this; }

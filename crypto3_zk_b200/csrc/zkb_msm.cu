@@ -17,6 +17,9 @@
 //   6 combine     sum_w 2^(c w) S_w on the host (c W doublings; zkb_msm_host.cpp)
 #include <stdio.h>
 #include <string.h>
+#ifndef ZKB_MSM_MUL_INLINE
+#define ZKB_MUL_OUTLINE 1
+#endif
 #include "zkb_curve.cuh"
 #include "zkb_internal.h"
 
