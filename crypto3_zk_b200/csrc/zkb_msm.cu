@@ -11,10 +11,15 @@
 //                 Groth16 assignments put most points into one bucket - the reference pre-filters
 //                 them on the CPU, knowledge_commitment_multiexp.hpp:88-101)
 //   3 scatter     counting sort of (point index, sign) by bucket
-//   4 accumulate  one thread per task: XYZZ += affine point (mixed add, 8M+2S)
-//   5 reduce      per window S_w = sum_k (k+1) B_k via radix-32 digit sums of the bucket index
-//                 (every level is a flat, short-chain parallel sum; no serial running sum over 2^(c-1))
-//   6 combine     sum_w 2^(c w) S_w on the host (c W doublings; zkb_msm_host.cpp)
+//   4 order       tasks are ordered by length (counting sort over <= MSM_TASK_CAP lengths) so that the 32
+//                 tasks of a warp run the same number of additions (bucket sizes are Poisson distributed;
+//                 unsorted, a warp waits for its longest bucket: ~30 % of the lanes idle at 32 points/bucket)
+//   5 accumulate  one thread per task: XYZZ += affine point (mixed add, 8M+2S)
+//   6 reduce      per window S_w = sum_k (k+1) B_k by a radix-MSM_RED_L tree: every node turns L children
+//                 (A_j = plain sum, U_j = weighted sum relative to the child's start) into
+//                 A = sum A_j, U = sum U_j + span * sum j A_j  - short running sums at every level,
+//                 65536 threads at the leaves, no serial pass over the 2^(c-1) buckets of a window
+//   7 combine     sum_w 2^(c w) S_w on the host (c W doublings; zkb_msm_host.cpp)
 #include <stdio.h>
 #include <string.h>
 #ifndef ZKB_MSM_MUL_INLINE
@@ -80,11 +85,18 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint3
     }
 }
 
-// tasks per bucket from the bucket sizes
+// tasks per bucket from the bucket sizes; buckets that need more than one task are listed in `heavy`
 __global__ void __launch_bounds__(256) msm_ntasks_kernel(uint32_t nb, const uint32_t *__restrict__ counts,
-                                                         uint32_t *__restrict__ ntasks) {
+                                                         uint32_t *__restrict__ ntasks, uint32_t *__restrict__ n_heavy,
+                                                         uint32_t *__restrict__ heavy, uint32_t heavy_cap) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb) ntasks[b] = (counts[b] + MSM_TASK_CAP - 1) / MSM_TASK_CAP;
+    if (b >= nb) return;
+    uint32_t nt = (counts[b] + MSM_TASK_CAP - 1) / MSM_TASK_CAP;
+    ntasks[b] = nt;
+    if (nt > 1) {
+        uint32_t k = atomicAdd(n_heavy, 1u);
+        if (k < heavy_cap) heavy[k] = b;
+    }
 }
 
 // ---- exclusive scan over uint32 (three launches, 1024 items per block) --------------------------
@@ -209,12 +221,13 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F> *p) {
 
 template <class P>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ n_tasks, const MsmTask *__restrict__ tasks,
-                                                             const uint32_t *__restrict__ sorted,
+                                                             const uint32_t *__restrict__ perm, const uint32_t *__restrict__ sorted,
                                                              const Affine<Fp<P>> *__restrict__ points,
                                                              XYZZ<Fp<P>> *__restrict__ out) {
     typedef Fp<P> F;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *n_tasks) return;
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= *n_tasks) return;
+    const uint32_t t = perm[g];
     MsmTask task = tasks[t];
     XYZZ<F> acc = XYZZ<F>::infinity();
     for (uint32_t k = 0; k < task.len; k++) {
@@ -226,124 +239,155 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__r
     out[t] = acc;
 }
 
+// ------------------------------------------------------------------------------------ task order
+#define MSM_RED_LOG_L 3
+#define MSM_RED_L (1u << MSM_RED_LOG_L)
+
+// bins[MSM_TASK_CAP - len]++ (descending length order)
+__global__ void __launch_bounds__(256) msm_task_hist_kernel(const uint32_t *__restrict__ n_tasks, const MsmTask *__restrict__ tasks,
+                                                            uint32_t *__restrict__ bins) {
+    __shared__ uint32_t sh[MSM_TASK_CAP];
+    for (uint32_t k = threadIdx.x; k < MSM_TASK_CAP; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < *n_tasks) atomicAdd(&sh[MSM_TASK_CAP - tasks[t].len], 1u);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < MSM_TASK_CAP; k += blockDim.x)
+        if (sh[k]) atomicAdd(bins + k, sh[k]);
+}
+// single block: exclusive scan of the MSM_TASK_CAP bins into bin_off; clears the cursors
+__global__ void __launch_bounds__(MSM_TASK_CAP) msm_task_scan_kernel(const uint32_t *__restrict__ bins, uint32_t *__restrict__ bin_off,
+                                                                     uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t sh[MSM_TASK_CAP];
+    uint32_t v = bins[threadIdx.x];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < MSM_TASK_CAP; d <<= 1) {
+        uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    bin_off[threadIdx.x] = sh[threadIdx.x] - v;
+    cursor[threadIdx.x] = 0;
+}
+// perm[position in length order] = task id (one global atomic per block and non-empty bin)
+__global__ void __launch_bounds__(256) msm_task_permute_kernel(const uint32_t *__restrict__ n_tasks, const MsmTask *__restrict__ tasks,
+                                                               const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ cursor,
+                                                               uint32_t *__restrict__ perm) {
+    __shared__ uint32_t cnt[MSM_TASK_CAP], base[MSM_TASK_CAP];
+    for (uint32_t k = threadIdx.x; k < MSM_TASK_CAP; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bin = 0, rank = 0;
+    bool live = t < *n_tasks;
+    if (live) {
+        bin = MSM_TASK_CAP - tasks[t].len;
+        rank = atomicAdd(&cnt[bin], 1u);
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < MSM_TASK_CAP; k += blockDim.x)
+        if (cnt[k]) base[k] = atomicAdd(cursor + k, cnt[k]);
+    __syncthreads();
+    if (live) perm[bin_off[bin] + base[bin] + rank] = t;
+}
+
+// ------------------------------------------------------------------------------------ heavy buckets
+// A bucket with more than MSM_TASK_CAP points was accumulated as several tasks (the top window of a
+// 255-bit scalar has only a few significant bits, so its handful of buckets hold N/8 points each; 0/1-heavy
+// Groth16 assignments put almost everything into bucket 0 of window 0 - the reference filters those on the
+// CPU, knowledge_commitment_multiexp.hpp:88-101).  One block per such bucket adds its task results pairwise
+// in place (a tree over global memory), leaves the total in the bucket's first task and sets ntasks to 1.
+template <class P>
+__global__ void __launch_bounds__(256) msm_heavy_tree_kernel(const uint32_t *__restrict__ n_heavy, const uint32_t *__restrict__ heavy,
+                                                             uint32_t heavy_cap, const uint32_t *__restrict__ task_offsets,
+                                                             uint32_t *__restrict__ ntasks, XYZZ<Fp<P>> *__restrict__ tout) {
+    uint32_t nh = *n_heavy;
+    if (nh > heavy_cap) nh = heavy_cap;
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        const uint32_t b = heavy[h], t0 = task_offsets[b], nt = ntasks[b];
+        for (uint32_t s = 1; s < nt; s <<= 1) {
+            for (uint32_t i = threadIdx.x * 2 * s; i + s < nt; i += blockDim.x * 2 * s) {
+                XYZZ<Fp<P>> x = tout[t0 + i];
+                x.add(tout[t0 + i + s]);
+                tout[t0 + i] = x;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) ntasks[b] = 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------ reduce
-// Geometry of the radix-32 digit decomposition of the bucket index k in [0, 2^(c-1)).
-struct MsmLevels {
-    int n_levels;
-    int bits[8];      // bits of level l
-    int shift[8];     // bit offset of level l
-    int log_per;      // unused
-};
-__host__ __device__ inline MsmLevels msm_levels(int c) {
-    MsmLevels L;
-    int rem = c - 1, l = 0, sh = 0;
-    while (rem > 0) {
-        int b = rem < MSM_LEVEL_BITS ? rem : MSM_LEVEL_BITS;
-        L.bits[l] = b;
-        L.shift[l] = sh;
-        sh += b;
-        rem -= b;
-        l++;
-    }
-    if (l == 0) {  // c == 1: a single bucket
-        L.bits[0] = 0; L.shift[0] = 0; l = 1;
-    }
-    L.n_levels = l;
-    L.log_per = 0;
-    return L;
-}
-
-// R1: thread per (window, level, digit, chunk): sum of `chunk_len` buckets sharing that digit.
-// A bucket's value is the sum of its tasks' partial results.
-template <class P>
-__global__ void __launch_bounds__(128) msm_reduce_gather_kernel(int c, int W, int level, int log_chunk,
-                                                                const uint32_t *__restrict__ task_offsets,
-                                                                const uint32_t *__restrict__ ntasks,
-                                                                const XYZZ<Fp<P>> *__restrict__ task_out,
-                                                                XYZZ<Fp<P>> *__restrict__ tmp) {
+// One tree level.  Items of a window are (A, U) pairs (level 0: A = bucket value = sum of the bucket's task
+// results, U = 0).  Node (w, s) folds items s*L .. s*L+L-1:
+//     A' = sum_j A_j                                   ("run": running sum from the top item down)
+//     U' = sum_j U_j + 2^span_bits * sum_j j A_j       ("acc" += run after every step but the last; "usum")
+// so that at the root S_w = sum_k (k+1) B_k = U + A (written to outA when `root`).
+// The three running sums of a node are three dependent chains of XYZZ additions, and the upper levels have
+// far fewer nodes than the GPU has lanes, so a node is spread over LPN adjacent lanes of a warp (roles run /
+// usum / acc; acc trails run by one step through shared memory): the chain per level is L + 1 additions
+// instead of 3 L.  Level 0 has no U: LPN = 2.
+template <class P, int LPN>
+__global__ void __launch_bounds__(128) msm_reduce_level_kernel(int W, uint32_t n_in, int span_bits, int root,
+                                                               const uint32_t *__restrict__ task_offsets,
+                                                               const uint32_t *__restrict__ ntasks,
+                                                               const XYZZ<Fp<P>> *__restrict__ inA,
+                                                               const XYZZ<Fp<P>> *__restrict__ inU,
+                                                               XYZZ<Fp<P>> *__restrict__ outA, XYZZ<Fp<P>> *__restrict__ outU) {
     typedef Fp<P> F;
-    const MsmLevels L = msm_levels(c);
-    const int b = L.bits[level], s = L.shift[level];
-    const uint32_t M = 1u << (c - 1);
-    const uint32_t per_digit = M >> b;                 // buckets sharing one digit value
-    const uint32_t nchunks = (per_digit + (1u << log_chunk) - 1) >> log_chunk;
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = (uint32_t)W * (1u << b) * nchunks;
-    if (tid >= total) return;
-    uint32_t chunk = tid % nchunks;
-    uint32_t D = (tid / nchunks) & ((1u << b) - 1);
-    uint32_t w = tid / (nchunks << b);
-    XYZZ<F> acc = XYZZ<F>::infinity();
-    uint32_t j0 = chunk << log_chunk, j1 = j0 + (1u << log_chunk);
-    if (j1 > per_digit) j1 = per_digit;
-    for (uint32_t j = j0; j < j1; j++) {
-        uint32_t low = j & ((1u << s) - 1), high = j >> s;
-        uint32_t k = (high << (s + b)) | (D << s) | low;
-        uint32_t bucket = w * M + k;
-        uint32_t t0 = task_offsets[bucket], nt = ntasks[bucket];
-        for (uint32_t t = 0; t < nt; t++) acc.add(task_out[t0 + t]);
+    typedef XYZZ<F> Pt;
+    constexpr bool LEVEL0 = LPN == 2;
+    constexpr int ROLE_RUN = 0, ROLE_ACC = 1, ROLE_USUM = 2;          // LPN == 4: lane 3 idles
+    constexpr int NODES = 128 / LPN;
+    __shared__ Pt sh_run[2][NODES];
+    __shared__ Pt sh_usum[LEVEL0 ? 1 : NODES];
+    const uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t node = gtid / LPN, ln = threadIdx.x / LPN;
+    const int role = gtid % LPN;
+    const bool live = node < (uint32_t)W * n_out;
+    const uint32_t w = live ? node / n_out : 0, s = live ? node % n_out : 0;
+    const uint32_t j0 = s << MSM_RED_LOG_L;
+    uint32_t j1 = j0 + MSM_RED_L;
+    if (j1 > n_in) j1 = n_in;
+    Pt x = Pt::infinity();
+    for (uint32_t step = 0; step <= MSM_RED_L; step++) {
+        // step k handles item j = j1-1-k (run, usum) and folds the run value of step k-1 into acc
+        const bool has_item = live && step < j1 - j0;
+        const uint32_t j = j1 - 1 - step;
+        const uint64_t idx = (uint64_t)w * n_in + j;
+        // every role funnels into ONE call site of add() (a warp runs its roles in lockstep)
+        const Pt *src = nullptr;
+        uint32_t cnt = 0;
+        if (role == ROLE_RUN && has_item) {
+            if (LEVEL0) { src = inA + task_offsets[idx]; cnt = ntasks[idx]; }
+            else { src = inA + idx; cnt = 1; }
+        } else if (role == ROLE_USUM && has_item) {
+            src = inU + idx; cnt = 1;
+        } else if (role == ROLE_ACC && live && step >= 1 && step < j1 - j0) {
+            src = &sh_run[(step - 1) & 1][ln]; cnt = 1;   // run after item j1-step, which is > j0
+        }
+        for (uint32_t t = 0; t < cnt; t++) x.add(src[t]);
+        if (role == ROLE_RUN && has_item) sh_run[step & 1][ln] = x;
+        __syncwarp();
     }
-    tmp[tid] = acc;
-}
-
-// R2: thread per (window, level-slot, digit): sums its chunks.  Output layout P[w][slot][32].
-template <class P>
-__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(int W, int bits, int slot, int n_slots, uint32_t nchunks,
-                                                                const XYZZ<Fp<P>> *__restrict__ tmp,
-                                                                XYZZ<Fp<P>> *__restrict__ Pout) {
-    typedef Fp<P> F;
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = (uint32_t)W << bits;
-    if (tid >= total) return;
-    uint32_t D = tid & ((1u << bits) - 1), w = tid >> bits;
-    XYZZ<F> acc = XYZZ<F>::infinity();
-    const XYZZ<F> *src = tmp + (uint64_t)tid * nchunks;
-    for (uint32_t k = 0; k < nchunks; k++) acc.add(src[k]);
-    Pout[((uint64_t)w * n_slots + slot) * 32 + D] = acc;
-}
-
-// R3: thread per (window, slot): slot < n_levels -> Q = sum_D D * P[D] (running sum from the top);
-// slot == n_levels -> plain sum of level 0 (= sum of all buckets).
-template <class P>
-__global__ void __launch_bounds__(64) msm_reduce_weighted_kernel(int c, int W, const XYZZ<Fp<P>> *__restrict__ Pin,
-                                                                 XYZZ<Fp<P>> *__restrict__ Q) {
-    typedef Fp<P> F;
-    const MsmLevels L = msm_levels(c);
-    const int n_slots = L.n_levels;
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (uint32_t)W * (n_slots + 1)) return;
-    uint32_t slot = tid % (n_slots + 1), w = tid / (n_slots + 1);
-    XYZZ<F> acc = XYZZ<F>::infinity();
-    if (slot == (uint32_t)n_slots) {
-        const XYZZ<F> *p = Pin + ((uint64_t)w * n_slots) * 32;
-        for (int D = 0; D < (1 << L.bits[0]); D++) acc.add(p[D]);
-    } else {
-        const XYZZ<F> *p = Pin + ((uint64_t)w * n_slots + slot) * 32;
-        XYZZ<F> run = XYZZ<F>::infinity();
-        for (int D = (1 << L.bits[slot]) - 1; D >= 1; D--) {
-            run.add(p[D]);
-            acc.add(run);
+    if (!LEVEL0 && role == ROLE_USUM && live) sh_usum[ln] = x;
+    __syncwarp();
+    if (!live) return;
+    if (role == ROLE_RUN) {
+        if (!root) outA[node] = x;
+    } else if (role == ROLE_ACC) {
+        for (int i = 0; i < span_bits; i++) x = x.dbl();
+        if (!LEVEL0) x.add(sh_usum[ln]);
+        if (root) {   // S_w = U + A
+            x.add(sh_run[(j1 - j0 - 1) & 1][ln]);
+            outA[node] = x;
+        } else {
+            outU[node] = x;
         }
     }
-    Q[tid] = acc;
-}
-
-// R4: thread per window: S_w = plain + sum_l 2^shift[l] Q[l]
-template <class P>
-__global__ void __launch_bounds__(32) msm_reduce_window_kernel(int c, int W, const XYZZ<Fp<P>> *__restrict__ Q,
-                                                               XYZZ<Fp<P>> *__restrict__ S) {
-    typedef Fp<P> F;
-    const MsmLevels L = msm_levels(c);
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= (uint32_t)W) return;
-    const XYZZ<F> *q = Q + (uint64_t)w * (L.n_levels + 1);
-    XYZZ<F> acc = q[L.n_levels - 1];
-    for (int l = L.n_levels - 2; l >= 0; l--) {
-        for (int i = 0; i < L.bits[l]; i++) acc = acc.dbl();
-        acc.add(q[l]);
-    }
-    acc.add(q[L.n_levels]);
-    S[w] = acc;
 }
 
 // ------------------------------------------------------------------------------------ host driver
@@ -365,7 +409,6 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     const int W = (SCALAR_BITS + 1 + c - 1) / c;
     const uint32_t M = 1u << (c - 1);
     const uint32_t nb = (uint32_t)W * M;
-    const MsmLevels L = msm_levels(c);
     const uint64_t total_keys = (uint64_t)W * n;
     if (n >= (1ull << 31) || total_keys >= (1ull << 32))
         return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "MSM: W*n must be < 2^32 (split the range across calls/GPUs)");
@@ -379,20 +422,13 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     size_t o_ntasks = carve((size_t)nb * 4), o_toffs = carve((size_t)nb * 4);
     size_t o_bsums = carve(((size_t)nb / 1024 + 2) * 4), o_totals = carve(16);
     size_t o_tasks = carve(max_tasks * sizeof(MsmTask)), o_tout = carve(max_tasks * sizeof(Pt));
-    // reduce temporaries: per level W * 2^bits * nchunks partial sums
-    uint32_t max_tmp = 0, nchunks_l[8], logchunk_l[8];
-    for (int l = 0; l < L.n_levels; l++) {
-        uint32_t per_digit = M >> L.bits[l];
-        int lg = 0;
-        while ((1u << lg) < per_digit) lg++;
-        logchunk_l[l] = (lg + 1) / 2;
-        nchunks_l[l] = (per_digit + (1u << logchunk_l[l]) - 1) >> logchunk_l[l];
-        uint32_t cnt = (uint32_t)W * (1u << L.bits[l]) * nchunks_l[l];
-        if (cnt > max_tmp) max_tmp = cnt;
-    }
-    size_t o_tmp = carve((size_t)max_tmp * sizeof(Pt));
-    size_t o_P = carve((size_t)W * L.n_levels * 32 * sizeof(Pt));
-    size_t o_Q = carve((size_t)W * (L.n_levels + 1) * sizeof(Pt));
+    size_t o_perm = carve(max_tasks * 4), o_bins = carve(3 * MSM_TASK_CAP * 4);
+    // at most total_keys / CAP buckets can hold more than CAP points
+    const uint32_t heavy_cap = (uint32_t)(total_keys / MSM_TASK_CAP + 1);
+    size_t o_heavy = carve((size_t)(heavy_cap + 1) * 4);
+    // reduce tree: level l holds W * ceil(M / L^(l+1)) (A, U) pairs; two ping-pong buffers of the level-0 size
+    const uint32_t n_lvl0 = (M + MSM_RED_L - 1) >> MSM_RED_LOG_L;
+    size_t o_red = carve((size_t)4 * W * n_lvl0 * sizeof(Pt));
     size_t o_S = carve((size_t)W * sizeof(Pt));
     void *base;
     ZKB_TRY(ctx_scratch(ctx, "msm", off, &base));
@@ -402,32 +438,54 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     uint32_t *ntasks = (uint32_t *)(B + o_ntasks), *toffs = (uint32_t *)(B + o_toffs);
     uint32_t *bsums = (uint32_t *)(B + o_bsums), *totals = (uint32_t *)(B + o_totals);
     MsmTask *tasks = (MsmTask *)(B + o_tasks);
-    Pt *tout = (Pt *)(B + o_tout), *tmp = (Pt *)(B + o_tmp), *Pl = (Pt *)(B + o_P), *Q = (Pt *)(B + o_Q), *S = (Pt *)(B + o_S);
+    uint32_t *n_heavy = (uint32_t *)(B + o_heavy), *heavy = n_heavy + 1;
+    uint32_t *perm = (uint32_t *)(B + o_perm), *bins = (uint32_t *)(B + o_bins), *bin_off = bins + MSM_TASK_CAP,
+             *bin_cur = bins + 2 * MSM_TASK_CAP;
+    Pt *tout = (Pt *)(B + o_tout), *red = (Pt *)(B + o_red), *S = (Pt *)(B + o_S);
 
     // counts and cursor are adjacent carve-outs: one memset
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(cursor, 0, (size_t)nb * 4, st));
     msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, (const uint32_t *)d_scalars, c, W, keys, counts);
-    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, ntasks);
+    ZKB_CUDA_OK(ctx, cudaMemsetAsync(n_heavy, 0, 4, st));
+    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, ntasks, n_heavy, heavy, heavy_cap);
     ctx->launches += 2;
     ZKB_TRY(exclusive_scan(ctx, nb, counts, offsets, bsums, totals, st));
     ZKB_TRY(exclusive_scan(ctx, nb, ntasks, toffs, bsums, totals + 1, st));
     msm_fill_tasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, offsets, toffs, tasks);
     msm_scatter_kernel<<<(unsigned)((total_keys + 255) / 256), 256, 0, st>>>(total_keys, (uint32_t)n, keys, offsets, cursor, sorted);
     const Affine<F> *pts = (const Affine<F> *)bases->d_points + offset;
-    msm_accumulate_kernel<P><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(totals + 1, tasks, sorted, pts, tout);
-    ctx->launches += 3;
-    for (int l = 0; l < L.n_levels; l++) {
-        uint32_t cnt = (uint32_t)W * (1u << L.bits[l]) * nchunks_l[l];
-        msm_reduce_gather_kernel<P><<<(cnt + 127) / 128, 128, 0, st>>>(c, W, l, (int)logchunk_l[l], toffs, ntasks, tout, tmp);
-        uint32_t cnt2 = (uint32_t)W << L.bits[l];
-        msm_reduce_chunks_kernel<P><<<(cnt2 + 127) / 128, 128, 0, st>>>(W, L.bits[l], l, L.n_levels, nchunks_l[l], tmp, Pl);
-        ctx->launches += 2;
+    const unsigned task_blocks = (unsigned)((max_tasks + 255) / 256);
+    ZKB_CUDA_OK(ctx, cudaMemsetAsync(bins, 0, MSM_TASK_CAP * 4, st));
+    msm_task_hist_kernel<<<task_blocks, 256, 0, st>>>(totals + 1, tasks, bins);
+    msm_task_scan_kernel<<<1, MSM_TASK_CAP, 0, st>>>(bins, bin_off, bin_cur);
+    msm_task_permute_kernel<<<task_blocks, 256, 0, st>>>(totals + 1, tasks, bin_off, bin_cur, perm);
+    msm_accumulate_kernel<P><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(totals + 1, tasks, perm, sorted, pts, tout);
+    msm_heavy_tree_kernel<P><<<heavy_cap < 1024 ? heavy_cap : 1024, 256, 0, st>>>(n_heavy, heavy, heavy_cap, toffs, ntasks, tout);
+    ctx->launches += 7;
+    {
+        uint32_t n_in = M;
+        int span_bits = 0, level = 0;
+        const size_t half = (size_t)2 * W * n_lvl0;   // elements per ping-pong buffer (A then U)
+        while (true) {
+            uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
+            Pt *src = red + (size_t)((level + 1) & 1) * half, *dst = red + (size_t)(level & 1) * half;
+            const Pt *inA = level == 0 ? tout : src, *inU = level == 0 ? nullptr : src + (size_t)W * n_lvl0;
+            const bool root = n_out == 1;
+            uint32_t cnt = (uint32_t)W * n_out;
+            if (level == 0)
+                msm_reduce_level_kernel<P, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
+                                                                                   root ? S : dst, dst + (size_t)W * n_lvl0);
+            else
+                msm_reduce_level_kernel<P, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
+                                                                                   root ? S : dst, dst + (size_t)W * n_lvl0);
+            ctx->launches++;
+            if (root) break;
+            n_in = n_out;
+            span_bits += MSM_RED_LOG_L;
+            level++;
+        }
     }
-    uint32_t cnt3 = (uint32_t)W * (L.n_levels + 1);
-    msm_reduce_weighted_kernel<P><<<(cnt3 + 63) / 64, 64, 0, st>>>(c, W, Pl, Q);
-    msm_reduce_window_kernel<P><<<(W + 31) / 32, 32, 0, st>>>(c, W, Q, S);
-    ctx->launches += 2;
     ZKB_CUDA_OK(ctx, cudaGetLastError());
     std::vector<uint32_t> hs((size_t)W * 4 * F::N);
     ZKB_CUDA_OK(ctx, cudaMemcpyAsync(hs.data(), S, hs.size() * 4, cudaMemcpyDeviceToHost, st));

@@ -345,6 +345,55 @@ def test_msm_edge_cases(ctx, C):
     assert ctx.multiexp(be, to_arr([r - 3] * 700)) == C.mul(P, 700 * (r - 3))
 
 
+
+def _grid_msm_case(ctx, C, log_n, scalars_fn, seed):
+    """MSM over n = 2^log_n grid points P_i = A[i % m] + B[i / m] (built on the device) checked through the
+    size-independent identity  sum s_i P_i = sum_a (sum_{i%m=a} s_i) A_a + sum_b (sum_{i/m=b} s_i) B_b,
+    whose right-hand side is an (m + n/m)-point MSM the oracle does on the CPU."""
+    r = C.scalar_field.p
+    n, m = 1 << log_n, 256
+    nb = n // m
+    rnd = random.Random(seed)
+
+    def progression(count):   # P_0 + k D by a running addition (cheap in Python, distinct w.h.p.)
+        cur, D, out = C.mul(C.gen, rnd.randrange(1, r)), C.mul(C.gen, rnd.randrange(1, r)), []
+        for _ in range(count):
+            out.append(cur)
+            cur = C.add(cur, D)
+        return out
+    A, Bt = progression(m), progression(nb)
+    pts = ctx.grid_points(C.name, n, enc_points(C, A), enc_points(C, Bt))
+    bases = ctx.msm_bases(C.name, pts)
+    sc = scalars_fn(n, rnd, r)
+    arr = np.zeros((n, 8), dtype=np.uint32)
+    for k in range(8):
+        arr[:, k] = [(v >> (32 * k)) & 0xFFFFFFFF for v in sc]
+    got = ctx.multiexp(bases, dev(arr))
+    sa, sb = [0] * m, [0] * nb
+    for i, v in enumerate(sc):
+        sa[i % m] += v
+        sb[i // m] += v
+    want = C.msm_bdlo12(A + Bt, [v % r for v in sa + sb])
+    assert got == want
+    bases.free()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "all_equal", "zero_one", "top_window"])
+def test_msm_large_grid_identity(ctx, kind):
+    """2^17..2^20-point BLS12-381 MSMs: uniform 255-bit scalars (the top signed window holds only a few
+    significant bits, so its buckets are split into many tasks), all-equal scalars (one bucket per
+    window), a 0/1-heavy Groth16-style assignment (knowledge_commitment_multiexp.hpp:88-101) and scalars
+    that differ only in the top window."""
+    C = curves.BLS12_381_G1
+    fns = {
+        "uniform": lambda n, rnd, r: [rnd.randrange(r) for _ in range(n)],
+        "all_equal": lambda n, rnd, r: [r - 12345] * n,
+        "zero_one": lambda n, rnd, r: [rnd.choice([0, 1, 1, 1, 1, 1, 1, rnd.randrange(r)]) for _ in range(n)],
+        "top_window": lambda n, rnd, r: [((rnd.randrange(7) << 252) + 99) % r for _ in range(n)],
+    }
+    _grid_msm_case(ctx, C, 20 if kind == "uniform" else 17, fns[kind], 77)
+
+
 def test_kzg_commit_identity_2p16(ctx):
     """BASELINE config #1: KZG commit of a degree-2^16 polynomial over BLS12-381 (kzg.hpp:143-148):
     with commitment_key[i] = alpha^i G the commitment equals f(alpha) G (test/commitment/kzg.cpp:97)."""
