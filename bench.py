@@ -211,7 +211,7 @@ def extras(args, torch, ctx, dev, hbm_peak):
     msm_e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
     c = max(2, min(20, log_m - 4))
     W = (255 + 1 + c - 1) // c
-    fq_mults = nm * W * 10 + W * (1 << (c - 1)) * 3 * 14 + 255 * 8
+    fq_mults = nm * W * 10 + W * (1 << (c - 1)) * 2 * 14 + 255 * 8   # SURVEY 8(d) work model
     ex["msm_g1_2p%d_bls12_381" % log_m] = {
         "ms": msm_ms, "e2e_ms_host_scalars": msm_e2e_ms, "window_bits": c, "windows": W,
         "work_model_fq_mults": fq_mults,

@@ -136,6 +136,13 @@ int zkb_ctx_release_caches(zkb_ctx *ctx) {
 void zkb_ctx_destroy(zkb_ctx *ctx) {
     if (!ctx) return;
     zkb_ctx_release_caches(ctx);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
     delete ctx;
 }
 

@@ -21,6 +21,9 @@ struct zkb_ctx {
     std::map<std::string, Buf> scratch;
     // cached device tables (twiddles, coset powers), keyed by a descriptive string
     std::map<std::string, Buf> tables;
+    // copy streams + events of the host-buffer pipeline (created on first use, see host_pipeline())
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
 };
 
 namespace zkb {

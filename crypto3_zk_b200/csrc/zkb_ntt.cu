@@ -294,6 +294,67 @@ struct Staged {  // host<->device staging for ZKB_MEM_HOST callers
     }
 };
 bool is_ntt_field(int f) { return f >= ZKB_FIELD_BLS12_381_FR && f <= ZKB_FIELD_PALLAS_FQ; }
+
+// Host-buffer callers (ZKB_MEM_HOST) of the batched transforms: polynomials stream through two device
+// slots so that the upload of chunk k+1 and the download of chunk k-1 overlap the kernels of chunk k
+// (PCIe is full duplex; the LDE of config #2 returns 8x what it reads, so the download is the bound).
+// `compute(nb, din, dout)` enqueues the kernels for nb polynomials on `st`.
+template <class Fn>
+int host_pipeline(zkb_ctx *ctx, cudaStream_t st, uint32_t batch, size_t in_poly_bytes, size_t out_poly_bytes,
+                  const void *in, void *out, Fn compute) {
+    if (!ctx->copy_in) {
+        ZKB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        ZKB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            ZKB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            ZKB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+            ZKB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t target = 256ull << 20;   // bytes of output per chunk
+    uint32_t chunk = (uint32_t)(target / out_poly_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    void *din[2], *dout[2];
+    char *base_in, *base_out;
+    ZKB_TRY(ctx_scratch(ctx, "pipe_in", 2 * chunk * in_poly_bytes, (void **)&base_in));
+    ZKB_TRY(ctx_scratch(ctx, "pipe_out", 2 * chunk * out_poly_bytes, (void **)&base_out));
+    for (int i = 0; i < 2; i++) {
+        din[i] = base_in + (size_t)i * chunk * in_poly_bytes;
+        dout[i] = base_out + (size_t)i * chunk * out_poly_bytes;
+    }
+    int status = ZKB_OK;
+    uint32_t k = 0;
+    for (uint32_t b0 = 0; b0 < batch && status == ZKB_OK; b0 += chunk, k++) {
+        const uint32_t nb = batch - b0 < chunk ? batch - b0 : chunk;
+        const int s = k & 1;
+        cudaError_t e = cudaSuccess;
+        if (k >= 2) e = cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0);     // slot's previous kernels have read it
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(din[s], (const char *)in + (size_t)b0 * in_poly_bytes, nb * in_poly_bytes,
+                                cudaMemcpyHostToDevice, ctx->copy_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[s], ctx->copy_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0);
+        if (e == cudaSuccess && k >= 2) e = cudaStreamWaitEvent(st, ctx->ev_d2h[s], 0);   // slot's previous output is home
+        if (e != cudaSuccess) { status = ctx_fail(ctx, ZKB_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(e)); break; }
+        status = compute(nb, (const void *)din[s], dout[s]);
+        if (status != ZKB_OK) break;
+        e = cudaEventRecord(ctx->ev_comp[s], st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[s], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char *)out + (size_t)b0 * out_poly_bytes, dout[s], nb * out_poly_bytes,
+                                cudaMemcpyDeviceToHost, ctx->copy_out);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[s], ctx->copy_out);
+        if (e != cudaSuccess) status = ctx_fail(ctx, ZKB_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(e));
+    }
+    // the call returns with the results in `out` (and nothing in flight, also on the error path)
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_in), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ctx->copy_out);
+    if (status != ZKB_OK) return status;
+    ZKB_CUDA_OK(ctx, e1);
+    ZKB_CUDA_OK(ctx, e2);
+    ZKB_CUDA_OK(ctx, e3);
+    return ZKB_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -308,13 +369,11 @@ int zkb_ntt(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *in, 
     ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     size_t bytes = ((size_t)batch << log_n) * 32;
-    Staged sg(ctx, st, mem);
-    const void *din;
-    void *dout;
-    ZKB_TRY(sg.in("io_in", in, bytes, &din));
-    ZKB_TRY(sg.out_buf("io_in", out, bytes, &dout));   // in place on the staging buffer
-    ZKB_TRY(ntt_device(ctx, field, log_n, batch, din, dout, inverse, coset_shift, 1ull << log_n, 1ull << log_n, st));
-    return sg.out(out, dout, bytes);
+    if (mem != ZKB_MEM_DEVICE)
+        return host_pipeline(ctx, st, batch, bytes / batch, bytes / batch, in, out, [&](uint32_t nb, const void *di, void *dout) {
+            return ntt_device(ctx, field, log_n, nb, di, dout, inverse, coset_shift, 1ull << log_n, 1ull << log_n, st);
+        });
+    return ntt_device(ctx, field, log_n, batch, in, out, inverse, coset_shift, 1ull << log_n, 1ull << log_n, st);
 }
 
 int zkb_lde(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *in, void *out, int mem,
@@ -326,14 +385,12 @@ int zkb_lde(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch
     if (batch == 0) return ZKB_OK;
     ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    size_t ib = ((size_t)batch << log_n_in) * 32, ob = ((size_t)batch << log_n_out) * 32;
-    Staged sg(ctx, st, mem);
-    const void *din;
-    void *dout;
-    ZKB_TRY(sg.in("io_in", in, ib, &din));
-    ZKB_TRY(sg.out_buf("io_out", out, ob, &dout));
-    ZKB_TRY(lde_device(ctx, field, log_n_in, log_n_out, batch, din, dout, st));
-    return sg.out(out, dout, ob);
+    if (mem != ZKB_MEM_DEVICE)
+        return host_pipeline(ctx, st, batch, (size_t)32 << log_n_in, (size_t)32 << log_n_out, in, out,
+                             [&](uint32_t nb, const void *di, void *dout) {
+                                 return lde_device(ctx, field, log_n_in, log_n_out, nb, di, dout, st);
+                             });
+    return lde_device(ctx, field, log_n_in, log_n_out, batch, in, out, st);
 }
 
 int zkb_vec(zkb_ctx *ctx, int field, int op, uint64_t n, const void *a, const void *b, const void *c,
