@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 
 from . import capi
-from .fields import CURVE_BY_NAME, FIELD_BY_NAME
+from .fields import CURVE_BY_NAME, FIELD_BY_NAME, coord_limbs
 
 
 def _field_id(field):
@@ -104,7 +104,7 @@ class MsmBases:
 
     def __init__(self, ctx, curve, points, stream=None):
         self._ctx, self.curve = ctx, _curve(curve)
-        cl = FIELD_BY_NAME[self.curve.base_field].limbs32
+        cl = coord_limbs(self.curve)
         b = _Buf(points)
         n = b.nbytes // (2 * cl * 4)
         if n * 2 * cl * 4 != b.nbytes:
@@ -112,7 +112,7 @@ class MsmBases:
         h = ctypes.c_void_p()
         capi.check(capi.lib().zkb_msm_bases_create(ctx._h, self.curve.cid, n, b.ptr, b.mem, _stream_ptr(points, stream),
                                                    ctypes.byref(h)), ctx._h)
-        self._h, self.n, self.coord_limbs = h, n, cl
+        self._h, self.n, self.coord_limbs, self.deg = h, n, cl, self.curve.deg
 
     def free(self):
         if self._h:
@@ -254,7 +254,7 @@ class Context:
         res = (ctypes.c_uint32 * (2 * cl))()
         capi.check(capi.lib().zkb_msm(self._h, bases._h, offset, n, sb.ptr, sb.mem, res, _stream_ptr(scalars, stream)),
                    self._h)
-        return _affine_from_limbs(res, cl)
+        return _affine_from_limbs(res, cl, bases.deg)
 
     def multiexp_partial(self, bases, scalars, offset=0, n=None, stream=None):
         """Partial sum in XYZZ/Montgomery limbs (numpy [4*coord_limbs]) for multi-GPU point sharding."""
@@ -270,7 +270,7 @@ class Context:
         """Synthetic bases on the device: out[i] = table_a[i % m] + table_b[i // m] (torch int32 [n,2,cl])."""
         import torch
         c = _curve(curve)
-        cl = FIELD_BY_NAME[c.base_field].limbs32
+        cl = coord_limbs(c)
         ta = np.ascontiguousarray(table_a, dtype=np.uint32)
         tb = np.ascontiguousarray(table_b, dtype=np.uint32)
         m = ta.size // (2 * cl)
@@ -287,7 +287,12 @@ class Context:
         return r.value
 
 
-def _affine_from_limbs(res, cl):
+def _affine_from_limbs(res, cl, deg=1):
+    """(x, y) as Python ints ((c0, c1) tuples per coordinate on the G2 groups); None = infinity."""
+    if deg == 2:
+        h = cl // 2
+        v = [sum(int(res[k * h + i]) << (32 * i) for i in range(h)) for k in range(4)]
+        return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
     x = sum(int(res[i]) << (32 * i) for i in range(cl))
     y = sum(int(res[cl + i]) << (32 * i) for i in range(cl))
     return None if x == 0 and y == 0 else (x, y)
@@ -296,11 +301,11 @@ def _affine_from_limbs(res, cl):
 def msm_combine(curve, partials):
     """Adds per-GPU partial sums (rows of XYZZ limbs) on the host -> affine (x, y) or None."""
     c = _curve(curve)
-    cl = FIELD_BY_NAME[c.base_field].limbs32
+    cl = coord_limbs(c)
     p = np.ascontiguousarray(np.asarray(partials, dtype=np.uint32).reshape(-1, 4 * cl))
     res = (ctypes.c_uint32 * (2 * cl))()
     capi.check(capi.lib().zkb_msm_combine(c.cid, p.shape[0], capi.u32_ptr(p), res))
-    return _affine_from_limbs(res, cl)
+    return _affine_from_limbs(res, cl, c.deg)
 
 
 def field_generator(field):

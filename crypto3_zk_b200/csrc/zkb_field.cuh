@@ -264,4 +264,53 @@ struct Fp {
     }
 };
 
+// Quadratic extension B[u]/(u^2 + 1) - the coordinate field of the G2 groups of BLS12-381 and BN254
+// (both use the non-residue -1).  Generic over the base type so that the device Fp<P> and the host
+// HostFp<P> share it; interface = what the group formulas of zkb_curve.cuh use.  Limb layout at the
+// ABI: c0 || c1.
+template <class B>
+struct Fp2 {
+    static constexpr int N = 2 * B::N;
+    B c0, c1;
+
+    ZKB_HD static Fp2 zero() { Fp2 r; r.c0 = B::zero(); r.c1 = B::zero(); return r; }
+    ZKB_HD static Fp2 one() { Fp2 r; r.c0 = B::one(); r.c1 = B::zero(); return r; }
+    ZKB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    ZKB_HD bool operator==(const Fp2 &o) const { return c0 == o.c0 && c1 == o.c1; }
+    ZKB_HD bool operator!=(const Fp2 &o) const { return !(*this == o); }
+    ZKB_HD friend Fp2 operator+(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+    ZKB_HD friend Fp2 operator-(const Fp2 &a, const Fp2 &b) { Fp2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+    ZKB_HD Fp2 neg() const { Fp2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
+    ZKB_HD Fp2 dbl() const { Fp2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
+    // Karatsuba: 3 base multiplications
+    ZKB_HD friend Fp2 operator*(const Fp2 &a, const Fp2 &b) {
+        B t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+        B t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+        Fp2 r;
+        r.c0 = t0 - t1;
+        r.c1 = t2 - t0 - t1;
+        return r;
+    }
+    // (a0 + a1)(a0 - a1) + 2 a0 a1 u : 2 base multiplications
+    ZKB_HD Fp2 sqr() const {
+        B s = c0 + c1, d = c0 - c1, m = c0 * c1;
+        Fp2 r;
+        r.c0 = s * d;
+        r.c1 = m.dbl();
+        return r;
+    }
+    ZKB_HD Fp2 to_mont() const { Fp2 r; r.c0 = c0.to_mont(); r.c1 = c1.to_mont(); return r; }
+    ZKB_HD Fp2 from_mont() const { Fp2 r; r.c0 = c0.from_mont(); r.c1 = c1.from_mont(); return r; }
+    ZKB_HD Fp2 inverse() const {   // conj / norm (0 -> 0)
+        B n = (c0.sqr() + c1.sqr()).inverse();
+        Fp2 r;
+        r.c0 = c0 * n;
+        r.c1 = (c1 * n).neg();
+        return r;
+    }
+    ZKB_HD Fp2 &operator+=(const Fp2 &o) { *this = *this + o; return *this; }
+    ZKB_HD Fp2 &operator-=(const Fp2 &o) { *this = *this - o; return *this; }
+    ZKB_HD Fp2 &operator*=(const Fp2 &o) { *this = *this * o; return *this; }
+};
+
 }  // namespace zkb

@@ -41,13 +41,29 @@ struct zkb_msm_bases {
     void *d_points;  // Affine<F>, Montgomery form
 };
 
+// coordinate fields of the supported groups
+typedef Fp<params::Bls12381Fq> FqBls;
+typedef Fp<params::Bn254Fq> FqBn;
+typedef Fp<params::PallasFp> FpPallas;
+typedef Fp2<FqBls> Fq2Bls;
+typedef Fp2<FqBn> Fq2Bn;
+#define ZKB_DISPATCH_CURVE(curve, ...)                                 \
+    switch (curve) {                                                     \
+        case ZKB_CURVE_BLS12_381_G1: { typedef FqBls CF; enum { SB = params::Bls12381Fr::BITS }; __VA_ARGS__; } break;  \
+        case ZKB_CURVE_BN254_G1: { typedef FqBn CF; enum { SB = params::Bn254Fr::BITS }; __VA_ARGS__; } break;          \
+        case ZKB_CURVE_PALLAS: { typedef FpPallas CF; enum { SB = params::PallasFq::BITS }; __VA_ARGS__; } break;       \
+        case ZKB_CURVE_BLS12_381_G2: { typedef Fq2Bls CF; enum { SB = params::Bls12381Fr::BITS }; __VA_ARGS__; } break; \
+        case ZKB_CURVE_BN254_G2: { typedef Fq2Bn CF; enum { SB = params::Bn254Fr::BITS }; __VA_ARGS__; } break;         \
+        default: break;                                                  \
+    }
+
 #define MSM_TASK_CAP 256u
 #define MSM_SENTINEL 0xffffffffu
 #define MSM_LEVEL_BITS 5
 
 // ------------------------------------------------------------------------------------ small kernels
-template <class P>
-__global__ void __launch_bounds__(256) points_to_mont_kernel(uint64_t n, Affine<Fp<P>> *pts) {
+template <class F>
+__global__ void __launch_bounds__(256) points_to_mont_kernel(uint64_t n, Affine<F> *pts) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pts[i] = pts[i].to_mont();
 }
@@ -219,12 +235,11 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F> *p) {
     return r;
 }
 
-template <class P>
+template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ n_tasks, const MsmTask *__restrict__ tasks,
                                                              const uint32_t *__restrict__ perm, const uint32_t *__restrict__ sorted,
-                                                             const Affine<Fp<P>> *__restrict__ points,
-                                                             XYZZ<Fp<P>> *__restrict__ out) {
-    typedef Fp<P> F;
+                                                             const Affine<F> *__restrict__ points,
+                                                             XYZZ<F> *__restrict__ out) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= *n_tasks) return;
     const uint32_t t = perm[g];
@@ -298,17 +313,17 @@ __global__ void __launch_bounds__(256) msm_task_permute_kernel(const uint32_t *_
 // Groth16 assignments put almost everything into bucket 0 of window 0 - the reference filters those on the
 // CPU, knowledge_commitment_multiexp.hpp:88-101).  One block per such bucket adds its task results pairwise
 // in place (a tree over global memory), leaves the total in the bucket's first task and sets ntasks to 1.
-template <class P>
+template <class F>
 __global__ void __launch_bounds__(256) msm_heavy_tree_kernel(const uint32_t *__restrict__ n_heavy, const uint32_t *__restrict__ heavy,
                                                              uint32_t heavy_cap, const uint32_t *__restrict__ task_offsets,
-                                                             uint32_t *__restrict__ ntasks, XYZZ<Fp<P>> *__restrict__ tout) {
+                                                             uint32_t *__restrict__ ntasks, XYZZ<F> *__restrict__ tout) {
     uint32_t nh = *n_heavy;
     if (nh > heavy_cap) nh = heavy_cap;
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         const uint32_t b = heavy[h], t0 = task_offsets[b], nt = ntasks[b];
         for (uint32_t s = 1; s < nt; s <<= 1) {
             for (uint32_t i = threadIdx.x * 2 * s; i + s < nt; i += blockDim.x * 2 * s) {
-                XYZZ<Fp<P>> x = tout[t0 + i];
+                XYZZ<F> x = tout[t0 + i];
                 x.add(tout[t0 + i + s]);
                 tout[t0 + i] = x;
             }
@@ -329,14 +344,13 @@ __global__ void __launch_bounds__(256) msm_heavy_tree_kernel(const uint32_t *__r
 // far fewer nodes than the GPU has lanes, so a node is spread over LPN adjacent lanes of a warp (roles run /
 // usum / acc; acc trails run by one step through shared memory): the chain per level is L + 1 additions
 // instead of 3 L.  Level 0 has no U: LPN = 2.
-template <class P, int LPN>
+template <class F, int LPN>
 __global__ void __launch_bounds__(128) msm_reduce_level_kernel(int W, uint32_t n_in, int span_bits, int root,
                                                                const uint32_t *__restrict__ task_offsets,
                                                                const uint32_t *__restrict__ ntasks,
-                                                               const XYZZ<Fp<P>> *__restrict__ inA,
-                                                               const XYZZ<Fp<P>> *__restrict__ inU,
-                                                               XYZZ<Fp<P>> *__restrict__ outA, XYZZ<Fp<P>> *__restrict__ outU) {
-    typedef Fp<P> F;
+                                                               const XYZZ<F> *__restrict__ inA,
+                                                               const XYZZ<F> *__restrict__ inU,
+                                                               XYZZ<F> *__restrict__ outA, XYZZ<F> *__restrict__ outU) {
     typedef XYZZ<F> Pt;
     constexpr bool LEVEL0 = LPN == 2;
     constexpr int ROLE_RUN = 0, ROLE_ACC = 1, ROLE_USUM = 2;          // LPN == 4: lane 3 idles
@@ -400,10 +414,9 @@ static int msm_pick_c(uint64_t n) {
     return c;
 }
 
-template <class P, int SCALAR_BITS>
+template <class F, int SCALAR_BITS>
 static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
                      uint32_t *partial_host, cudaStream_t st) {
-    typedef Fp<P> F;
     typedef XYZZ<F> Pt;
     const int c = msm_pick_c(n);
     const int W = (SCALAR_BITS + 1 + c - 1) / c;
@@ -460,8 +473,8 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     msm_task_hist_kernel<<<task_blocks, 256, 0, st>>>(totals + 1, tasks, bins);
     msm_task_scan_kernel<<<1, MSM_TASK_CAP, 0, st>>>(bins, bin_off, bin_cur);
     msm_task_permute_kernel<<<task_blocks, 256, 0, st>>>(totals + 1, tasks, bin_off, bin_cur, perm);
-    msm_accumulate_kernel<P><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(totals + 1, tasks, perm, sorted, pts, tout);
-    msm_heavy_tree_kernel<P><<<heavy_cap < 1024 ? heavy_cap : 1024, 256, 0, st>>>(n_heavy, heavy, heavy_cap, toffs, ntasks, tout);
+    msm_accumulate_kernel<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(totals + 1, tasks, perm, sorted, pts, tout);
+    msm_heavy_tree_kernel<F><<<heavy_cap < 1024 ? heavy_cap : 1024, 256, 0, st>>>(n_heavy, heavy, heavy_cap, toffs, ntasks, tout);
     ctx->launches += 7;
     {
         uint32_t n_in = M;
@@ -474,10 +487,10 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
             const bool root = n_out == 1;
             uint32_t cnt = (uint32_t)W * n_out;
             if (level == 0)
-                msm_reduce_level_kernel<P, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
+                msm_reduce_level_kernel<F, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
                                                                                    root ? S : dst, dst + (size_t)W * n_lvl0);
             else
-                msm_reduce_level_kernel<P, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
+                msm_reduce_level_kernel<F, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
                                                                                    root ? S : dst, dst + (size_t)W * n_lvl0);
             ctx->launches++;
             if (root) break;
@@ -495,32 +508,22 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
 
 static int msm_run(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
                    uint32_t *partial_host, cudaStream_t st) {
-    switch (bases->curve) {
-        case ZKB_CURVE_BLS12_381_G1:
-            return msm_run_t<params::Bls12381Fq, params::Bls12381Fr::BITS>(ctx, bases, offset, n, d_scalars, partial_host, st);
-        case ZKB_CURVE_BN254_G1:
-            return msm_run_t<params::Bn254Fq, params::Bn254Fr::BITS>(ctx, bases, offset, n, d_scalars, partial_host, st);
-        case ZKB_CURVE_PALLAS:
-            return msm_run_t<params::PallasFp, params::PallasFq::BITS>(ctx, bases, offset, n, d_scalars, partial_host, st);
-    }
+    ZKB_DISPATCH_CURVE(bases->curve, return msm_run_t<CF, SB>(ctx, bases, offset, n, d_scalars, partial_host, st))
     return ZKB_ERR_INVALID_ARGUMENT;
 }
 
+// u32 limbs per affine coordinate (x or y)
 static int curve_coord_limbs(int curve) {
-    switch (curve) {
-        case ZKB_CURVE_BLS12_381_G1: return 12;
-        case ZKB_CURVE_BN254_G1: case ZKB_CURVE_PALLAS: return 8;
-    }
+    ZKB_DISPATCH_CURVE(curve, return CF::N)
     return 0;
 }
 
 // ------------------------------------------------------------------------------------ synthetic points
 // out[i] = A[i % m] + B[i / m] (affine, canonical): lets benchmarks and tests build millions of valid,
 // distinct curve points from two small host-made tables ("generate on GPU").
-template <class P>
-__global__ void __launch_bounds__(128) grid_points_kernel(uint64_t n, uint32_t m, const Affine<Fp<P>> *__restrict__ A,
-                                                          const Affine<Fp<P>> *__restrict__ Bt, Affine<Fp<P>> *__restrict__ out) {
-    typedef Fp<P> F;
+template <class F>
+__global__ void __launch_bounds__(128) grid_points_kernel(uint64_t n, uint32_t m, const Affine<F> *__restrict__ A,
+                                                          const Affine<F> *__restrict__ Bt, Affine<F> *__restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     XYZZ<F> acc = XYZZ<F>::from_affine(A[i % m].to_mont());
@@ -528,10 +531,10 @@ __global__ void __launch_bounds__(128) grid_points_kernel(uint64_t n, uint32_t m
     out[i] = acc.to_affine().from_mont();
 }
 
-template <class P>
+template <class F>
 static int grid_points_t(zkb_ctx *ctx, uint64_t n, uint32_t m, const void *dA, const void *dB, void *dout, cudaStream_t st) {
-    typedef Affine<Fp<P>> A;
-    grid_points_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, m, (const A *)dA, (const A *)dB, (A *)dout);
+    typedef Affine<F> A;
+    grid_points_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, m, (const A *)dA, (const A *)dB, (A *)dout);
     ctx->launches++;
     ZKB_CUDA_OK(ctx, cudaGetLastError());
     return ZKB_OK;
@@ -556,12 +559,8 @@ int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const vo
     ZKB_TRY(ctx_scratch(ctx, "grid_b", nb * pb, &dB));
     ZKB_CUDA_OK(ctx, cudaMemcpyAsync(dA, table_a, m * pb, cudaMemcpyHostToDevice, st));
     ZKB_CUDA_OK(ctx, cudaMemcpyAsync(dB, table_b, nb * pb, cudaMemcpyHostToDevice, st));
-    int s;
-    switch (curve) {
-        case ZKB_CURVE_BLS12_381_G1: s = grid_points_t<params::Bls12381Fq>(ctx, n, m, dA, dB, out_device, st); break;
-        case ZKB_CURVE_BN254_G1: s = grid_points_t<params::Bn254Fq>(ctx, n, m, dA, dB, out_device, st); break;
-        default: s = grid_points_t<params::PallasFp>(ctx, n, m, dA, dB, out_device, st); break;
-    }
+    int s = ZKB_ERR_INVALID_ARGUMENT;
+    ZKB_DISPATCH_CURVE(curve, s = grid_points_t<CF>(ctx, n, m, dA, dB, out_device, st))
     ZKB_TRY(s);
     ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
     return ZKB_OK;
@@ -589,11 +588,7 @@ int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points
             return ctx_fail(ctx, ZKB_ERR_CUDA, std::string("copy MSM bases: ") + cudaGetErrorString(ce));
         }
         unsigned blocks = (unsigned)((n + 255) / 256);
-        switch (curve) {
-            case ZKB_CURVE_BLS12_381_G1: points_to_mont_kernel<params::Bls12381Fq><<<blocks, 256, 0, st>>>(n, (Affine<Fp<params::Bls12381Fq>> *)d); break;
-            case ZKB_CURVE_BN254_G1: points_to_mont_kernel<params::Bn254Fq><<<blocks, 256, 0, st>>>(n, (Affine<Fp<params::Bn254Fq>> *)d); break;
-            default: points_to_mont_kernel<params::PallasFp><<<blocks, 256, 0, st>>>(n, (Affine<Fp<params::PallasFp>> *)d); break;
-        }
+        ZKB_DISPATCH_CURVE(curve, points_to_mont_kernel<CF><<<blocks, 256, 0, st>>>(n, (Affine<CF> *)d))
         ctx->launches++;
         cudaError_t ke = cudaStreamSynchronize(st);
         if (ke != cudaSuccess) {
@@ -646,7 +641,7 @@ int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, u
 int zkb_msm(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
             uint32_t *result_affine, void *stream) {
     if (!ctx || !bases || !result_affine) return ZKB_ERR_INVALID_ARGUMENT;
-    uint32_t partial[4 * 12];
+    uint32_t partial[4 * 24];
     ZKB_TRY(zkb_msm_partial(ctx, bases, offset, n, scalars, mem, partial, stream));
     return zkb_msm_combine(bases->curve, 1, partial, result_affine);
 }

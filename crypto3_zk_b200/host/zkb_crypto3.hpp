@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/zkb200.h"
+#include "../csrc/zkb_field.cuh"   // Fp2<B> (generic over the base type; compiled for the host here)
 #include "../csrc/zkb_hostfield.h"
 
 namespace nil {
@@ -119,6 +120,41 @@ template <> struct alt_bn128_fq<254> : zkb_field<::zkb::params::Bn254Fq, ZKB_FIE
 struct pallas_base_field : zkb_field<::zkb::params::PallasFp, ZKB_FIELD_PALLAS_FP> {};
 struct pallas_scalar_field : zkb_field<::zkb::params::PallasFq, ZKB_FIELD_PALLAS_FQ> {};
 
+// Fq2 = Fq[u]/(u^2 + 1): coordinate field of the G2 groups (`fields::fp2<...>` upstream); canonical limbs
+// are c0 || c1.  Only what the group value type below needs.
+template <class BaseField>
+struct zkb_field2 {
+    typedef ::zkb::Fp2<typename BaseField::backend> backend;
+    typedef BaseField underlying_field_type;
+    static constexpr int limbs32 = 2 * BaseField::limbs32;
+    struct value_type {
+        typedef zkb_field2 field_type;
+        backend data;  // Montgomery form
+        value_type() : data(backend::zero()) {}
+        static value_type zero() { return value_type(); }
+        static value_type one() { value_type r; r.data = backend::one(); return r; }
+        static value_type from_canonical_limbs(const std::uint32_t *l) {
+            value_type r;
+            r.data.c0 = BaseField::backend::from_limbs32(l).to_mont();
+            r.data.c1 = BaseField::backend::from_limbs32(l + BaseField::limbs32).to_mont();
+            return r;
+        }
+        void to_canonical_limbs(std::uint32_t *l) const {
+            data.c0.from_mont().to_limbs32(l);
+            data.c1.from_mont().to_limbs32(l + BaseField::limbs32);
+        }
+        bool is_zero() const { return data.is_zero(); }
+        value_type operator+(const value_type &o) const { value_type r; r.data = data + o.data; return r; }
+        value_type operator-(const value_type &o) const { value_type r; r.data = data - o.data; return r; }
+        value_type operator*(const value_type &o) const { value_type r; r.data = data * o.data; return r; }
+        value_type operator-() const { value_type r; r.data = data.neg(); return r; }
+        bool operator==(const value_type &o) const { return data == o.data; }
+        bool operator!=(const value_type &o) const { return !(data == o.data); }
+        value_type inversed() const { value_type r; r.data = data.inverse(); return r; }
+        value_type squared() const { value_type r; r.data = data.sqr(); return r; }
+    };
+};
+
 // arithmetic_params<F>::multiplicative_generator as used for the coset shift (r1cs_to_qap.hpp:266-269)
 template <class FieldType>
 struct arithmetic_params {
@@ -153,7 +189,7 @@ struct zkb_curve_g1 {
         }
         // the group generator, `value_type::one()` in the reference (kzg.hpp:102,112)
         static value_type one() {
-            std::uint32_t l[24] = {0};
+            std::uint32_t l[48] = {0};
             zkb_curve_generator(CurveId, l);
             return from_affine(BaseField::value_type::from_canonical_limbs(l),
                                BaseField::value_type::from_canonical_limbs(l + BaseField::limbs32));
@@ -177,12 +213,15 @@ template <> struct bls12<381> {
     typedef fields::bls12_fq<381> base_field_type;
     typedef fields::bls12_fr<381> scalar_field_type;
     template <class...> using g1_type = zkb_curve_g1<base_field_type, scalar_field_type, ZKB_CURVE_BLS12_381_G1>;
+    // G2 over Fq2 (B_query of r1cs_gg_ppzksnark, prover.hpp:113-119; v-keys of ipp2): same Jacobian value type
+    template <class...> using g2_type = zkb_curve_g1<fields::zkb_field2<base_field_type>, scalar_field_type, ZKB_CURVE_BLS12_381_G2>;
 };
 template <std::size_t> struct alt_bn128;
 template <> struct alt_bn128<254> {
     typedef fields::alt_bn128_fq<254> base_field_type;
     typedef fields::alt_bn128_fr<254> scalar_field_type;
     template <class...> using g1_type = zkb_curve_g1<base_field_type, scalar_field_type, ZKB_CURVE_BN254_G1>;
+    template <class...> using g2_type = zkb_curve_g1<fields::zkb_field2<base_field_type>, scalar_field_type, ZKB_CURVE_BN254_G2>;
 };
 struct pallas {
     typedef fields::pallas_base_field base_field_type;
@@ -238,7 +277,7 @@ public:
         std::vector<std::uint32_t> sc(cnt * 8 + 8);
         std::size_t i = 0;
         for (ScalarIt it = s0; it != s1; ++it, ++i) it->to_canonical_limbs(&sc[8 * i]);
-        std::uint32_t res[2 * 12] = {0};
+        std::uint32_t res[2 * 24] = {0};
         zkb_ctx *ctx = zkb_detail::context();
         zkb_detail::check(zkb_msm(ctx, h, offset, cnt, sc.data(), ZKB_MEM_HOST, res, nullptr), ctx, "zkb_msm");
         bool inf = true;

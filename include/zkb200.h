@@ -50,7 +50,13 @@ typedef enum {
     ZKB_FIELD_BN254_FQ = 5      /* coordinate field, no NTT */
 } zkb_field;
 
-typedef enum { ZKB_CURVE_BLS12_381_G1 = 0, ZKB_CURVE_BN254_G1 = 1, ZKB_CURVE_PALLAS = 2 } zkb_curve;
+/* G2 groups (coordinates in Fq2 = Fq[u]/(u^2+1), limbs c0 || c1): the B_query / knowledge-commitment side of
+ * the Groth16 prover (r1cs_gg_ppzksnark/prover.hpp:113-119, knowledge_commitment_multiexp.hpp:107) and the
+ * G2 commitment keys of ipp2 (ipp2/prover.hpp:209-212). */
+typedef enum {
+    ZKB_CURVE_BLS12_381_G1 = 0, ZKB_CURVE_BN254_G1 = 1, ZKB_CURVE_PALLAS = 2,
+    ZKB_CURVE_BLS12_381_G2 = 3, ZKB_CURVE_BN254_G2 = 4
+} zkb_curve;
 
 typedef enum { ZKB_HASH_KECCAK_256 = 0, ZKB_HASH_SHA2_256 = 1, ZKB_HASH_KECCAK_512 = 2 } zkb_hash;
 

@@ -23,9 +23,15 @@ static int failures = 0;
         }                                                                    \
     } while (0)
 
+template <class Curve, bool G2>
+struct group_of { typedef typename Curve::template g1_type<> type; };
 template <class Curve>
+struct group_of<Curve, true> { typedef typename Curve::template g2_type<> type; };
+
+template <class Curve, bool G2 = false>
 static void kzg_basic_test() {
-    typedef typename Curve::template g1_type<> g1_type;
+    // G2 = true runs the same identities on g2_type (the group of B_query, prover.hpp:113-119)
+    typedef typename group_of<Curve, G2>::type g1_type;
     typedef typename Curve::scalar_field_type::value_type scalar_value_type;
     typedef typename g1_type::value_type g1_value_type;
     scalar_value_type alpha = 10u;
@@ -154,6 +160,8 @@ int main(int argc, char **argv) {
         kzg_basic_test<algebra::curves::bls12<381>>();
         kzg_basic_test<algebra::curves::alt_bn128<254>>();
         kzg_basic_test<algebra::curves::pallas>();
+        kzg_basic_test<algebra::curves::bls12<381>, true>();
+        kzg_basic_test<algebra::curves::alt_bn128<254>, true>();
         domain_and_fold_test<algebra::fields::bls12_fr<381>>();
         domain_and_fold_test<algebra::fields::alt_bn128_fr<254>>();
         domain_and_fold_test<algebra::fields::pallas_base_field>();

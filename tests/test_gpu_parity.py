@@ -247,7 +247,13 @@ def test_lpc_commit_many_polys_bls(ctx):
 
 # ------------------------------------------------------------------------------------------ MSM
 def enc_points(C, pts):
+    """Affine points -> [n, 2, coord_limbs] u32 (G2: every coordinate is c0 || c1)."""
     n = C.coord_limbs32
+    if isinstance(C.F.zero, tuple):
+        vals = []
+        for P in pts:
+            vals += [0, 0, 0, 0] if P is None else [P[0][0], P[0][1], P[1][0], P[1][1]]
+        return to_arr(vals, n // 2).reshape(len(pts), 2, n)
     vals = []
     for P in pts:
         vals += [0, 0] if P is None else [P[0], P[1]]
@@ -297,6 +303,53 @@ def test_msm_golden_bellperson_vectors(ctx):
         srs = [C.mul(C.gen, pow(s, i, p)) for i in range(2 * n)]
         b = ctx.msm_bases(C.name, enc_points(C, srs))
         assert ctx.multiexp(b, to_arr(quo)) == (_i(exp[0]), _i(exp[1]))
+    # prove_commitment_v: the same on G2 (f_v with r_shift = 1 over h^(alpha^i), conformity.cpp:876-892)
+    C2 = curves.BLS12_381_G2
+    co, pw = [1], 1
+    for x in tr:
+        co += [cc * (x * pw % p) % p for cc in co]
+        pw = pw * pw % p
+    quo_v, carry = [0] * n, 0
+    for i in range(n - 1, 0, -1):
+        carry = (co[i] + carry * z) % p
+        quo_v[i - 1] = carry
+    for s, exp in ((alpha, pc["comm_v"][0]), (beta, pc["comm_v"][1])):
+        srs = [C2.mul(C2.gen, pow(s, i, p)) for i in range(n)]
+        b = ctx.msm_bases(C2.name, enc_points(C2, srs))
+        want = ((_i(exp[0][0]), _i(exp[0][1])), (_i(exp[1][0]), _i(exp[1][1])))
+        assert ctx.multiexp(b, to_arr(quo_v)) == want
+
+
+@pytest.mark.parametrize("C", [curves.BLS12_381_G2, curves.BN254_G2], ids=lambda c: c.name)
+def test_msm_g2_vs_oracle(ctx, C):
+    """G2 MSM (B_query of the Groth16 prover, prover.hpp:113-119; ipp2 v-keys): random points, special
+    scalars, repeated / opposite / infinite points, sub-ranges, 0/1-heavy assignments."""
+    r = C.scalar_field.p
+    rnd = random.Random(5)
+    for n in (1, 3, 64, 700):
+        pts = C.random_points(n, 30 + n)
+        sc = fields.random_elements(C.scalar_field, n, 40 + n)
+        b = ctx.msm_bases(C.name, enc_points(C, pts))
+        assert ctx.multiexp(b, to_arr(sc)) == C.msm_bdlo12(pts, sc)
+        if n >= 64:
+            assert ctx.multiexp(b, to_arr(sc[5:25]), offset=5, n=20) == C.msm_naive(pts[5:25], sc[5:25])
+    pts = C.random_points(12, 9)
+    P, Q = pts[0], pts[1]
+    pts2 = [P] * 5 + [C.neg(P), None, Q, None, P]
+    sc2 = [5, 5, 7, 1, r - 1, 5, 9, 3, 0, (1 << 254) % r]
+    b2 = ctx.msm_bases(C.name, enc_points(C, pts2))
+    assert ctx.multiexp(b2, to_arr(sc2)) == C.msm_naive(pts2, sc2)
+    b3 = ctx.msm_bases(C.name, enc_points(C, [P, C.neg(P)]))
+    assert ctx.multiexp(b3, to_arr([77, 77])) is None
+    n = 1200
+    ptsn = C.random_points(n, 8)
+    scn = [rnd.choice([0, 1, 1, 1, rnd.randrange(r)]) for _ in range(n)]
+    bn = ctx.msm_bases(C.name, enc_points(C, ptsn))
+    assert ctx.multiexp(bn, to_arr(scn)) == C.msm_with_mixed_addition(ptsn, scn)
+    from crypto3_zk_b200 import msm_combine
+    p0 = ctx.multiexp_partial(bn, to_arr(scn[:500]), offset=0, n=500)
+    p1 = ctx.multiexp_partial(bn, to_arr(scn[500:]), offset=500, n=700)
+    assert msm_combine(C.name, [p0, p1]) == C.msm_with_mixed_addition(ptsn, scn)
 
 
 @pytest.mark.parametrize("C", [curves.BLS12_381_G1, curves.BN254_G1, curves.PALLAS], ids=lambda c: c.name)
