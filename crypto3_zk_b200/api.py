@@ -114,6 +114,13 @@ class MsmBases:
                                                    ctypes.byref(h)), ctx._h)
         self._h, self.n, self.coord_limbs, self.deg = h, n, cl, self.curve.deg
 
+    def precompute(self, window_bits=0, max_bytes=8 << 30, stream=None):
+        """Builds the window table 2^(c w) P_i once (zkb_msm_bases_precompute): later multiexps over these
+        bases use ceil((bits+1)/c) windows that share one bucket set.  Returns self."""
+        capi.check(capi.lib().zkb_msm_bases_precompute(self._ctx._h, self._h, window_bits, max_bytes,
+                                                       _stream_ptr(None, stream)), self._ctx._h)
+        return self
+
     def free(self):
         if self._h:
             capi.lib().zkb_msm_bases_free(self._h)

@@ -39,6 +39,10 @@ struct zkb_msm_bases {
     int curve;
     uint64_t n;
     void *d_points;  // Affine<F>, Montgomery form
+    // optional window table (zkb_msm_bases_precompute): table[w * n + i] = 2^(table_c * w) * P_i, affine,
+    // Montgomery form, w < table_w; window 0 is d_points itself when table == nullptr
+    void *d_table = nullptr;
+    int table_c = 0, table_w = 0;
 };
 
 // coordinate fields of the supported groups
@@ -58,6 +62,7 @@ typedef Fp2<FqBn> Fq2Bn;
     }
 
 #define MSM_TASK_CAP 256u
+#define MSM_HEAVY_MIN_TASKS 8u
 #define MSM_SENTINEL 0xffffffffu
 #define MSM_LEVEL_BITS 5
 
@@ -69,8 +74,10 @@ __global__ void __launch_bounds__(256) points_to_mont_kernel(uint64_t n, Affine<
 }
 
 // scalars: 8 canonical limbs each.  keys[w * n + i]
+// win_stride = buckets per window (2^(c-1)), or 0 when all windows share one bucket set (window table)
 __global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint32_t *__restrict__ scalars, int c, int W,
-                                                         uint32_t *__restrict__ keys, uint32_t *__restrict__ counts) {
+                                                         uint32_t win_stride, uint32_t *__restrict__ keys,
+                                                         uint32_t *__restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4 *sp = reinterpret_cast<const uint4 *>(scalars) + 2 * (uint64_t)i;
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint3
                 carry = 1;
             }
             if (mag != 0) {
-                uint32_t bucket = (uint32_t)w * half + (mag - 1);
+                uint32_t bucket = (uint32_t)w * win_stride + (mag - 1);
                 key = (bucket << 1) | neg;
                 atomicAdd(counts + bucket, 1u);
             }
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint3
     }
 }
 
-// tasks per bucket from the bucket sizes; buckets that need more than one task are listed in `heavy`
+// tasks per bucket from the bucket sizes; buckets split into more than MSM_HEAVY_MIN_TASKS tasks are listed in `heavy`
 __global__ void __launch_bounds__(256) msm_ntasks_kernel(uint32_t nb, const uint32_t *__restrict__ counts,
                                                          uint32_t *__restrict__ ntasks, uint32_t *__restrict__ n_heavy,
                                                          uint32_t *__restrict__ heavy, uint32_t heavy_cap) {
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(256) msm_ntasks_kernel(uint32_t nb, const uint
     if (b >= nb) return;
     uint32_t nt = (counts[b] + MSM_TASK_CAP - 1) / MSM_TASK_CAP;
     ntasks[b] = nt;
-    if (nt > 1) {
+    if (nt > MSM_HEAVY_MIN_TASKS) {   // a few tasks are added serially by the level-0 reduce
         uint32_t k = atomicAdd(n_heavy, 1u);
         if (k < heavy_cap) heavy[k] = b;
     }
@@ -207,7 +214,9 @@ __global__ void __launch_bounds__(256) msm_fill_tasks_kernel(uint32_t nb, const 
     }
 }
 
-__global__ void __launch_bounds__(256) msm_scatter_kernel(uint64_t total, uint32_t n, const uint32_t *__restrict__ keys,
+// pt_stride = 0: every window reads the same n points; window table: window w reads points [w * pt_stride, ..)
+__global__ void __launch_bounds__(256) msm_scatter_kernel(uint64_t total, uint32_t n, uint32_t pt_stride,
+                                                          const uint32_t *__restrict__ keys,
                                                           const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
                                                           uint32_t *__restrict__ sorted) {
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(uint64_t total, uint32
     uint32_t key = keys[idx];
     if (key == MSM_SENTINEL) return;
     uint32_t bucket = key >> 1;
-    uint32_t i = (uint32_t)(idx % n);
+    uint32_t i = (uint32_t)(idx % n) + (uint32_t)(idx / n) * pt_stride;
     uint32_t pos = atomicAdd(cursor + bucket, 1u);
     sorted[offsets[bucket] + pos] = (i << 1) | (key & 1);
 }
@@ -418,10 +427,15 @@ template <class F, int SCALAR_BITS>
 static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
                      uint32_t *partial_host, cudaStream_t st) {
     typedef XYZZ<F> Pt;
-    const int c = msm_pick_c(n);
-    const int W = (SCALAR_BITS + 1 + c - 1) / c;
+    // with a window table every digit window adds 2^(c w) P_i straight into ONE bucket set
+    const bool tabled = bases->d_table != nullptr;
+    const int c = tabled ? bases->table_c : msm_pick_c(n);
+    const int W = (SCALAR_BITS + 1 + c - 1) / c;        // digit windows
+    const int WB = tabled ? 1 : W;                      // bucket sets
     const uint32_t M = 1u << (c - 1);
-    const uint32_t nb = (uint32_t)W * M;
+    const uint32_t nb = (uint32_t)WB * M;
+    if (tabled && (W > bases->table_w || (uint64_t)W * bases->n >= (1ull << 31)))
+        return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "MSM: window table does not cover the scalar width");
     const uint64_t total_keys = (uint64_t)W * n;
     if (n >= (1ull << 31) || total_keys >= (1ull << 32))
         return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "MSM: W*n must be < 2^32 (split the range across calls/GPUs)");
@@ -436,13 +450,13 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     size_t o_bsums = carve(((size_t)nb / 1024 + 2) * 4), o_totals = carve(16);
     size_t o_tasks = carve(max_tasks * sizeof(MsmTask)), o_tout = carve(max_tasks * sizeof(Pt));
     size_t o_perm = carve(max_tasks * 4), o_bins = carve(3 * MSM_TASK_CAP * 4);
-    // at most total_keys / CAP buckets can hold more than CAP points
+    // at most total_keys / CAP buckets can hold more than CAP points (the list is a superset bound)
     const uint32_t heavy_cap = (uint32_t)(total_keys / MSM_TASK_CAP + 1);
     size_t o_heavy = carve((size_t)(heavy_cap + 1) * 4);
     // reduce tree: level l holds W * ceil(M / L^(l+1)) (A, U) pairs; two ping-pong buffers of the level-0 size
     const uint32_t n_lvl0 = (M + MSM_RED_L - 1) >> MSM_RED_LOG_L;
-    size_t o_red = carve((size_t)4 * W * n_lvl0 * sizeof(Pt));
-    size_t o_S = carve((size_t)W * sizeof(Pt));
+    size_t o_red = carve((size_t)4 * WB * n_lvl0 * sizeof(Pt));
+    size_t o_S = carve((size_t)WB * sizeof(Pt));
     void *base;
     ZKB_TRY(ctx_scratch(ctx, "msm", off, &base));
     char *B = (char *)base;
@@ -459,15 +473,15 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     // counts and cursor are adjacent carve-outs: one memset
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(cursor, 0, (size_t)nb * 4, st));
-    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, (const uint32_t *)d_scalars, c, W, keys, counts);
+    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, (const uint32_t *)d_scalars, c, W, tabled ? 0u : M, keys, counts);
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(n_heavy, 0, 4, st));
     msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, ntasks, n_heavy, heavy, heavy_cap);
     ctx->launches += 2;
     ZKB_TRY(exclusive_scan(ctx, nb, counts, offsets, bsums, totals, st));
     ZKB_TRY(exclusive_scan(ctx, nb, ntasks, toffs, bsums, totals + 1, st));
     msm_fill_tasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, offsets, toffs, tasks);
-    msm_scatter_kernel<<<(unsigned)((total_keys + 255) / 256), 256, 0, st>>>(total_keys, (uint32_t)n, keys, offsets, cursor, sorted);
-    const Affine<F> *pts = (const Affine<F> *)bases->d_points + offset;
+    msm_scatter_kernel<<<(unsigned)((total_keys + 255) / 256), 256, 0, st>>>(total_keys, (uint32_t)n, tabled ? (uint32_t)bases->n : 0u, keys, offsets, cursor, sorted);
+    const Affine<F> *pts = (const Affine<F> *)(tabled ? bases->d_table : bases->d_points) + offset;
     const unsigned task_blocks = (unsigned)((max_tasks + 255) / 256);
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(bins, 0, MSM_TASK_CAP * 4, st));
     msm_task_hist_kernel<<<task_blocks, 256, 0, st>>>(totals + 1, tasks, bins);
@@ -479,19 +493,19 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     {
         uint32_t n_in = M;
         int span_bits = 0, level = 0;
-        const size_t half = (size_t)2 * W * n_lvl0;   // elements per ping-pong buffer (A then U)
+        const size_t half = (size_t)2 * WB * n_lvl0;   // elements per ping-pong buffer (A then U)
         while (true) {
             uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
             Pt *src = red + (size_t)((level + 1) & 1) * half, *dst = red + (size_t)(level & 1) * half;
-            const Pt *inA = level == 0 ? tout : src, *inU = level == 0 ? nullptr : src + (size_t)W * n_lvl0;
+            const Pt *inA = level == 0 ? tout : src, *inU = level == 0 ? nullptr : src + (size_t)WB * n_lvl0;
             const bool root = n_out == 1;
-            uint32_t cnt = (uint32_t)W * n_out;
+            uint32_t cnt = (uint32_t)WB * n_out;
             if (level == 0)
-                msm_reduce_level_kernel<F, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
-                                                                                   root ? S : dst, dst + (size_t)W * n_lvl0);
+                msm_reduce_level_kernel<F, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, toffs, ntasks, inA, inU,
+                                                                                   root ? S : dst, dst + (size_t)WB * n_lvl0);
             else
-                msm_reduce_level_kernel<F, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(W, n_in, span_bits, root, toffs, ntasks, inA, inU,
-                                                                                   root ? S : dst, dst + (size_t)W * n_lvl0);
+                msm_reduce_level_kernel<F, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, toffs, ntasks, inA, inU,
+                                                                                   root ? S : dst, dst + (size_t)WB * n_lvl0);
             ctx->launches++;
             if (root) break;
             n_in = n_out;
@@ -500,10 +514,10 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
         }
     }
     ZKB_CUDA_OK(ctx, cudaGetLastError());
-    std::vector<uint32_t> hs((size_t)W * 4 * F::N);
+    std::vector<uint32_t> hs((size_t)WB * 4 * F::N);
     ZKB_CUDA_OK(ctx, cudaMemcpyAsync(hs.data(), S, hs.size() * 4, cudaMemcpyDeviceToHost, st));
     ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    return msm_window_combine(bases->curve, c, W, hs.data(), partial_host);
+    return msm_window_combine(bases->curve, c, WB, hs.data(), partial_host);
 }
 
 static int msm_run(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
@@ -537,6 +551,52 @@ static int grid_points_t(zkb_ctx *ctx, uint64_t n, uint32_t m, const void *dA, c
     grid_points_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, m, (const A *)dA, (const A *)dB, (A *)dout);
     ctx->launches++;
     ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------------------------ window table
+// table[w * n + i] = 2^(c w) P_i for w = 1 .. W-1 (affine, Montgomery form; row 0 is a copy of the bases).
+// A commitment key / proving-key query vector is long-lived, so this is paid once: afterwards every digit
+// window of an MSM adds into the same 2^(c-1) buckets (no per-window bucket sets, no window combine) and c
+// can be as large as log2 n, which cuts the number of windows W = ceil((bits+1)/c).
+template <class F>
+__global__ void __launch_bounds__(128) msm_table_kernel(uint64_t n, int c, int W, const Affine<F> *__restrict__ pts,
+                                                        Affine<F> *__restrict__ table) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = pts[i];
+    table[i] = p;
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    for (int w = 1; w < W; w++) {
+        for (int k = 0; k < c; k++) acc = acc.dbl();
+        p = acc.to_affine();                 // one inversion per point and window (setup cost)
+        table[(uint64_t)w * n + i] = p;
+        acc = XYZZ<F>::from_affine(p);       // keep ZZ = ZZZ = 1: the next c doublings start cheap
+    }
+}
+
+template <class F, int SCALAR_BITS>
+static int msm_table_t(zkb_ctx *ctx, zkb_msm_bases *b, int c, uint64_t max_bytes, cudaStream_t st) {
+    const int W = (SCALAR_BITS + 1 + c - 1) / c;
+    const uint64_t bytes = (uint64_t)W * b->n * sizeof(Affine<F>);
+    if (bytes > max_bytes || (uint64_t)W * b->n >= (1ull << 31))
+        return ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, "zkb_msm_bases_precompute: table exceeds max_bytes");
+    void *t = nullptr;
+    cudaError_t e = cudaMalloc(&t, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, "cudaMalloc MSM window table");
+    }
+    msm_table_kernel<F><<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(b->n, c, W, (const Affine<F> *)b->d_points, (Affine<F> *)t);
+    ctx->launches++;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(t);
+        return ctx_fail(ctx, ZKB_ERR_CUDA, std::string("msm_table_kernel: ") + cudaGetErrorString(e));
+    }
+    b->d_table = t;
+    b->table_c = c;
+    b->table_w = W;
     return ZKB_OK;
 }
 
@@ -607,14 +667,32 @@ int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points
 
 void zkb_msm_bases_free(zkb_msm_bases *b) {
     if (!b) return;
-    if (b->d_points) {
+    if (b->d_points || b->d_table) {
         cudaSetDevice(b->ctx->device);
-        cudaFree(b->d_points);
+        if (b->d_points) cudaFree(b->d_points);
+        if (b->d_table) cudaFree(b->d_table);
     }
     delete b;
 }
 
 uint64_t zkb_msm_bases_size(const zkb_msm_bases *b) { return b ? b->n : 0; }
+
+int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *b, int window_bits, uint64_t max_bytes, void *stream) {
+    if (!ctx || !b || b->ctx != ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (b->d_table || b->n == 0) return ZKB_OK;
+    int c = window_bits;
+    if (c == 0) {   // one bucket per ~2 points of a full-length MSM
+        c = 1;
+        while ((1ull << c) < b->n) c++;
+        if (c < 8) c = 8;
+        if (c > 22) c = 22;
+    }
+    if (c < 2 || c > 24) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_msm_bases_precompute: window_bits out of range");
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ZKB_DISPATCH_CURVE(b->curve, return msm_table_t<CF, SB>(ctx, b, c, max_bytes, st))
+    return ZKB_ERR_INVALID_ARGUMENT;
+}
 
 int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
                     uint32_t *partial_xyzz_host, void *stream) {

@@ -266,6 +266,11 @@ public:
     multiexp_bases(multiexp_bases &&o) noexcept : h(o.h), n(o.n) { o.h = nullptr; }
     ~multiexp_bases() { if (h) zkb_msm_bases_free(h); }
     std::size_t size() const { return n; }
+    // one-off window table for a key that serves many multiexps (zkb_msm_bases_precompute)
+    void precompute(int window_bits = 0, std::uint64_t max_bytes = 8ull << 30) {
+        zkb_ctx *ctx = zkb_detail::context();
+        zkb_detail::check(zkb_msm_bases_precompute(ctx, h, window_bits, max_bytes, nullptr), ctx, "zkb_msm_bases_precompute");
+    }
 
     // sum_i scalars[i] * bases[offset + i]
     template <class ScalarIt>

@@ -7,7 +7,7 @@
 import numpy as np
 
 from .api import msm_combine
-from .fields import CURVE_BY_NAME, FIELD_BY_NAME
+from .fields import CURVE_BY_NAME, coord_limbs
 
 
 def shard_range(n, rank, world):
@@ -26,7 +26,7 @@ def allgather_combine(curve, partial, group=None, device=None):
     import torch
     import torch.distributed as dist
     c = CURVE_BY_NAME[curve] if isinstance(curve, str) else curve
-    words = 4 * FIELD_BY_NAME[c.base_field].limbs32
+    words = 4 * coord_limbs(c)
     p = np.ascontiguousarray(partial, dtype=np.uint32).reshape(words)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return msm_combine(c, p.reshape(1, words))

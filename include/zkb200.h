@@ -157,6 +157,13 @@ int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points
                          zkb_msm_bases **out);
 void zkb_msm_bases_free(zkb_msm_bases *bases);
 uint64_t zkb_msm_bases_size(const zkb_msm_bases *bases);
+/* Optional, once per base vector: builds the window table 2^(c w) * P_i (w < ceil((bits+1)/c)) next to the
+ * bases so that later zkb_msm / zkb_msm_partial calls on them add every digit window into one bucket set.
+ * Same results, fewer windows; costs ceil((bits+1)/c) times the memory of the bases and one inversion per
+ * point and window.  window_bits = 0 picks c = log2 n (clamped to [8, 22]); fails with ZKB_ERR_OUT_OF_MEMORY
+ * (bases stay usable) when the table would exceed max_bytes.  For a commitment key that serves many commits
+ * (kzg.hpp:100-118 builds it once per params_type). */
+int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *bases, int window_bits, uint64_t max_bytes, void *stream);
 /* result = sum_{i<n} scalars[i] * bases[offset+i]; scalars canonical limbs of the curve's scalar field;
  * result_affine: host buffer, (x||y) canonical limbs, all-zero for infinity.  Zero scalars are skipped and
  * unit scalars cost one mixed addition, so multiexp and multiexp_with_mixed_addition map to the same call. */

@@ -51,6 +51,8 @@ def main():
             tabs[i, 1] = [(pt[1] >> (32 * k)) & 0xFFFFFFFF for k in range(12)]
         pts = ctx.grid_points("bls12_381_g1", nm, tabs[:m], tabs[m:])
         bases = ctx.msm_bases("bls12_381_g1", pts)
+        if len(sys.argv) > 3:          # window table with this many bits (0 = automatic)
+            bases.precompute(int(sys.argv[3]), 64 << 30)
         sc = rand((nm, 8), 13)
         fn = lambda: ctx.multiexp(bases, sc)
     else:

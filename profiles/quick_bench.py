@@ -46,7 +46,7 @@ def msm_setup(ctx, curve, log_m):
         tabs[i, 0] = [(pt[0] >> (32 * k)) & 0xFFFFFFFF for k in range(cl)]
         tabs[i, 1] = [(pt[1] >> (32 * k)) & 0xFFFFFFFF for k in range(cl)]
     pts = ctx.grid_points(curve, nm, tabs[:m], tabs[m:])
-    return ctx.msm_bases(curve, pts), rand((nm, 8), 13)
+    return ctx.msm_bases(curve, pts), rand((nm, 8), 13), pts
 
 
 def main():
@@ -79,8 +79,12 @@ def main():
         elif w.startswith("msm"):
             lg = int(w[3:])
             curve = "bls12_381_g1"
-            bases, sc = msm_setup(ctx, curve, lg)
+            bases, sc, pts = msm_setup(ctx, curve, lg)
             out["%s_%s_ms" % (w, curve)] = tcuda(lambda: ctx.multiexp(bases, sc), 5, 2)
+            for wb in [int(x) for x in os.environ.get("MSM_TABLE_BITS", "").split(",") if x]:
+                bt = ctx.msm_bases(curve, pts).precompute(wb, 64 << 30)
+                out["%s_%s_table%d_ms" % (w, curve, wb)] = tcuda(lambda: ctx.multiexp(bt, sc), 5, 2)
+                bt.free()
             bases.free()
     ctx.close()
     print(json.dumps(out))

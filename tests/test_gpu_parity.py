@@ -362,6 +362,14 @@ def test_msm_vs_oracle(ctx, C, n):
     # sub-range of resident bases (prover.hpp:133-139 passes iterator sub-ranges)
     if n >= 7:
         assert ctx.multiexp(b, to_arr(sc[2:6]), offset=2, n=4) == C.msm_naive(pts[2:6], sc[2:6])
+    # the same through a window table (zkb_msm_bases_precompute), default and explicit window sizes
+    want = C.msm_bdlo12(pts, sc)
+    for wb in (0, 5, 11):
+        bt = ctx.msm_bases(C.name, enc_points(C, pts)).precompute(wb)
+        assert ctx.multiexp(bt, to_arr(sc)) == want
+        if n >= 7:
+            assert ctx.multiexp(bt, to_arr(sc[2:6]), offset=2, n=4) == C.msm_naive(pts[2:6], sc[2:6])
+        bt.free()
 
 
 @pytest.mark.parametrize("C", [curves.BLS12_381_G1, curves.BN254_G1, curves.PALLAS], ids=lambda c: c.name)
@@ -399,7 +407,7 @@ def test_msm_edge_cases(ctx, C):
 
 
 
-def _grid_msm_case(ctx, C, log_n, scalars_fn, seed):
+def _grid_msm_case(ctx, C, log_n, scalars_fn, seed, table=0):
     """MSM over n = 2^log_n grid points P_i = A[i % m] + B[i / m] (built on the device) checked through the
     size-independent identity  sum s_i P_i = sum_a (sum_{i%m=a} s_i) A_a + sum_b (sum_{i/m=b} s_i) B_b,
     whose right-hand side is an (m + n/m)-point MSM the oracle does on the CPU."""
@@ -422,6 +430,14 @@ def _grid_msm_case(ctx, C, log_n, scalars_fn, seed):
     for k in range(8):
         arr[:, k] = [(v >> (32 * k)) & 0xFFFFFFFF for v in sc]
     got = ctx.multiexp(bases, dev(arr))
+    if table:   # same sum through the window table, whole range and a sub-range that starts inside it
+        bases.precompute(table)
+        assert ctx.multiexp(bases, dev(arr)) == got
+        h = n // 2 + 3
+        from crypto3_zk_b200 import msm_combine
+        p0 = ctx.multiexp_partial(bases, dev(arr[:h]), offset=0, n=h)
+        p1 = ctx.multiexp_partial(bases, dev(arr[h:]), offset=h, n=n - h)
+        assert msm_combine(C.name, [p0, p1]) == got
     sa, sb = [0] * m, [0] * nb
     for i, v in enumerate(sc):
         sa[i % m] += v
@@ -444,7 +460,7 @@ def test_msm_large_grid_identity(ctx, kind):
         "zero_one": lambda n, rnd, r: [rnd.choice([0, 1, 1, 1, 1, 1, 1, rnd.randrange(r)]) for _ in range(n)],
         "top_window": lambda n, rnd, r: [((rnd.randrange(7) << 252) + 99) % r for _ in range(n)],
     }
-    _grid_msm_case(ctx, C, 20 if kind == "uniform" else 17, fns[kind], 77)
+    _grid_msm_case(ctx, C, 20 if kind == "uniform" else 17, fns[kind], 77, table={"uniform": 20, "all_equal": 13}.get(kind, 17))
 
 
 def test_kzg_commit_identity_2p16(ctx):
