@@ -18,6 +18,7 @@
 // in the data, so vectors go to the device as they are (Montgomery in, Montgomery out, no conversion
 // pass); MSM scalars/points and Merkle-leaf inputs are converted to the ABI's canonical form on the way in.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -514,6 +515,73 @@ math::polynomial_dfs<typename FieldType::value_type> fold_polynomial(math::polyn
     return math::polynomial_dfs<V>(domain->size() / 2 - 1, std::move(out));
 }
 }  // namespace detail
+
+// ---- knowledge commitments (Groth16 B_query: pairs (G2, G1) that share one scalar) ----------------------
+}  // namespace commitments
+}  // namespace zk
+namespace container {
+// crypto3-containers' sparse_vector as the call sites use it (indices sorted ascending, values aligned)
+template <class T>
+struct sparse_vector {
+    std::vector<std::size_t> indices;
+    std::vector<typename T::value_type> values;
+    std::size_t domain_size_ = 0;
+    std::size_t size() const { return indices.size(); }
+};
+}  // namespace container
+namespace zk {
+namespace commitments {
+namespace detail {
+// element_kc<T1, T2> (detail/polynomial/element_knowledge_commitment.hpp:54-186): the pair (g, h)
+template <class T1, class T2>
+struct element_kc {
+    typename T1::value_type g;
+    typename T2::value_type h;
+    element_kc() : g(T1::value_type::zero()), h(T2::value_type::zero()) {}
+    element_kc(const typename T1::value_type &g_, const typename T2::value_type &h_) : g(g_), h(h_) {}
+    static element_kc zero() { return element_kc(); }
+    bool is_zero() const { return g.is_zero() && h.is_zero(); }
+    bool operator==(const element_kc &o) const { return g == o.g && h == o.h; }
+    bool operator!=(const element_kc &o) const { return !(*this == o); }
+};
+}  // namespace detail
+template <class T1, class T2>
+struct knowledge_commitment {
+    typedef T1 type1;
+    typedef T2 type2;
+    typedef detail::element_kc<T1, T2> value_type;
+};
+template <class T1, class T2>
+using knowledge_commitment_vector = container::sparse_vector<knowledge_commitment<T1, T2>>;
+
+// kc_multiexp_with_mixed_addition (knowledge_commitment_multiexp.hpp:57-108): the entries of `vec` whose
+// index lies in [min_idx, max_idx) take the scalar scalar_start[index - min_idx]; upstream skips zero
+// scalars, adds unit scalars directly and runs multiexp<Method> over the rest on the (g, h) pairs.  Here the
+// same selection feeds two device MSMs (one per group) that share the gathered scalars; zero digits are
+// skipped and a unit scalar is a single mixed addition on the device.
+template <class MultiexpMethod, class T1, class T2, class InputFieldIterator>
+typename knowledge_commitment<T1, T2>::value_type kc_multiexp_with_mixed_addition(
+    const knowledge_commitment_vector<T1, T2> &vec, const std::size_t min_idx, const std::size_t max_idx,
+    InputFieldIterator scalar_start, InputFieldIterator scalar_end, const std::size_t chunks) {
+    typedef typename std::iterator_traits<InputFieldIterator>::value_type field_value_type;
+    const std::size_t scalar_length = (std::size_t)std::distance(scalar_start, scalar_end);
+    if (scalar_length > vec.domain_size_) throw std::invalid_argument("kc_multiexp: more scalars than the vector's domain");
+    auto index_it = std::lower_bound(vec.indices.begin(), vec.indices.end(), min_idx);
+    auto value_it = vec.values.begin() + (index_it - vec.indices.begin());
+    std::vector<field_value_type> p;
+    std::vector<typename T1::value_type> g;
+    std::vector<typename T2::value_type> h;
+    for (; index_it != vec.indices.end() && *index_it < max_idx; ++index_it, ++value_it) {
+        const std::size_t scalar_position = *index_it - min_idx;
+        if (scalar_position >= scalar_length) throw std::invalid_argument("kc_multiexp: index outside the scalar range");
+        p.push_back(*(scalar_start + scalar_position));
+        g.push_back(value_it->g);
+        h.push_back(value_it->h);
+    }
+    return typename knowledge_commitment<T1, T2>::value_type(
+        algebra::multiexp<MultiexpMethod>(g.begin(), g.end(), p.begin(), p.end(), chunks),
+        algebra::multiexp<MultiexpMethod>(h.begin(), h.end(), p.begin(), p.end(), chunks));
+}
 
 // the precommitment (containers::merkle_tree<Hash,2>) kept on the device
 template <int HashId>

@@ -23,6 +23,41 @@ static int failures = 0;
         }                                                                    \
     } while (0)
 
+
+// knowledge_commitment_multiexp.hpp:57-108 on (G2, G1) pairs, the shape of the Groth16 B_query
+// (r1cs_gg_ppzksnark/prover.hpp:113-119): sparse indices, a [min, max) window, zero and unit scalars.
+template <class Curve>
+static void kc_multiexp_test() {
+    typedef typename Curve::template g1_type<> g1_type;
+    typedef typename Curve::template g2_type<> g2_type;
+    typedef typename Curve::scalar_field_type::value_type fr;
+    typedef zk::commitments::knowledge_commitment<g2_type, g1_type> kc;
+    zk::commitments::knowledge_commitment_vector<g2_type, g1_type> vec;
+    std::vector<typename g1_type::value_type> gen1 = {g1_type::value_type::one()};
+    std::vector<typename g2_type::value_type> gen2 = {g2_type::value_type::one()};
+    algebra::multiexp_bases<g1_type> G1(gen1.begin(), gen1.end());
+    algebra::multiexp_bases<g2_type> G2(gen2.begin(), gen2.end());
+    auto mul1 = [&](std::uint64_t k) { std::vector<fr> s = {fr(k)}; return G1.multiexp(0, s.begin(), s.end()); };
+    auto mul2 = [&](std::uint64_t k) { std::vector<fr> s = {fr(k)}; return G2.multiexp(0, s.begin(), s.end()); };
+    // value at index i: (i+2) * G2, (3i+1) * G1 ; indices 1, 2, 5, 6, 9, 12 of a domain of 16
+    const std::size_t idx[] = {1, 2, 5, 6, 9, 12};
+    for (std::size_t i : idx) {
+        vec.indices.push_back(i);
+        vec.values.push_back(typename kc::value_type(mul2(i + 2), mul1(3 * i + 1)));
+    }
+    vec.domain_size_ = 16;
+    // scalars for positions min_idx .. : window [2, 10) -> indices 2, 5, 6, 9 with scalars s[0], s[3], s[4], s[7]
+    std::vector<fr> s = {fr(7u), fr(100u), fr(100u), fr(0u), fr(1u), fr(100u), fr(100u), fr(5u)};
+    auto r = zk::commitments::kc_multiexp_with_mixed_addition<algebra::policies::multiexp_method_BDLO12>(vec, 2, 10, s.begin(), s.end(), 1);
+    // expected: g = 7*(2+2) + 0*(5+2) + 1*(6+2) + 5*(9+2) = 91 ; h = 7*7 + 0 + 1*19 + 5*28 = 208
+    CHECK(r.g == mul2(91));
+    CHECK(r.h == mul1(208));
+    CHECK(!(r == kc::value_type::zero()));
+    // empty window -> zero
+    auto z = zk::commitments::kc_multiexp_with_mixed_addition<algebra::policies::multiexp_method_BDLO12>(vec, 3, 5, s.begin(), s.begin() + 2, 1);
+    CHECK(z.is_zero());
+}
+
 template <class Curve, bool G2>
 struct group_of { typedef typename Curve::template g1_type<> type; };
 template <class Curve>
@@ -162,6 +197,8 @@ int main(int argc, char **argv) {
         kzg_basic_test<algebra::curves::pallas>();
         kzg_basic_test<algebra::curves::bls12<381>, true>();
         kzg_basic_test<algebra::curves::alt_bn128<254>, true>();
+        kc_multiexp_test<algebra::curves::bls12<381>>();
+        kc_multiexp_test<algebra::curves::alt_bn128<254>>();
         domain_and_fold_test<algebra::fields::bls12_fr<381>>();
         domain_and_fold_test<algebra::fields::alt_bn128_fr<254>>();
         domain_and_fold_test<algebra::fields::pallas_base_field>();

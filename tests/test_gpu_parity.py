@@ -178,6 +178,48 @@ def test_vec_ops(ctx):
     assert from_arr(host(got)) == [(x * y - z) * s % F.p for x, y, z in zip(a, b, c)]
 
 
+@pytest.mark.parametrize("F", [fields.BN254_FR, fields.BLS12_381_FR], ids=lambda f: f.name)
+def test_witness_map_flow_vs_oracle(ctx, F):
+    """r1cs_to_qap<F>::witness_map (zk/snark/reductions/r1cs_to_qap.hpp:219-325), the FFT part of the Groth16
+    prover: 3 iFFT, 3 coset FFT, A o B - C, divide_by_z_on_coset, coset iFFT, on the device in the reference's
+    order of operations, against the oracle's literal restatement.  Evaluation vectors stay on the device."""
+    from crypto3_zk_b200 import capi
+    p, g = F.p, F.g
+    for log_m in (6, 11):
+        m = 1 << log_m
+        aA, aB, aC = (fields.random_elements(F, m, 50 + k + log_m) for k in range(3))
+        d1, d2, d3 = fields.random_elements(F, 3, 60 + log_m)
+        # ---- oracle (CPU)
+        dom = ntt.EvaluationDomain(F, m)
+        oA, oB, oC = list(aA), list(aB), list(aC)
+        dom.inverse_fft(oA)
+        dom.inverse_fft(oB)
+        coeffs = [(d2 * x + d1 * y) % p for x, y in zip(oA, oB)] + [0]
+        coeffs[0] = (coeffs[0] - d3) % p
+        dom.add_poly_z(d1 * d2 % p, coeffs)
+        oA, oB = ntt.coset_fft(oA, F, g), ntt.coset_fft(oB, F, g)
+        dom.inverse_fft(oC)
+        oC = ntt.coset_fft(oC, F, g)
+        H = [(x * y - z) % p for x, y, z in zip(oA, oB, oC)]
+        dom.divide_by_z_on_coset(H)
+        H = ntt.coset_inverse_fft(H, F, g)
+        want = [(c + h) % p for c, h in zip(coeffs, H)] + [coeffs[m]]
+        # ---- device
+        dA, dB, dC = (dev(to_arr(v).reshape(1, m, 8)) for v in (aA, aB, aC))
+        cA, cB, cC = (ctx.ntt(F.name, d, log_m, inverse=True) for d in (dA, dB, dC))
+        gA, gB = from_arr(host(cA)), from_arr(host(cB))
+        eA, eB, eC = (ctx.ntt(F.name, c, log_m, coset_shift=g) for c in (cA, cB, cC))
+        zinv = F.inv((pow(g, m, p) - 1) % p)
+        Ht = ctx.vec(F.name, capi.VEC_MUL_SUB_SCALE, eA, eB, eC, scalar=zinv)
+        Hc = from_arr(host(ctx.ntt(F.name, Ht, log_m, inverse=True, coset_shift=g)))
+        got = [(d2 * x + d1 * y) % p for x, y in zip(gA, gB)] + [0]
+        got[0] = (got[0] - d3) % p
+        got[m] = (got[m] + d1 * d2) % p
+        got[0] = (got[0] - d1 * d2) % p
+        got = [(c + h) % p for c, h in zip(got, Hc)] + [got[m]]
+        assert got == want
+
+
 @pytest.mark.parametrize("F", fields.NTT_FIELDS, ids=lambda f: f.name)
 @pytest.mark.parametrize("log_n", [1, 2, 6, 11])
 def test_fri_fold_vs_oracle(ctx, F, log_n):
