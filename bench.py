@@ -298,6 +298,31 @@ def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
     return out
 
 
+def lpc_sharded_extra(args, torch, ctx, dev, dist, rank, world):
+    """LPC commit of config #2 (args.batch polynomials in total) with the polynomials sharded over the ranks
+    (SURVEY 8(e)): per-rank LDE, one NCCL all-to-all regroup by leaf range, per-rank subtree, top levels from
+    the all-gathered subtree roots.  Strong scaling; device time, max over ranks."""
+    from crypto3_zk_b200.sharding import lpc_commit_sharded
+    per = max(1, args.batch // world)
+    x = rand_elems(torch, (per, 1 << args.log_in, 8), 2000 + rank, dev)
+    out = {}
+    for name, hid in (("keccak256", 0), ("sha256", 1)):
+        root = lpc_commit_sharded(ctx, "pallas_fq", hid, x, args.log_in, args.log_out, 1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            root = lpc_commit_sharded(ctx, "pallas_fq", hid, x, args.log_in, args.log_out, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = {"ms": float(t.item()), "root": root.hex()}
+    return {"lpc_commit_config2_sharded": {"polys_total": per * world, "polys_per_gpu": per, "n_gpus": world, "scaling": "strong",
+                                           "collective": "all_to_all_single of (N-1)/N of the LDE output, all_gather of N roots", **out}}
+
+
 def lpc_extra(args, torch, ctx, x, hbm_peak):
     from crypto3_zk_b200 import capi
     res = {}
@@ -458,10 +483,16 @@ def main():
     if world > 1 and not args.no_extras:
         del x, y
         torch.cuda.empty_cache()
+        sh = {}
         try:
-            sh = msm_sharded_extra(args, torch, ctx, dev, dist, rank, world)
+            sh.update(lpc_sharded_extra(args, torch, ctx, dev, dist, rank, world))
         except Exception as e:   # extras must never lose the headline
-            sh = {"error": repr(e)}
+            sh["lpc_error"] = repr(e)
+        torch.cuda.empty_cache()
+        try:
+            sh.update(msm_sharded_extra(args, torch, ctx, dev, dist, rank, world))
+        except Exception as e:
+            sh["msm_error"] = repr(e)
         line["extra"] = sh
     if rank == 0:
         print(json.dumps(line))

@@ -248,6 +248,17 @@ class Context:
                    self._h)
         return MerkleTree(self, th, bytes(root), db) if keep_tree else bytes(root)
 
+    def merkle_root_of_digests(self, hash_id, digests):
+        """Root of the binary tree over the given child digests (bytes, count a power of two): the top levels above
+        per-GPU subtrees."""
+        db = capi.lib().zkb_merkle_digest_bytes(hash_id)
+        blob = b"".join(bytes(d) for d in digests)
+        if len(blob) != db * len(digests):
+            raise ValueError("digests must be %d bytes each" % db)
+        root = (ctypes.c_uint8 * max(db, 1))()
+        capi.check(capi.lib().zkb_merkle_root_of_digests(self._h, hash_id, len(digests), blob, root, None), self._h)
+        return bytes(root)
+
     # ------------------------------------------------------------------ MSM
     def msm_bases(self, curve, points, stream=None):
         return MsmBases(self, curve, points, stream)

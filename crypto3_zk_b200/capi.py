@@ -18,7 +18,7 @@ SYMBOLS = [
     "zkb_ctx_last_error", "zkb_ctx_set_scratch_limit", "zkb_ctx_release_caches", "zkb_ctx_kernel_launches",
     "zkb_field_limbs", "zkb_field_two_adicity", "zkb_field_generator", "zkb_field_unity_root", "zkb_curve_generator",
     "zkb_ntt", "zkb_lde", "zkb_vec", "zkb_fri_fold", "zkb_lpc_commit", "zkb_merkle_commit",
-    "zkb_merkle_digest_bytes", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
+    "zkb_merkle_digest_bytes", "zkb_merkle_root_of_digests", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
     "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul",
 ]
@@ -81,6 +81,7 @@ def lib():
     L.zkb_msm_bases_create.argtypes = [vp, i, u64, vp, i, vp, ctypes.POINTER(vp)]
     L.zkb_msm_bases_free.argtypes = [vp]
     L.zkb_msm_bases_free.restype = None
+    L.zkb_merkle_root_of_digests.argtypes = [vp, i, u32, ctypes.c_char_p, u8p, vp]
     L.zkb_msm_bases_precompute.argtypes = [vp, vp, i, u64, vp]
     L.zkb_msm_bases_size.argtypes = [vp]
     L.zkb_msm_bases_size.restype = u64

@@ -375,6 +375,39 @@ int zkb_merkle_commit(zkb_ctx *ctx, int field, int hash, int log_n, int fri_step
     return merkle_build(ctx, hash, log_n, fri_step, batch, d, root_out, tree_out, st);
 }
 
+int zkb_merkle_root_of_digests(zkb_ctx *ctx, int hash, uint32_t count, const uint8_t *digests, uint8_t *root_out, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    const int db = digest_bytes_of(hash);
+    if (!db || !digests || !root_out || count == 0 || (count & (count - 1)))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_merkle_root_of_digests: count must be a power of two");
+    if (count == 1) {
+        memcpy(root_out, digests, db);
+        return ZKB_OK;
+    }
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    void *p;
+    ZKB_TRY(ctx_scratch(ctx, "merkle_top", (size_t)2 * count * db, &p));
+    uint8_t *child = (uint8_t *)p;
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(child, digests, (size_t)count * db, cudaMemcpyHostToDevice, st));
+    for (uint64_t n = count; n > 1; n >>= 1) {
+        uint8_t *parent = child + n * db;
+        uint64_t parents = n >> 1;
+        unsigned pb = (unsigned)((parents + 127) / 128);
+        switch (hash) {
+            case ZKB_HASH_KECCAK_256: node_hash_keccak_kernel<17, 4><<<pb, 128, 0, st>>>(parents, (const uint64_t *)child, (uint64_t *)parent); break;
+            case ZKB_HASH_KECCAK_512: node_hash_keccak_kernel<9, 8><<<pb, 128, 0, st>>>(parents, (const uint64_t *)child, (uint64_t *)parent); break;
+            default: node_hash_sha256_kernel<<<pb, 128, 0, st>>>(parents, (const uint32_t *)child, (uint32_t *)parent); break;
+        }
+        ctx->launches++;
+        child = parent;
+    }
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(root_out, child, db, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return ZKB_OK;
+}
+
 int zkb_lpc_commit(zkb_ctx *ctx, int field, int hash, int log_n_in, int log_n_out, int fri_step, uint32_t batch,
                    const void *polys, int mem, uint8_t *root_out, zkb_merkle_tree **tree_out, void *stream) {
     if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;

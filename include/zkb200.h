@@ -141,6 +141,10 @@ int zkb_lpc_commit(zkb_ctx *ctx, int field, int hash, int log_n_in, int log_n_ou
 /* Merkle tree only, over already extended evaluations [batch][2^log_n] (basic_fri.hpp:732 path) */
 int zkb_merkle_commit(zkb_ctx *ctx, int field, int hash, int log_n, int fri_step, uint32_t batch,
                       const void *evals, int mem, uint8_t *root_out, zkb_merkle_tree **tree_out, void *stream);
+/* root of the binary tree over `count` (a power of two) child digests given on the HOST: the top log2(count) levels
+ * of a tree whose subtrees were committed separately (one per GPU, leaf ranges in rank order) */
+int zkb_merkle_root_of_digests(zkb_ctx *ctx, int hash, uint32_t count, const uint8_t *digests, uint8_t *root_out,
+                               void *stream);
 int zkb_merkle_digest_bytes(int hash);
 uint64_t zkb_merkle_leaves(const zkb_merkle_tree *tree);
 /* authentication path of leaf `index`: `depth` sibling digests, leaf level first

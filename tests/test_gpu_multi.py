@@ -50,3 +50,49 @@ def test_point_sharded_msm_nccl():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _lpc_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from crypto3_zk_b200 import Context
+    from crypto3_zk_b200.sharding import lpc_commit_sharded
+    ctx = Context(rank)
+    ok = True
+    for hid, fri_step, log_in, log_out, per_rank in ((0, 1, 10, 13, 3), (1, 2, 8, 10, 1), (0, 1, 14, 17, 4)):
+        g = torch.Generator(device="cpu").manual_seed(5 + log_in)
+        allp = torch.randint(-2**31, 2**31 - 1, (per_rank * world, 1 << log_in, 8), dtype=torch.int32, generator=g)
+        allp[..., 7] &= 0x0FFFFFFF
+        mine = allp[rank * per_rank:(rank + 1) * per_rank].cuda()
+        got = lpc_commit_sharded(ctx, "pallas_fq", hid, mine, log_in, log_out, fri_step)
+        want = ctx.lpc_commit("pallas_fq", hid, allp.cuda(), log_in, log_out, fri_step)   # whole batch on one GPU
+        ok = ok and got == want
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_polynomial_sharded_lpc_commit_nccl():
+    """LDE sharded by polynomial, one all-to-all regroup by leaf range, per-rank subtrees, top levels
+    from the all-gathered subtree roots - same root as the single-GPU commit of the whole batch."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_lpc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
