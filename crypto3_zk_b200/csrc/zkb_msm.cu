@@ -413,6 +413,115 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(int W, uint32_t n
     }
 }
 
+// ---- upper levels: one XYZZ operation spread over a quad of lanes ---------------------------------
+// The upper tree levels have few nodes and are pure dependent chains: what counts is the latency of one
+// XYZZ addition (14 sequential field products for a lone lane, ~16 us).  Here the four lanes of a quad hold
+// the same operands, each computes one of up to four independent products of a stage, and the products
+// are exchanged with warp shuffles: an addition is 4 product latencies deep, a doubling 3.
+template <class P>
+__device__ __forceinline__ Fp<P> quad_from(const Fp<P> &x, int src) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.l[i] = __shfl_sync(0xffffffffu, x.l[i], src, 4);
+    return r;
+}
+template <class F>
+__device__ __forceinline__ F quad_pick(int sub, const F &a0, const F &a1, const F &a2, const F &a3) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) r.l[i] = sub == 0 ? a0.l[i] : sub == 1 ? a1.l[i] : sub == 2 ? a2.l[i] : a3.l[i];
+    return r;
+}
+// p + q on every lane of the quad (all 32 lanes of the warp must call it; `sub` = lane & 3)
+template <class F>
+__device__ __forceinline__ XYZZ<F> quad_add(const XYZZ<F> &p, const XYZZ<F> &q, int sub) {
+    const bool p_inf = p.is_infinity(), q_inf = q.is_infinity();
+    F t = quad_pick(sub, p.X, q.X, p.Y, q.Y) * quad_pick(sub, q.ZZ, p.ZZ, q.ZZZ, p.ZZZ);
+    const F U1 = quad_from(t, 0), U2 = quad_from(t, 1), S1 = quad_from(t, 2), S2 = quad_from(t, 3);
+    const F Pd = U2 - U1, R = S2 - S1;
+    t = quad_pick(sub, Pd, R, p.ZZ, p.ZZZ) * quad_pick(sub, Pd, R, q.ZZ, q.ZZZ);
+    const F PP = quad_from(t, 0), RR = quad_from(t, 1), ZZa = quad_from(t, 2), ZZZa = quad_from(t, 3);
+    t = quad_pick(sub, Pd, U1, ZZa, ZZa) * PP;
+    const F PPP = quad_from(t, 0), Q = quad_from(t, 1);
+    XYZZ<F> r;
+    r.ZZ = quad_from(t, 2);
+    r.X = RR - PPP - Q.dbl();
+    t = quad_pick(sub, R, S1, ZZZa, ZZZa) * quad_pick(sub, Q - r.X, PPP, PPP, PPP);
+    r.Y = quad_from(t, 0) - quad_from(t, 1);
+    r.ZZZ = quad_from(t, 2);
+    // exceptional inputs are uniform over the quad (same operands on its four lanes)
+    if (q_inf) return p;
+    if (p_inf) return q;
+    if (Pd.is_zero()) return R.is_zero() ? p.dbl() : XYZZ<F>::infinity();
+    return r;
+}
+// 2 p on every lane of the quad (dbl-2008-s-1)
+template <class F>
+__device__ __forceinline__ XYZZ<F> quad_dbl(const XYZZ<F> &p, int sub) {
+    const F U = p.Y.dbl();
+    F t = quad_pick(sub, U, p.X, U, U) * quad_pick(sub, U, p.X, U, U);
+    const F V = quad_from(t, 0), XX = quad_from(t, 1);
+    const F M = XX.dbl() + XX;
+    t = quad_pick(sub, U, p.X, M, V) * quad_pick(sub, V, V, M, p.ZZ);
+    const F W = quad_from(t, 0), S = quad_from(t, 1), MM = quad_from(t, 2);
+    XYZZ<F> r;
+    r.ZZ = quad_from(t, 3);
+    r.X = MM - S.dbl();
+    t = quad_pick(sub, M, W, W, W) * quad_pick(sub, S - r.X, p.Y, p.ZZZ, p.ZZZ);
+    r.Y = quad_from(t, 0) - quad_from(t, 1);
+    r.ZZZ = quad_from(t, 2);
+    if (p.is_infinity() || p.Y.is_zero()) return XYZZ<F>::infinity();
+    return r;
+}
+
+// Same node arithmetic as msm_reduce_level_kernel<F, 4> (roles run / acc / usum) with every role's accumulator
+// replicated over a quad: 16 lanes per node, 8 nodes per 128-thread block.  Upper levels only (inA/inU are
+// (A, U) arrays of the previous level).
+template <class F>
+__global__ void __launch_bounds__(128) msm_reduce_level_quad_kernel(int W, uint32_t n_in, int span_bits, int root,
+                                                                    const XYZZ<F> *__restrict__ inA,
+                                                                    const XYZZ<F> *__restrict__ inU,
+                                                                    XYZZ<F> *__restrict__ outA, XYZZ<F> *__restrict__ outU) {
+    typedef XYZZ<F> Pt;
+    constexpr int ROLE_RUN = 0, ROLE_ACC = 1, ROLE_USUM = 2;   // role 3 idles
+    constexpr int NODES = 128 / 16;
+    __shared__ Pt sh_run[2][NODES];
+    __shared__ Pt sh_usum[NODES];
+    const uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t node = gtid >> 4, ln = threadIdx.x >> 4;
+    const int role = (gtid >> 2) & 3, sub = gtid & 3;
+    const bool live = node < (uint32_t)W * n_out;
+    const uint32_t w = live ? node / n_out : 0, s = live ? node % n_out : 0;
+    const uint32_t j0 = s << MSM_RED_LOG_L;
+    uint32_t j1 = j0 + MSM_RED_L;
+    if (j1 > n_in) j1 = n_in;
+    const Pt inf = Pt::infinity();
+    Pt x = inf;
+    for (uint32_t step = 0; step <= MSM_RED_L; step++) {
+        const bool has_item = live && step < j1 - j0;
+        const uint64_t idx = (uint64_t)w * n_in + (j1 - 1 - step);
+        const Pt *src = nullptr;
+        if (role == ROLE_RUN && has_item) src = inA + idx;
+        else if (role == ROLE_USUM && has_item) src = inU + idx;
+        else if (role == ROLE_ACC && live && step >= 1 && step < j1 - j0) src = &sh_run[(step - 1) & 1][ln];
+        // every lane of the warp runs the quad addition (shuffles); lanes without work add infinity
+        x = quad_add(x, src ? *src : inf, sub);
+        if (role == ROLE_RUN && has_item && sub == 0) sh_run[step & 1][ln] = x;
+        __syncwarp();
+    }
+    if (role == ROLE_USUM && live && sub == 0) sh_usum[ln] = x;
+    __syncwarp();
+    // acc: * 2^span_bits, + usum (+ run at the root); the other roles run along on infinity
+    Pt y = role == ROLE_ACC ? x : inf;
+    for (int i = 0; i < span_bits; i++) y = quad_dbl(y, sub);
+    y = quad_add(y, role == ROLE_ACC && live ? sh_usum[ln] : inf, sub);
+    if (root) y = quad_add(y, role == ROLE_ACC && live ? sh_run[(j1 - j0 - 1) & 1][ln] : inf, sub);
+    if (!live || sub != 0) return;
+    if (role == ROLE_RUN && !root) outA[node] = x;
+    if (role == ROLE_ACC) (root ? outA : outU)[node] = y;
+}
+
 // ------------------------------------------------------------------------------------ host driver
 static int msm_pick_c(uint64_t n) {
     int lg = 0;
@@ -500,12 +609,17 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
             const Pt *inA = level == 0 ? tout : src, *inU = level == 0 ? nullptr : src + (size_t)WB * n_lvl0;
             const bool root = n_out == 1;
             uint32_t cnt = (uint32_t)WB * n_out;
-            if (level == 0)
+            if (level == 0) {
                 msm_reduce_level_kernel<F, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, toffs, ntasks, inA, inU,
                                                                                    root ? S : dst, dst + (size_t)WB * n_lvl0);
-            else
+            } else if (F::N <= 12 && cnt <= 2048) {   // few nodes left: latency matters, quad-cooperative additions
+                if constexpr (F::N <= 12)
+                msm_reduce_level_quad_kernel<F><<<(cnt * 16 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, inA, inU, root ? S : dst,
+                                                                                      dst + (size_t)WB * n_lvl0);
+            } else {
                 msm_reduce_level_kernel<F, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, toffs, ntasks, inA, inU,
                                                                                    root ? S : dst, dst + (size_t)WB * n_lvl0);
+            }
             ctx->launches++;
             if (root) break;
             n_in = n_out;
