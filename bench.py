@@ -447,9 +447,10 @@ def main():
     # ---- roofline of the dominant kernel (ntt_pass_kernel: every launch of the step is this kernel)
     alg_bytes = args.batch * (n_in + n_out) * 32           # read the 2 GiB input once, write the 16 GiB result once
     per_launch = alg_bytes / max(launches / args.steps, 1)
-    traffic = None
+    traffic = None   # DRAM read+write bytes per launch from the committed ncu --set full capture
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
+        traffic = tj["dram_bytes_per_polynomial"] * args.batch / max(launches / args.steps, 1)
     except Exception:
         pass
     ach = alg_bytes / (ms_per_step * 1e-3) / 1e9

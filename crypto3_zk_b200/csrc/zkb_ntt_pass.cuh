@@ -1,5 +1,5 @@
 // One pass of the multi-pass NTT: a CTA owns a tile of R = 2^log_r rows x ZKB_NTT_C columns held in
-// shared memory, runs a radix-2^log_r decimation-in-frequency sub-NTT down the rows (radix-4 steps,
+// shared memory, runs a radix-2^log_r sub-NTT down the rows (natural order in, bit-reversed out; radix-4 steps,
 // 2 butterfly levels per shared-memory round trip), and writes the tile back multiplied by the
 // inter-pass twiddles.  Columns are independent transforms, laid out so that every global access is
 // a contiguous run (ZKB_NTT_C elements = 256 B along the column axis, or R elements when the row
@@ -195,49 +195,57 @@ ZKB_HD F ntt_tw(const NttPassParams &p, uint32_t e, int log_size) {
     return ntt_ld_tab<F>(p.tw, (uint64_t)e << (ZKB_NTT_TW_LOG - log_size));
 }
 
-// radix-2 DIF level with half-distance h = 2^log_h
+// The in-tile sub-transform splits the polynomial by halves (natural order in, bit-reversed order out)
+// with Cooley-Tukey butterflies (a, b) -> (a + c b, a - c b): at the level with half-distance h = 2^log_h
+// the rows form m = R / 2h blocks and block B evaluates on the coset w^{brev(B)} of the subgroup of order 2h,
+// so its twiddle is c_B = w_R^{brev(B) h} - one constant per block, nothing per position.  Block 0 has c = 1
+// (no product at all); compared with Gentleman-Sande butterflies (a + b, (a - b) w^j) this removes the unit
+// twiddles of every level, not only of the last one.
+
+// one level with half-distance h = 2^log_h
 template <class F>
 ZKB_HD void ntt_phase_radix2(const NttPassParams &p, u128 *smem, int log_h, uint32_t tid,
                                     uint32_t nthreads) {
     const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r, h = 1u << log_h;
+    const int lvl = p.log_r - 1 - log_h;               // number of blocks = 2^lvl
     for (uint32_t task = tid; task < (R / 2) * C; task += nthreads) {
         uint32_t c = task % C, g = task / C;
-        uint32_t j = g & (h - 1);
-        uint32_t i = ((g >> log_h) << (log_h + 1)) + j;
+        uint32_t j = g & (h - 1), blk = g >> log_h;
+        uint32_t i = (blk << (log_h + 1)) + j;
         F a = ntt_ld_elem<F>(smem, p.log_r, i, c), b = ntt_ld_elem<F>(smem, p.log_r, i + h, c);
-        F s = a + b, d = a - b;
-        if (h > 1) d = d * ntt_tw<F>(p, j, log_h + 1);
-        ntt_st_elem<F>(smem, p.log_r, i, c, s);
-        ntt_st_elem<F>(smem, p.log_r, i + h, c, d);
+        if (blk != 0) b = b * ntt_tw<F>(p, brev(blk, lvl) << log_h, p.log_r);
+        ntt_st_elem<F>(smem, p.log_r, i, c, a + b);
+        ntt_st_elem<F>(smem, p.log_r, i + h, c, a - b);
     }
 }
 
-// two fused DIF levels with half-distances h = 2^log_h and h/2
+// two fused levels with half-distances h = 2^log_h and q = h/2: block B of the first level splits into
+// blocks 2B, 2B+1 of the second; with beta = brev(B): c = w^{2 beta q}, c0 = w^{beta q}, c1 = c0 w_4
 template <class F>
 ZKB_HD void ntt_phase_radix4(const NttPassParams &p, u128 *smem, int log_h, uint32_t tid,
                                     uint32_t nthreads) {
     const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r, h = 1u << log_h, q = h >> 1;
     const int log_q = log_h - 1;
+    const int lvl = p.log_r - 1 - log_h;
     for (uint32_t task = tid; task < (R / 4) * C; task += nthreads) {
         uint32_t c = task % C, g = task / C;
-        uint32_t j = g & (q - 1);
-        uint32_t i = ((g >> log_q) << (log_h + 1)) + j;
+        uint32_t j = g & (q - 1), blk = g >> log_q;
+        uint32_t i = (blk << (log_h + 1)) + j;
         F x0 = ntt_ld_elem<F>(smem, p.log_r, i, c), x2 = ntt_ld_elem<F>(smem, p.log_r, i + h, c);
-        F y0 = x0 + x2, y2 = x0 - x2;
         F x1 = ntt_ld_elem<F>(smem, p.log_r, i + q, c), x3 = ntt_ld_elem<F>(smem, p.log_r, i + h + q, c);
-        F y1 = x1 + x3, y3 = x1 - x3;
-        if (q > 1) y2 = y2 * ntt_tw<F>(p, j, log_h + 1);      // j == 0 is the only exponent when q == 1
-        y3 = y3 * ntt_tw<F>(p, j + q, log_h + 1);
-        F z0 = y0 + y1, z1 = y0 - y1, z2 = y2 + y3, z3 = y2 - y3;
-        if (q > 1) {
-            F w = ntt_tw<F>(p, j, log_h);
-            z1 = z1 * w;
-            z3 = z3 * w;
+        const uint32_t e0 = brev(blk, lvl) << log_q;    // beta q  (< R/4)
+        if (blk != 0) {
+            F w = ntt_tw<F>(p, 2 * e0, p.log_r);
+            x2 = x2 * w;
+            x3 = x3 * w;
         }
-        ntt_st_elem<F>(smem, p.log_r, i, c, z0);
-        ntt_st_elem<F>(smem, p.log_r, i + q, c, z1);
-        ntt_st_elem<F>(smem, p.log_r, i + h, c, z2);
-        ntt_st_elem<F>(smem, p.log_r, i + h + q, c, z3);
+        F y0 = x0 + x2, y2 = x0 - x2, y1 = x1 + x3, y3 = x1 - x3;
+        if (blk != 0) y1 = y1 * ntt_tw<F>(p, e0, p.log_r);
+        y3 = y3 * ntt_tw<F>(p, e0 + (R >> 2), p.log_r);
+        ntt_st_elem<F>(smem, p.log_r, i, c, y0 + y1);
+        ntt_st_elem<F>(smem, p.log_r, i + q, c, y0 - y1);
+        ntt_st_elem<F>(smem, p.log_r, i + h, c, y2 + y3);
+        ntt_st_elem<F>(smem, p.log_r, i + h + q, c, y2 - y3);
     }
 }
 
