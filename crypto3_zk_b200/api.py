@@ -30,6 +30,27 @@ def _limbs(val, n):
     return (ctypes.c_uint32 * n)(*[(int(val) >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
 
 
+def _int_rows(vals, n=8):
+    """list of integers -> [len, n] uint32 limb array"""
+    a = np.zeros((len(vals), n), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        v = int(v)
+        for l in range(n):
+            a[i, l] = (v >> (32 * l)) & 0xFFFFFFFF
+    return a
+
+
+def _ints(arr):
+    """[len, n] uint32 limb array -> list of integers"""
+    out = []
+    for row in np.asarray(arr, dtype=np.uint32).reshape(-1, arr.shape[-1]).tolist():
+        v = 0
+        for l, x in enumerate(row):
+            v |= x << (32 * l)
+        out.append(v)
+    return out
+
+
 class _Buf:
     """Pointer + location of a caller buffer."""
 
@@ -90,6 +111,43 @@ class MerkleTree:
     def free(self):
         if self._h:
             capi.lib().zkb_merkle_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SparseMatrix:
+    """One side (A, B or C) of an r1cs_constraint_system as a device-resident CSR matrix."""
+
+    def __init__(self, ctx, field, rows, cols, row_ptr, col_idx, values, stream=None):
+        self._ctx, self.field, self.rows, self.cols = ctx, field, int(rows), int(cols)
+        rp = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        ci = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        va = np.ascontiguousarray(values, dtype=np.uint32)
+        if rp.shape != (self.rows + 1,) or va.size != ci.size * 8:
+            raise ValueError("CSR arrays: row_ptr [rows+1], col_idx [nnz], values [nnz, 8]")
+        self._h = ctypes.c_void_p()
+        capi.check(capi.lib().zkb_sparse_matrix_create(
+            ctx._h, _field_id(field), self.rows, self.cols, rp.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+            capi.u32_ptr(ci) if ci.size else None, capi.u32_ptr(va) if va.size else None,
+            ctypes.c_void_p(int(stream)) if stream is not None else None, ctypes.byref(self._h)), ctx._h)
+
+    def matvec(self, x, out, stream=None):
+        """out[i] = <row i, x>; x: [cols, 8] host array or device tensor, out: device tensor with >= rows elements."""
+        bx, bo = _Buf(x), _Buf(out, writable=True)
+        if bx.nbytes != self.cols * 32 or bo.mem != capi.MEM_DEVICE or bo.nbytes < self.rows * 32:
+            raise ValueError("x must hold `cols` elements and out (device) at least `rows`")
+        capi.check(capi.lib().zkb_sparse_matvec(self._ctx._h, self._h, bx.ptr, bx.mem, bo.ptr, _stream_ptr(out, stream)),
+                   self._ctx._h)
+        return out
+
+    def free(self):
+        if self._h:
+            capi.lib().zkb_sparse_matrix_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -258,6 +316,120 @@ class Context:
         root = (ctypes.c_uint8 * max(db, 1))()
         capi.check(capi.lib().zkb_merkle_root_of_digests(self._h, hash_id, len(digests), blob, root, None), self._h)
         return bytes(root)
+
+    def fri_commit_phase(self, field, hash_id, f, log_n, step_list, challenge, keep_trees=False, keep_fs=False,
+                         stream=None):
+        """Commit phase of zk::algorithms::proof_eval<FRI> (basic_fri.hpp:706-737) on the device.
+        f: combined Q in evaluation form on D[0] (2^log_n elements, device tensor or host array).
+        challenge(round, root_bytes, count) -> list of `count` integers < p: the caller's transcript
+        (transcript(root); alphas = transcript.challenge() x count).
+        Returns a dict: roots, alphas (ints), final_polynomial (ints, coefficients), trees (MerkleTree per round or
+        None), fs (device tensor with f after every round, back to back, or None)."""
+        fid = _field_id(field)
+        b = _Buf(f)
+        if b.nbytes != (1 << log_n) * 32:
+            raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "f is not [2^log_n, 8] uint32")
+        steps = [int(s) for s in step_list]
+        rounds, total = len(steps), sum(steps)
+        if rounds == 0 or min(steps) < 1 or total > log_n:
+            raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "step_list must be non-empty, >= 1 each, sum <= log_n")
+        db = capi.lib().zkb_merkle_digest_bytes(hash_id)
+        failure = []
+
+        def _cb(user, rnd, root, root_bytes, count, out):
+            try:
+                vals = challenge(int(rnd), bytes(root[:root_bytes]), int(count))
+                if len(vals) != count:
+                    raise ValueError("challenge callback returned %d values, expected %d" % (len(vals), count))
+                for k, v in enumerate(vals):
+                    for l in range(8):
+                        out[8 * k + l] = (int(v) >> (32 * l)) & 0xFFFFFFFF
+                return 0
+            except Exception as e:   # never unwind through the C frames
+                failure.append(e)
+                return 1
+
+        cb = capi.FRI_CHALLENGE_FN(_cb)
+        roots = (ctypes.c_uint8 * (db * rounds))()
+        trees = (ctypes.c_void_p * rounds)() if keep_trees else None
+        fs = None
+        if keep_fs:
+            import torch
+            acc, n_fs = log_n, 0
+            for s in steps:
+                acc -= s
+                n_fs += 1 << acc
+            dev = f.device if _is_torch(f) else torch.device("cuda", self.device)
+            fs = torch.empty((n_fs, 8), dtype=torch.int32, device=dev)
+        alphas = np.zeros((total, 8), dtype=np.uint32)
+        final = np.zeros((1 << (log_n - total), 8), dtype=np.uint32)
+        status = capi.lib().zkb_fri_commit_phase(
+            self._h, fid, hash_id, log_n, b.ptr, b.mem, (ctypes.c_uint32 * rounds)(*steps), rounds, cb, None, roots,
+            trees, fs.data_ptr() if fs is not None else None, capi.u32_ptr(alphas), capi.u32_ptr(final),
+            _stream_ptr(f, stream))
+        if failure:
+            raise failure[0]
+        capi.check(status, self._h)
+        raw = bytes(roots)
+        root_list = [raw[i * db:(i + 1) * db] for i in range(rounds)]
+        tree_list = None
+        if keep_trees:
+            tree_list = [MerkleTree(self, ctypes.c_void_p(trees[i]), root_list[i], db) for i in range(rounds)]
+        return {"roots": root_list, "alphas": _ints(alphas), "final_polynomial": _ints(final), "trees": tree_list, "fs": fs}
+
+    # ------------------------------------------------------------------ LPC opening side (eval_polys, combined Q)
+    def poly_evaluate(self, field, polys, n, points, dfs=False, stream=None):
+        """polys_evaluator::eval_polys (batched_commitment.hpp:176-190): value of every polynomial of the batch
+        ([batch, n, 8]; coefficient form, or evaluations on the 2^k subgroup when dfs) at every point.
+        Returns a list (per polynomial) of lists (per point) of integers."""
+        fid = _field_id(field)
+        b = _Buf(polys)
+        batch = b.nbytes // (n * 32)
+        pts = np.ascontiguousarray(_int_rows(points))
+        out = np.zeros((batch, len(points), 8), dtype=np.uint32)
+        capi.check(capi.lib().zkb_poly_evaluate(self._h, fid, capi.POLY_DFS if dfs else capi.POLY_COEFFICIENTS, n, batch,
+                                                b.ptr, b.mem, len(points), capi.u32_ptr(pts), capi.u32_ptr(out),
+                                                _stream_ptr(polys, stream)), self._h)
+        flat = _ints(out.reshape(-1, 8))
+        return [flat[i * len(points):(i + 1) * len(points)] for i in range(batch)]
+
+    def poly_lincomb(self, field, polys, n, scalars, constant=None, out=None, accumulate=False, stream=None):
+        """out[i] (+)= sum_j scalars[j] polys[j][i] - [i == 0] constant on device tensors (lpc.hpp:139-153)."""
+        fid = _field_id(field)
+        b = _Buf(polys)
+        batch = b.nbytes // (n * 32)
+        if len(scalars) != batch:
+            raise ValueError("one scalar per polynomial")
+        if out is None:
+            if accumulate:
+                raise ValueError("accumulate needs an existing output")
+            out = _empty_like(polys, (n, 8))
+        o = _Buf(out, writable=True)
+        if b.mem != capi.MEM_DEVICE or o.mem != capi.MEM_DEVICE:
+            raise ValueError("poly_lincomb works on device tensors")
+        sc = np.ascontiguousarray(_int_rows(scalars))
+        capi.check(capi.lib().zkb_poly_lincomb(self._h, fid, n, batch, b.ptr, capi.u32_ptr(sc),
+                                               _limbs(constant, 8) if constant is not None else None, o.ptr,
+                                               1 if accumulate else 0, _stream_ptr(polys, stream)), self._h)
+        return out
+
+    def poly_div_linear(self, field, poly, n, point, out=None, stream=None):
+        """(poly - poly(point)) / (X - point) on device tensors; returns (quotient, remainder)."""
+        fid = _field_id(field)
+        b = _Buf(poly)
+        if out is None:
+            out = _empty_like(poly, (n, 8))
+        o = _Buf(out, writable=True)
+        if b.mem != capi.MEM_DEVICE or o.mem != capi.MEM_DEVICE:
+            raise ValueError("poly_div_linear works on device tensors")
+        rem = np.zeros((1, 8), dtype=np.uint32)
+        capi.check(capi.lib().zkb_poly_div_linear(self._h, fid, n, b.ptr, _limbs(point, 8), o.ptr, capi.u32_ptr(rem),
+                                                  _stream_ptr(poly, stream)), self._h)
+        return out, _ints(rem)[0]
+
+    # ------------------------------------------------------------------ R1CS rows (r1cs_to_qap.hpp:245-248,289-291)
+    def sparse_matrix(self, field, rows, cols, row_ptr, col_idx, values, stream=None):
+        return SparseMatrix(self, field, rows, cols, row_ptr, col_idx, values, stream)
 
     # ------------------------------------------------------------------ MSM
     def msm_bases(self, curve, points, stream=None):

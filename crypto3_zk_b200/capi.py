@@ -21,7 +21,13 @@ SYMBOLS = [
     "zkb_merkle_digest_bytes", "zkb_merkle_root_of_digests", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
     "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul",
+    "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
+    "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec",
 ]
+POLY_COEFFICIENTS, POLY_DFS = 0, 1
+# int (*zkb_fri_challenge_fn)(void *user, uint32_t round, const uint8_t *root, uint32_t root_bytes, uint32_t count, uint32_t *alphas_out)
+FRI_CHALLENGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint8),
+                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32))
 
 
 class ZkbError(RuntimeError):
@@ -91,6 +97,15 @@ def lib():
     L.zkb_msm_g1.argtypes = [vp, i, u64, vp, vp, i, u32p, vp]
     L.zkb_g1_grid_points.argtypes = [vp, i, u64, u32, vp, vp, vp, vp]
     L.zkb_bench_field_mul.argtypes = [vp, i, u32, u32, u32, ctypes.POINTER(ctypes.c_double)]
+    L.zkb_fri_commit_phase.argtypes = [vp, i, i, i, vp, i, u32p, u32, FRI_CHALLENGE_FN, vp, u8p, ctypes.POINTER(vp), vp,
+                                       u32p, u32p, vp]
+    L.zkb_poly_evaluate.argtypes = [vp, i, i, u64, u32, vp, i, u32, u32p, u32p, vp]
+    L.zkb_poly_lincomb.argtypes = [vp, i, u64, u32, vp, u32p, u32p, vp, i, vp]
+    L.zkb_poly_div_linear.argtypes = [vp, i, u64, vp, u32p, vp, u32p, vp]
+    L.zkb_sparse_matrix_create.argtypes = [vp, i, u64, u64, ctypes.POINTER(u64), u32p, u32p, vp, ctypes.POINTER(vp)]
+    L.zkb_sparse_matrix_free.argtypes = [vp]
+    L.zkb_sparse_matrix_free.restype = None
+    L.zkb_sparse_matvec.argtypes = [vp, vp, vp, i, vp, vp]
     _lib = L
     return L
 

@@ -263,6 +263,10 @@ static int digest_bytes_of(int hash) {
 
 static int merkle_build(zkb_ctx *ctx, int hash, int log_d, int fri_step, uint32_t batch, const void *d_evals,
                         uint8_t *root_out, zkb_merkle_tree **tree_out, cudaStream_t st) {
+    return zkb::merkle_build_device(ctx, hash, log_d, fri_step, batch, d_evals, root_out, tree_out, st);
+}
+int zkb::merkle_build_device(zkb_ctx *ctx, int hash, int log_d, int fri_step, uint32_t batch, const void *d_evals,
+                             uint8_t *root_out, zkb_merkle_tree **tree_out, cudaStream_t st) {
     const int db = digest_bytes_of(hash);
     const uint64_t D = 1ull << log_d, leaves = D >> fri_step;
     uint8_t *nodes = nullptr;

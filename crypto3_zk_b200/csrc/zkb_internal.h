@@ -53,5 +53,10 @@ int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d
                const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st);
 int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
                cudaStream_t st);
+// one FRI fold on device buffers (alpha: host, canonical limbs)
+int fold_device(zkb_ctx *ctx, int field, int log_n, const void *d_f, const uint32_t *alpha, void *d_out, cudaStream_t st);
+// leaf packing + Merkle tree over extended evaluations [batch][2^log_d] on the device (zkb_hash.cu)
+int merkle_build_device(zkb_ctx *ctx, int hash, int log_d, int fri_step, uint32_t batch, const void *d_evals,
+                        uint8_t *root_out, zkb_merkle_tree **tree_out, cudaStream_t st);
 
 }  // namespace zkb

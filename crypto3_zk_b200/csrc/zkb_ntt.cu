@@ -267,6 +267,12 @@ static int fold_t(zkb_ctx *ctx, int log_n, const void *f, const uint32_t *alpha,
     return ZKB_OK;
 }
 
+namespace zkb {
+int fold_device(zkb_ctx *ctx, int field, int log_n, const void *d_f, const uint32_t *alpha, void *d_out, cudaStream_t st) {
+    ZKB_DISPATCH_NTT_FIELD(field, fold_t, ctx, log_n, d_f, alpha, d_out, st)
+}
+}  // namespace zkb
+
 // ------------------------------------------------------------------------------------ C ABI
 namespace {
 struct Staged {  // host<->device staging for ZKB_MEM_HOST callers
@@ -433,14 +439,7 @@ int zkb_fri_fold(zkb_ctx *ctx, int field, int log_n, const void *f, const uint32
     void *dout;
     ZKB_TRY(sg.in("io_in", f, ib, &df));
     ZKB_TRY(sg.out_buf("io_out", out, ob, &dout));
-    int s;
-    switch (field) {
-        case ZKB_FIELD_BLS12_381_FR: s = fold_t<params::Bls12381Fr>(ctx, log_n, df, alpha, dout, st); break;
-        case ZKB_FIELD_BN254_FR: s = fold_t<params::Bn254Fr>(ctx, log_n, df, alpha, dout, st); break;
-        case ZKB_FIELD_PALLAS_FP: s = fold_t<params::PallasFp>(ctx, log_n, df, alpha, dout, st); break;
-        default: s = fold_t<params::PallasFq>(ctx, log_n, df, alpha, dout, st); break;
-    }
-    ZKB_TRY(s);
+    ZKB_TRY(fold_device(ctx, field, log_n, df, alpha, dout, st));
     return sg.out(out, dout, ob);
 }
 

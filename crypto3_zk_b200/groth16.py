@@ -1,0 +1,155 @@
+"""Host mirror of r1cs_gg_ppzksnark_prover::process (zk/snark/systems/ppzksnark/r1cs_gg_ppzksnark/prover.hpp:73-158)
+over device-resident keys and vectors.
+
+Everything data-parallel runs in libzkb200.so:
+  rows of the constraint system   zkb_sparse_matvec                 (r1cs_to_qap.hpp:239-248, 289-291)
+  witness map                     zkb_ntt x 7, zkb_vec              (r1cs_to_qap.hpp:250-321; the three vectors are one batch)
+  evaluation_At / Bt / Ht / Lt    zkb_msm on resident query vectors (prover.hpp:108-139)
+The O(1) group operations of the proof assembly (prover.hpp:141-155) are folded into the MSMs as extra base points:
+  A = alpha + sum x_i A_i + r delta           = MSM([alpha_g1, delta_g1] ++ A_query, [1, r] ++ x)
+  B = beta + sum x_i B_i + s delta            (same, on G2 and on G1)
+  C = Ht + Lt + s A + r B_g1 - r s delta_g1   = one 5-point MSM over the intermediate results
+so no curve arithmetic runs on the host.  Points are affine (x, y) integers ((c0, c1) pairs on G2), None = infinity.
+"""
+import numpy as np
+
+from . import capi
+from .api import _int_rows
+from .fields import CURVE_BY_NAME, FIELD_BY_NAME, coord_limbs
+
+
+def _points_array(curve, pts):
+    """list of affine points (None = infinity) -> [n, 2, coord_limbs] uint32"""
+    cl = coord_limbs(curve)
+    out = np.zeros((len(pts), 2, cl), dtype=np.uint32)
+    for i, P in enumerate(pts):
+        if P is None:
+            continue
+        for k in range(2):
+            parts = P[k] if curve.deg == 2 else (P[k],)
+            h = cl // len(parts)
+            for j, v in enumerate(parts):
+                for l in range(h):
+                    out[i, k, j * h + l] = (int(v) >> (32 * l)) & 0xFFFFFFFF
+    return out
+
+
+class R1csConstraintSystem:
+    """r1cs_constraint_system: constraints as (a, b, c) lists of (variable index, coefficient) terms, index 0 = 1."""
+
+    def __init__(self, num_inputs, num_aux, constraints):
+        self.num_inputs, self.num_aux, self.constraints = int(num_inputs), int(num_aux), constraints
+
+    @property
+    def num_variables(self):
+        return self.num_inputs + self.num_aux
+
+    @property
+    def num_constraints(self):
+        return len(self.constraints)
+
+    def csr(self, side):
+        """CSR arrays (row_ptr u64, col u32, values [nnz, 8] u32) of one side (0 = a, 1 = b, 2 = c)."""
+        row_ptr = np.zeros(self.num_constraints + 1, dtype=np.uint64)
+        cols, vals = [], []
+        for i, con in enumerate(self.constraints):
+            for idx, co in con[side]:
+                cols.append(idx)
+                vals.append(co)
+            row_ptr[i + 1] = len(cols)
+        return row_ptr, np.asarray(cols, dtype=np.uint32), _int_rows(vals)
+
+
+class ProvingKey:
+    """r1cs_gg_ppzksnark proving key resident on one GPU.  Query vectors are lists of affine points or already
+    encoded [n, 2, limbs] arrays / device tensors."""
+
+    def __init__(self, ctx, curve_g1, curve_g2, cs, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, A_query, B_indices,
+                 B_g2, B_g1, H_query, L_query, csr=None, precompute=False):
+        import torch
+        self.ctx = ctx
+        self.g1 = CURVE_BY_NAME[curve_g1] if isinstance(curve_g1, str) else curve_g1
+        self.g2 = CURVE_BY_NAME[curve_g2] if isinstance(curve_g2, str) else curve_g2
+        self.F = FIELD_BY_NAME[self.g1.scalar_field]
+        self.cs = cs
+        self.delta_g1 = delta_g1
+        dev = "cuda:%d" % ctx.device
+
+        def enc(curve, head, query):
+            h = _points_array(curve, head)
+            if isinstance(query, list):
+                return np.concatenate([h, _points_array(curve, query)])
+            if isinstance(query, np.ndarray):
+                return np.concatenate([h, query])
+            return torch.cat([torch.from_numpy(h.view(np.int32)).to(query.device), query])
+
+        self.A = ctx.msm_bases(self.g1.name, enc(self.g1, [alpha_g1, delta_g1], A_query))
+        self.B2 = ctx.msm_bases(self.g2.name, enc(self.g2, [beta_g2, delta_g2], B_g2))
+        self.B1 = ctx.msm_bases(self.g1.name, enc(self.g1, [beta_g1, delta_g1], B_g1))
+        self.H = ctx.msm_bases(self.g1.name, enc(self.g1, [], H_query))
+        self.L = ctx.msm_bases(self.g1.name, enc(self.g1, [], L_query))
+        if precompute:
+            for b in (self.A, self.B1, self.H, self.L):
+                b.precompute()
+        self.B_index = torch.as_tensor(np.asarray(B_indices, dtype=np.int64), device=dev)
+        nc = cs.num_constraints
+        m = nc + cs.num_inputs + 1
+        if m & (m - 1):
+            raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT,
+                                          "num_constraints + num_inputs + 1 must be a power of two (basic_radix2_domain)")
+        self.m, self.log_m = m, m.bit_length() - 1
+        sides = csr if csr is not None else [cs.csr(k) for k in range(3)]
+        self.mats = [ctx.sparse_matrix(self.F.name, nc, cs.num_variables + 1, *sides[k]) for k in range(3)]
+
+
+def witness_map(ctx, pk, x):
+    """r1cs_to_qap<F>::witness_map with d1 = d2 = d3 = 0 (prover.hpp:78-82): x = (1, primary, auxiliary) on the device
+    -> coefficients_for_H [m, 8] (the entries m-1 and m of the reference's m+1 vector are zero by construction)."""
+    import torch
+    F, m, log_m = pk.F, pk.m, pk.log_m
+    cs = pk.cs
+    nc, ni = cs.num_constraints, cs.num_inputs
+    abc = torch.zeros((3, m, 8), dtype=torch.int32, device=x.device)
+    for k in range(3):
+        pk.mats[k].matvec(x, abc[k])
+    abc[0, nc:nc + ni + 1] = x[:ni + 1]          # the input-consistency constraints input_i * 0 = 0 (:239-242)
+    ctx.ntt(F.name, abc, log_m, inverse=True)
+    ctx.ntt(F.name, abc, log_m, coset_shift=F.generator)
+    z_inv = pow((pow(F.generator, m, F.p) - 1) % F.p, F.p - 2, F.p)   # divide_by_z_on_coset: Z(g) = g^m - 1
+    h = ctx.vec(F.name, capi.VEC_MUL_SUB_SCALE, abc[0], abc[1], abc[2], scalar=z_inv, out=abc[0])
+    ctx.ntt(F.name, h.unsqueeze(0), log_m, inverse=True, coset_shift=F.generator)
+    return h
+
+
+def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None):
+    """Returns (g1_A, g2_B, g1_C) in affine form.  r, s: the prover's zero-knowledge randomness (the reference draws
+    them with algebra::random_element, prover.hpp:91-92).  x_device: optional device tensor with the full assignment
+    (1, primary, auxiliary) as [num_variables + 1, 8] limbs; otherwise it is uploaded from the Python integers."""
+    import torch
+    F = pk.F
+    p = F.p
+    cs = pk.cs
+    nv, ni, m = cs.num_variables, cs.num_inputs, pk.m
+    dev = "cuda:%d" % ctx.device
+    if x_device is None:
+        full = [1] + [int(v) % p for v in primary_input] + [int(v) % p for v in auxiliary_input]
+        if len(full) != nv + 1:
+            raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "assignment size does not match the constraint system")
+        x_device = torch.from_numpy(_int_rows(full).view(np.int32)).to(dev)
+    x = x_device
+    h = witness_map(ctx, pk, x)
+
+    def head(*vals):
+        return torch.from_numpy(_int_rows([v % p for v in vals]).view(np.int32)).to(dev)
+
+    g1_A = ctx.multiexp(pk.A, torch.cat([head(1, r), x]))
+    xb = x.index_select(0, pk.B_index)
+    sb = torch.cat([head(1, s), xb])
+    g2_B = ctx.multiexp(pk.B2, sb)
+    g1_B = ctx.multiexp(pk.B1, sb)
+    ev_H = ctx.multiexp(pk.H, h[:m - 1].contiguous(), n=m - 1)
+    ev_L = ctx.multiexp(pk.L, x[ni + 1:].contiguous())
+    tail = ctx.msm_bases(pk.g1.name, _points_array(pk.g1, [ev_H, ev_L, g1_A, g1_B, pk.delta_g1]))
+    g1_C = ctx.multiexp(tail, _int_rows([1, 1, s % p, r % p, (-r * s) % p]))
+    tail.free()
+    return g1_A, g2_B, g1_C

@@ -1,0 +1,199 @@
+"""Host mirror of lpc_commitment_scheme (zk/commitments/polynomial/lpc.hpp:66-200) and its base
+polys_evaluator (zk/commitments/batched_commitment.hpp:60-250) over device-resident polynomials.
+
+What runs where:
+  commit(index)        zkb_lpc_commit: LDE of the batch to D[0] + leaf hash + Merkle tree        (lpc.hpp:101-106)
+  eval_polys()         batched inverse NTT + zkb_poly_evaluate                                      (batched_commitment.hpp:176-190)
+  proof_eval()         theta powers on the host; per unique point zkb_poly_lincomb + zkb_poly_div_linear;
+                       from_coefficients + resize to D[0] = one zero-padded NTT; then zkb_fri_commit_phase
+                       (lpc.hpp:113-200, basic_fri.hpp:706-737)
+The query phase, grinding and proof marshalling are not part of the hot path and are not built:
+proof_eval returns the evaluation table z, the combined Q on D[0] and the commit-phase outputs
+(fri_roots, alphas, fs, fri_trees, final_polynomial) that the reference's query phase starts from.
+Polynomials are polynomial_dfs values: evaluations on the 2^k subgroup, canonical uint32 limbs, torch CUDA tensors.
+"""
+import numpy as np
+
+from . import capi
+from .api import _int_rows
+from .fields import FIELD_BY_NAME
+
+
+class FriParams:
+    """commitments::detail::basic_batched_fri::params_type (basic_fri.hpp:151-183): r = max degree log,
+    D[i] of size 2^(r + expand_factor - i) (calculate_domain_set), step_list summing to r."""
+
+    def __init__(self, step_list, degree_log, lambda_=40, expand_factor=2):
+        self.step_list = [int(s) for s in step_list]
+        self.r = sum(self.step_list)
+        self.degree_log = int(degree_log)
+        self.lambda_ = int(lambda_)
+        self.expand_factor = int(expand_factor)
+        self.log_d0 = self.degree_log + self.expand_factor
+        if self.r > self.log_d0:
+            raise ValueError("sum(step_list) exceeds log2 |D[0]|")
+
+    @staticmethod
+    def with_max_step_one(degree_log, lambda_=40, expand_factor=2):
+        """params_type(max_step = 1, degree_log, lambda, expand_factor) (basic_fri.hpp:150-166), the constructor the
+        reference's Placeholder tests use (test/systems/plonk/placeholder/placeholder.cpp:231): r = degree_log - 1
+        rounds of step 1 (generate_random_step_list is deterministic for max_step = 1)."""
+        return FriParams([1] * (degree_log - 1), degree_log, lambda_, expand_factor)
+
+
+class LpcCommitmentScheme:
+    def __init__(self, ctx, field, hash_id, fri_params):
+        self.ctx, self.hash_id, self.fri = ctx, hash_id, fri_params
+        self.F = FIELD_BY_NAME[field] if isinstance(field, str) else field
+        self._polys = {}       # batch index -> list of [n, 8] device tensors (same n within a batch)
+        self._points = {}      # batch index -> list (per polynomial) of point lists
+        self._trees = {}
+        self._fixed = {}
+        self._locked = {}
+        self._etha = None
+        self._fixed_values = None
+        self.z = {}
+
+    # ---- polys_evaluator interface (batched_commitment.hpp:196-250)
+    def append_to_batch(self, index, poly):
+        if self._locked.get(index):
+            raise RuntimeError("batch %d is already committed" % index)
+        t = poly if poly.dim() == 3 else poly.unsqueeze(0)
+        for i in range(t.shape[0]):
+            self._polys.setdefault(index, []).append(t[i])
+
+    def append_eval_point(self, batch, point, poly=None):
+        """(batch, point): every polynomial of the batch; (batch, poly, point): one polynomial."""
+        pts = self._points.setdefault(batch, [[] for _ in self._polys[batch]])
+        targets = range(len(pts)) if poly is None else [poly]
+        for i in targets:
+            pts[i].append(int(point) % self.F.p)
+
+    def set_batch_size(self, index, size):
+        self._points[index] = [[] for _ in range(size)]
+
+    def _batch_tensor(self, index):
+        import torch
+        polys = self._polys[index]
+        n = polys[0].shape[0]
+        if any(p.shape[0] != n for p in polys):
+            raise ValueError("polynomials of one batch must have the same size")
+        return torch.stack(polys).contiguous(), n
+
+    # ---- lpc_commitment_scheme (lpc.hpp:95-111)
+    def commit(self, index):
+        self._locked[index] = True
+        self._points.setdefault(index, [[] for _ in self._polys[index]])
+        batch, n = self._batch_tensor(index)
+        log_n = n.bit_length() - 1
+        tree = self.ctx.lpc_commit(self.F.name, self.hash_id, batch, log_n, self.fri.log_d0, self.fri.step_list[0],
+                                   keep_tree=True)
+        self._trees[index] = tree
+        return tree.root()
+
+    def mark_batch_as_fixed(self, index):
+        self._fixed[index] = True
+
+    def setup(self, transcript, fixed_values):
+        self._etha = transcript.challenge(self.F.p)
+        self._fixed_values = fixed_values
+
+    # ---- eval_polys (batched_commitment.hpp:176-190)
+    def eval_polys(self):
+        self._coeffs = {}
+        self.z = {}
+        for k in sorted(self._polys):
+            batch, n = self._batch_tensor(k)
+            import torch
+            co = torch.empty_like(batch)
+            self.ctx.ntt(self.F.name, batch, n.bit_length() - 1, inverse=True, out=co)
+            self._coeffs[k] = (co, n)
+            union = []
+            for pts in self._points[k]:
+                for x in pts:
+                    if x not in union:
+                        union.append(x)
+            if not union:
+                self.z[k] = [[] for _ in self._points[k]]
+                continue
+            vals = self.ctx.poly_evaluate(self.F.name, co, n, union)
+            self.z[k] = [[vals[i][union.index(x)] for x in pts] for i, pts in enumerate(self._points[k])]
+        return self.z
+
+    def _unique_points(self):
+        out = []
+        for k in sorted(self._points):
+            for pts in self._points[k]:
+                for x in pts:
+                    if x not in out:
+                        out.append(x)
+        return out
+
+    # ---- proof_eval up to the end of the FRI commit phase (lpc.hpp:113-200)
+    def proof_eval(self, transcript, keep_trees=False, keep_fs=False):
+        import torch
+        p = self.F.p
+        self.eval_polys()
+        for k in sorted(self._trees):
+            transcript(self._trees[k].root())
+        theta = transcript.challenge(p)
+        theta_acc = 1
+        n_max = max(n for _, n in self._coeffs.values())
+        dev = next(iter(self._coeffs.values()))[0].device
+        combined = torch.zeros((n_max, 8), dtype=torch.int32, device=dev)
+        numer = torch.empty((n_max, 8), dtype=torch.int32, device=dev)
+        quot = torch.empty((n_max, 8), dtype=torch.int32, device=dev)
+        remainders = []
+
+        def add_quotient(point, terms):
+            """terms: list of (batch index, scalars per polynomial, constant)"""
+            numer.zero_()
+            for k, scalars, constant in terms:
+                co, n = self._coeffs[k]
+                self.ctx.poly_lincomb(self.F.name, co, n, scalars, constant=constant, out=numer, accumulate=True)
+            _, rem = self.ctx.poly_div_linear(self.F.name, numer, n_max, point, out=quot)
+            remainders.append(rem)
+            self.ctx.vec(self.F.name, capi.VEC_ADD, combined, quot, out=combined)
+
+        for point in self._unique_points():
+            terms = []
+            for k in sorted(self._polys):
+                scalars, constant, used = [], 0, False
+                for i, pts in enumerate(self._points[k]):
+                    if point not in pts:
+                        scalars.append(0)
+                        continue
+                    j = pts.index(point)
+                    scalars.append(theta_acc)
+                    constant = (constant + self.z[k][i][j] * theta_acc) % p
+                    theta_acc = theta_acc * theta % p
+                    used = True
+                if used:
+                    terms.append((k, scalars, constant))
+            add_quotient(point, terms)
+        for k in sorted(self._polys):
+            if not self._fixed.get(k):
+                continue
+            scalars, constant = [], 0
+            for i in range(len(self._polys[k])):
+                scalars.append(theta_acc)
+                constant = (constant + self._fixed_values[k][i] * theta_acc) % p
+                theta_acc = theta_acc * theta % p
+            add_quotient(self._etha, [(k, scalars, constant)])
+        # combined_Q.from_coefficients(combined_Q_normal) and precommit's resize to D[0]: the same polynomial
+        # evaluated on D[0] - one forward NTT of the zero-padded coefficients
+        nd = 1 << self.fri.log_d0
+        q_d0 = torch.zeros((1, nd, 8), dtype=torch.int32, device=dev)
+        q_d0[0, :n_max] = combined
+        self.ctx.ntt(self.F.name, q_d0, self.fri.log_d0)
+        fri = self.ctx.fri_commit_phase(
+            self.F.name, self.hash_id, q_d0[0], self.fri.log_d0, self.fri.step_list,
+            lambda rnd, root, count: (transcript(root), [transcript.challenge(p) for _ in range(count)])[1],
+            keep_trees=keep_trees, keep_fs=keep_fs)
+        return {"z": self.z, "theta": theta, "combined_Q_normal": combined, "combined_Q": q_d0[0],
+                "remainders": remainders, "fri": fri}
+
+
+def host_poly(vals):
+    """list of integers -> [n, 8] uint32 array (helper for callers that hold Python integers)"""
+    return np.ascontiguousarray(_int_rows(vals))

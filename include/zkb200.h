@@ -65,6 +65,7 @@ typedef enum { ZKB_MEM_HOST = 0, ZKB_MEM_DEVICE = 1 } zkb_mem;
 typedef struct zkb_ctx zkb_ctx;
 typedef struct zkb_msm_bases zkb_msm_bases;
 typedef struct zkb_merkle_tree zkb_merkle_tree;
+typedef struct zkb_sparse_matrix zkb_sparse_matrix;
 
 /* ---- library / context ------------------------------------------------------------------- */
 const char *zkb_version(void);
@@ -151,6 +152,57 @@ uint64_t zkb_merkle_leaves(const zkb_merkle_tree *tree);
  * (containers::merkle_proof<Hash,2>(tree, index), basic_fri.hpp:526-531) */
 int zkb_merkle_path(zkb_ctx *ctx, const zkb_merkle_tree *tree, uint64_t index, uint8_t *path_out);
 void zkb_merkle_free(zkb_merkle_tree *tree);
+
+/* ---- FRI commit phase: zk::algorithms::proof_eval<FRI>, "Commit phase" ---------------------------- */
+/* zk/commitments/detail/polynomial/basic_fri.hpp:706-737.  f: the combined polynomial Q in evaluation form on
+ * D[0] (2^log_n elements).  For every round i < rounds: tree_i = precommit<FRI>(f, D[t], step_list[i]); its root
+ * goes to the caller's transcript, which answers with step_list[i] folding challenges; f is folded that many
+ * times (fold_polynomial(f, alpha_t, D[t]), t running over all steps).  The transcript stays on the reference
+ * side of the boundary: `challenge` is called once per round, on the calling thread, with the root digest, and
+ * writes `count` = step_list[round] field elements (canonical limbs, 8 per element) to alphas_out; a non-zero
+ * return aborts the call with ZKB_ERR_INVALID_ARGUMENT.
+ *   roots_out      host, rounds digests (fri_roots)
+ *   trees_out      NULL, or `rounds` handles (fri_trees; tree 0 is combined_Q_precommitment); free with zkb_merkle_free
+ *   fs_device_out  NULL, or DEVICE memory that receives f after every round back to back (fs[1..rounds]):
+ *                  sum_i 2^(log_n - step_list[0] - .. - step_list[i]) elements
+ *   alphas_out     NULL, or host, sum(step_list) elements
+ *   final_poly_out NULL, or host, 2^(log_n - sum(step_list)) elements: final_polynomial = f.coefficients() */
+typedef int (*zkb_fri_challenge_fn)(void *user, uint32_t round, const uint8_t *root, uint32_t root_bytes, uint32_t count,
+                                    uint32_t *alphas_out);
+int zkb_fri_commit_phase(zkb_ctx *ctx, int field, int hash, int log_n, const void *f, int mem, const uint32_t *step_list,
+                         uint32_t rounds, zkb_fri_challenge_fn challenge, void *user, uint8_t *roots_out,
+                         zkb_merkle_tree **trees_out, void *fs_device_out, uint32_t *alphas_out, uint32_t *final_poly_out,
+                         void *stream);
+
+/* ---- opening side of the LPC scheme: eval_polys and the combined quotient Q ------------------------- */
+typedef enum { ZKB_POLY_COEFFICIENTS = 0, ZKB_POLY_DFS = 1 } zkb_poly_form;
+/* polys_evaluator::eval_polys (zk/commitments/batched_commitment.hpp:176-190): _z(k,i,j) = polys[i].evaluate(point_j).
+ * polys: [batch][n], coefficient form (any n) or evaluations on the 2^k subgroup (ZKB_POLY_DFS, n = 2^k: the
+ * coefficients are recovered by one batched inverse NTT, as polynomial_dfs::evaluate does);
+ * points: host, npoints elements; out: host, [batch][npoints] elements. */
+int zkb_poly_evaluate(zkb_ctx *ctx, int field, int form, uint64_t n, uint32_t batch, const void *polys, int mem,
+                      uint32_t npoints, const uint32_t *points, uint32_t *out, void *stream);
+/* numerator of one point of lpc::proof_eval's combined Q (zk/commitments/polynomial/lpc.hpp:139-153, 163-176):
+ * out[i] (+)= sum_j scalars[j] * polys[j][i] - [i == 0] * constant, with scalars[j] = theta^k for the polynomials
+ * opened at the point and 0 for the others (skipped), constant = sum_j theta^k z_j (NULL = 0).
+ * polys / out: DEVICE, coefficient form, [batch][n] / [n]; scalars: host [batch]; accumulate != 0 adds to out. */
+int zkb_poly_lincomb(zkb_ctx *ctx, int field, uint64_t n, uint32_t batch, const void *polys_device, const uint32_t *scalars,
+                     const uint32_t *constant, void *out_device, int accumulate, void *stream);
+/* Q_normal / V with V = X - point (lpc.hpp:154,177): out = quotient (n-1 coefficients, out[n-1] = 0), the remainder
+ * in(point) is dropped like upstream polynomial division does and returned through remainder_out (host, may be
+ * NULL) so that callers can assert it is zero.  in / out: DEVICE, distinct buffers of n elements. */
+int zkb_poly_div_linear(zkb_ctx *ctx, int field, uint64_t n, const void *in_device, const uint32_t *point, void *out_device,
+                        uint32_t *remainder_out, void *stream);
+
+/* ---- R1CS rows: cs.constraints[i].a/b/c.evaluate(full_variable_assignment) --------------------------- */
+/* zk/snark/reductions/r1cs_to_qap.hpp:245-248, 289-291.  One CSR matrix per side of the constraint system (part of
+ * the proving key, so it is uploaded once): row i = linear combination i, column j = variable j with column 0 the
+ * constant 1 (x[0] = 1, x[1..] = primary || auxiliary input).  values: host, canonical limbs, nnz elements. */
+int zkb_sparse_matrix_create(zkb_ctx *ctx, int field, uint64_t rows, uint64_t cols, const uint64_t *row_ptr,
+                             const uint32_t *col_idx, const uint32_t *values, void *stream, zkb_sparse_matrix **out);
+void zkb_sparse_matrix_free(zkb_sparse_matrix *m);
+/* y[i] = sum_k values[k] * x[col_idx[k]] over row i; x: `cols` elements (host or device), y: DEVICE, `rows` elements */
+int zkb_sparse_matvec(zkb_ctx *ctx, const zkb_sparse_matrix *m, const void *x, int x_mem, void *y_device, void *stream);
 
 /* ---- MSM: algebra::multiexp<Method> / multiexp_with_mixed_addition<Method> --------------------- */
 /* Call sites: zk/commitments/polynomial/kzg.hpp:146,414,433 ; kzg_v2.hpp:215 ;

@@ -98,3 +98,27 @@ def lpc_commit(polys_dfs, field, degree_log, expand_factor, fri_step, h):
     """lpc_commitment_scheme::commit: D[0] has size 2^(degree_log+expand_factor) (basic_fri.hpp:162)."""
     levels, _ = precommit(polys_dfs, field, 1 << (degree_log + expand_factor), fri_step, h)
     return levels[-1][0]
+
+
+def commit_phase(f, field, log_n, step_list, h, transcript):
+    """Commit phase of zk::algorithms::proof_eval<FRI> (basic_fri.hpp:706-737), dfs form, literal order:
+    for every round: push f, tree = precommit(f, D[t], step_list[i]) (round 0: combined_Q_precommitment),
+    transcript(root), then step_list[i] times { alpha = transcript.challenge(); f = fold(f, alpha, D[t]); t++ }.
+    `transcript`: object with absorb(bytes) and challenge(field) (oracle.hashes.FiatShamirSequential).
+    Returns dict(fs, roots, alphas, final_polynomial, levels)."""
+    from .ntt import dfs_coefficients
+    f = list(f)
+    fs, roots, alphas, all_levels = [], [], [], []
+    t = 0
+    for i, step in enumerate(step_list):
+        fs.append(f)
+        levels, _ = precommit([f], field, 1 << (log_n - t), step, h)
+        all_levels.append(levels)
+        roots.append(levels[-1][0])
+        transcript.absorb(levels[-1][0])
+        for _ in range(step):
+            alphas.append(transcript.challenge(field))
+            f = fold_polynomial_dfs(f, alphas[t], field, 1 << (log_n - t))
+            t += 1
+    fs.append(f)
+    return {"fs": fs, "roots": roots, "alphas": alphas, "final_polynomial": dfs_coefficients(f, field), "levels": all_levels}

@@ -1,0 +1,278 @@
+"""GPU parity of the callers of the hot path through the C ABI:
+FRI commit phase, eval_polys, combined Q, and the lpc_commitment_scheme flow, bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import fields, fri, hashes, lpc, ntt
+
+pytestmark = pytest.mark.gpu
+
+HASHES = {0: hashes.keccak256, 1: hashes.sha256, 2: hashes.keccak512}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from crypto3_zk_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def to_arr(vals, limbs=8):
+    return fields.ints_to_u32_array(vals, limbs)
+
+
+def from_arr(a):
+    return fields.u32_array_to_ints(np.asarray(a).reshape(-1, a.shape[-1]))
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+class OracleTranscript:
+    """adapts oracle.hashes.FiatShamirSequential to the product's transcript interface"""
+
+    def __init__(self, h, F, init=b"\x00"):
+        self.t, self.F = hashes.FiatShamirSequential(h, init), F
+
+    def __call__(self, data):
+        self.t.absorb(data)
+
+    def challenge(self, modulus):
+        assert modulus == self.F.p
+        return self.t.challenge(self.F)
+
+
+@pytest.mark.parametrize("hid", [0, 1, 2], ids=["keccak256", "sha256", "keccak512"])
+@pytest.mark.parametrize("F,log_n,steps", [(fields.PALLAS_FQ, 6, [1, 1, 1]), (fields.PALLAS_FP, 8, [2, 1, 3]),
+                                           (fields.BLS12_381_FR, 7, [3, 2, 1, 1]), (fields.BN254_FR, 5, [1])],
+                         ids=lambda v: getattr(v, "name", str(v)))
+def test_fri_commit_phase_vs_oracle(ctx, hid, F, log_n, steps):
+    """zk::algorithms::proof_eval<FRI> commit phase (basic_fri.hpp:706-737)."""
+    h = HASHES[hid]
+    f = fields.random_elements(F, 1 << log_n, 11 + log_n)
+    want = fri.commit_phase(f, F, log_n, steps, h, hashes.FiatShamirSequential(h, b"init"))
+    tr = OracleTranscript(h, F, b"init")
+
+    def challenge(rnd, root, count):
+        tr(root)
+        return [tr.challenge(F.p) for _ in range(count)]
+
+    for data in (to_arr(f), dev(to_arr(f))):
+        tr = OracleTranscript(h, F, b"init")
+        got = ctx.fri_commit_phase(F.name, hid, data, log_n, steps, challenge, keep_trees=True, keep_fs=True)
+        assert got["roots"] == want["roots"]
+        assert got["alphas"] == want["alphas"]
+        assert got["final_polynomial"] == want["final_polynomial"]
+        assert from_arr(host(got["fs"])) == [v for fs in want["fs"][1:] for v in fs]
+        for tree, levels in zip(got["trees"], want["levels"]):
+            assert tree.root() == levels[-1][0]
+            idx = min(1, tree.leaves - 1)
+            assert tree.path(idx) == fri.merkle_proof(levels, idx)
+
+
+def test_fri_commit_phase_errors(ctx):
+    from crypto3_zk_b200 import capi
+    F = fields.PALLAS_FQ
+    f = to_arr(fields.random_elements(F, 16, 1))
+    with pytest.raises(capi.ZkbInvalidArgument):
+        ctx.fri_commit_phase(F.name, 0, f, 4, [3, 2], lambda r, root, c: [1] * c)
+    with pytest.raises(capi.ZkbInvalidArgument):
+        ctx.fri_commit_phase(F.name, 0, f, 4, [], lambda r, root, c: [1] * c)
+    with pytest.raises(ZeroDivisionError):   # an exception in the caller's transcript surfaces unchanged
+        ctx.fri_commit_phase(F.name, 0, f, 4, [1, 1], lambda r, root, c: [1 // 0])
+
+
+def test_fri_commit_phase_large_matches_coefficient_folds(ctx):
+    """Size-independent identity at a Placeholder-sized domain (2^20 rows, blow-up 4): the final polynomial equals
+    the coefficient folds f_even + alpha f_odd of the committed polynomial with the same challenges."""
+    import torch
+    from crypto3_zk_b200.transcript import FiatShamirSequential
+    F = fields.PALLAS_FQ
+    log_deg, log_n = 12, 22
+    co = fields.random_elements(F, 1 << log_deg, 77)
+    x = torch.zeros((1, 1 << log_n, 8), dtype=torch.int32, device="cuda")
+    x[0, :1 << log_deg] = dev(to_arr(co))
+    ctx.ntt(F.name, x, log_n)
+    tr = FiatShamirSequential(0)
+    steps = [1] * (log_deg - 1)
+    got = ctx.fri_commit_phase(F.name, 0, x[0], log_n, steps, lambda r, root, c: (tr(root), tr.challenges(F.p, c))[1])
+    c = co
+    for a in got["alphas"]:
+        c = fri.fold_polynomial_coeffs(c, a, F.p)
+    fin = got["final_polynomial"]
+    assert len(fin) == 1 << (log_n - sum(steps))
+    assert fin[:len(c)] == c and not any(fin[len(c):])
+
+
+@pytest.mark.parametrize("F", [fields.PALLAS_FQ, fields.BLS12_381_FR], ids=lambda f: f.name)
+@pytest.mark.parametrize("n,batch,npts", [(1, 1, 1), (5, 2, 1), (256, 3, 2), (1000, 2, 5), (5000, 4, 9)])
+def test_poly_evaluate_vs_oracle(ctx, F, n, batch, npts):
+    polys = [fields.random_elements(F, n, 100 + b) for b in range(batch)]
+    pts = fields.random_elements(F, npts, 9) if npts > 1 else [0]
+    want = [[lpc.poly_eval(c, x, F.p) for x in pts] for c in polys]
+    a = to_arr([v for c in polys for v in c]).reshape(batch, n, 8)
+    assert ctx.poly_evaluate(F.name, a, n, pts) == want
+    assert ctx.poly_evaluate(F.name, dev(a), n, pts) == want
+
+
+def test_poly_evaluate_dfs_and_large(ctx):
+    """polynomial_dfs::evaluate = coefficients() then the value; 2^20-sized columns against Horner on the CPU."""
+    F = fields.PALLAS_FQ
+    vals = [fields.random_elements(F, 64, 5 + b) for b in range(3)]
+    pts = fields.random_elements(F, 3, 6)
+    a = to_arr([v for c in vals for v in c]).reshape(3, 64, 8)
+    assert ctx.poly_evaluate(F.name, dev(a), 64, pts, dfs=True) == [[ntt.dfs_evaluate(v, F, x) for x in pts] for v in vals]
+    n = 1 << 20
+    rng = np.random.Generator(np.random.PCG64(5))
+    big = rng.integers(0, 1 << 32, size=(2, n, 8), dtype=np.uint64).astype(np.uint32)
+    big[..., 7] &= 0x0FFFFFFF
+    x = pts[0]
+    got = ctx.poly_evaluate(F.name, dev(big), n, [x, 1])
+    for b in range(2):
+        co = fields.u32_array_to_ints(big[b])
+        assert got[b][0] == lpc.poly_eval(co, x, F.p)
+        assert got[b][1] == sum(co) % F.p
+
+
+@pytest.mark.parametrize("F", [fields.PALLAS_FP, fields.BN254_FR], ids=lambda f: f.name)
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 2047, 2048, 2049, 5000, 1 << 15])
+def test_poly_div_linear_vs_oracle(ctx, F, n):
+    c = fields.random_elements(F, n, 200 + n)
+    z = fields.random_elements(F, 1, 3)[0]
+    q, rem = ctx.poly_div_linear(F.name, dev(to_arr(c)), n, z)
+    assert rem == lpc.poly_eval(c, z, F.p)
+    assert from_arr(host(q)) == lpc.poly_div_linear(c, z, F.p) + [0]
+
+
+def test_poly_lincomb_vs_oracle(ctx):
+    F = fields.PALLAS_FQ
+    p, n, batch = F.p, 300, 5
+    polys = [fields.random_elements(F, n, 300 + b) for b in range(batch)]
+    sc = fields.random_elements(F, batch, 7)
+    sc[2] = 0
+    const = 123456789
+    a = dev(to_arr([v for c in polys for v in c]).reshape(batch, n, 8))
+    want = [sum(s * c[i] for s, c in zip(sc, polys)) % p for i in range(n)]
+    want0 = list(want)
+    want0[0] = (want0[0] - const) % p
+    out = ctx.poly_lincomb(F.name, a, n, sc, constant=const)
+    assert from_arr(host(out)) == want0
+    ctx.poly_lincomb(F.name, a, n, sc, out=out, accumulate=True)
+    assert from_arr(host(out)) == [(x + y) % p for x, y in zip(want0, want)]
+
+
+@pytest.mark.parametrize("F,hid", [(fields.PALLAS_FQ, 0), (fields.BLS12_381_FR, 1)], ids=["pallas-keccak", "bls-sha256"])
+def test_lpc_scheme_flow_vs_oracle(ctx, F, hid):
+    """lpc_commitment_scheme: commit per batch (lpc.hpp:101-106), eval_polys (batched_commitment.hpp:176-190),
+    combined Q (lpc.hpp:126-181) and the FRI commit phase (basic_fri.hpp:706-737), in the reference's transcript order."""
+    from crypto3_zk_b200.lpc import FriParams, LpcCommitmentScheme
+    h, p = HASHES[hid], F.p
+    degree_log, expand, steps = 5, 2, [1, 2, 1]
+    n, log_d0 = 1 << degree_log, degree_log + expand
+    polys = {0: [fields.random_elements(F, n, 1 + i) for i in range(2)],
+             1: [fields.random_elements(F, n, 10 + i) for i in range(3)],
+             3: [fields.random_elements(F, n, 20)]}
+    y = fields.random_elements(F, 1, 99)[0]
+    yw = y * F.omega(degree_log) % p
+    points = {0: [[y], [y]], 1: [[y], [y, yw], [yw]], 3: [[y]]}
+    # ---- oracle, in the reference's order: setup (etha), commits, proof_eval
+    tr = hashes.FiatShamirSequential(h, b"\x05")
+    etha = tr.challenge(F)
+    roots = {k: fri.lpc_commit(polys[k], F, degree_log, expand, steps[0], h) for k in polys}
+    z = lpc.eval_polys(polys, points, F)
+    for k in sorted(roots):
+        tr.absorb(roots[k])
+    theta = tr.challenge(F)
+    fixed_values = {0: [lpc.poly_eval(ntt.dfs_coefficients(q, F), etha, p) for q in polys[0]]}
+    q_normal, q_dfs = lpc.combined_q(polys, points, z, theta, F, fixed_batches=(0,), etha=etha, fixed_values=fixed_values)
+    q_d0 = ntt.dfs_resize(q_dfs, F, 1 << log_d0)
+    want = fri.commit_phase(q_d0, F, log_d0, steps, h, tr)
+    # ---- device
+    scheme = LpcCommitmentScheme(ctx, F.name, hid, FriParams(steps, degree_log, 40, expand))
+    t2 = OracleTranscript(h, F, b"\x05")
+    for k in polys:
+        scheme.append_to_batch(k, dev(to_arr([v for c in polys[k] for v in c]).reshape(len(polys[k]), n, 8)))
+    scheme.mark_batch_as_fixed(0)
+    scheme.setup(t2, fixed_values)
+    assert {k: scheme.commit(k) for k in polys} == roots
+    for k in points:
+        for i, pts in enumerate(points[k]):
+            for x in pts:
+                scheme.append_eval_point(k, x, poly=i)
+    got = scheme.proof_eval(t2, keep_fs=True)
+    assert got["z"] == z
+    assert got["theta"] == theta
+    assert got["remainders"] == [0] * len(got["remainders"]) and len(got["remainders"]) == 3
+    assert from_arr(host(got["combined_Q_normal"])) == q_normal + [0] * (n - len(q_normal))
+    assert from_arr(host(got["combined_Q"])) == q_d0
+    assert got["fri"]["roots"] == want["roots"]
+    assert got["fri"]["alphas"] == want["alphas"]
+    assert got["fri"]["final_polynomial"] == want["final_polynomial"]
+
+
+# ------------------------------------------------------------------------------------------ Groth16 (config #4)
+@pytest.mark.parametrize("F", [fields.BN254_FR, fields.BLS12_381_FR], ids=lambda f: f.name)
+def test_sparse_matvec_vs_oracle(ctx, F):
+    """cs.constraints[i].a/b/c.evaluate(full_variable_assignment) (r1cs_to_qap.hpp:245-248, 289-291), including the
+    closing constraint of generate_r1cs_example_with_field_input whose rows sum every variable (long-row path)."""
+    import torch
+    from crypto3_zk_b200.groth16 import R1csConstraintSystem
+    from oracle import groth16
+    p = F.p
+    cs, primary, aux = groth16.example_with_field_input(F, 5000, 10, seed=3)
+    x = [1] + primary + aux
+    pcs = R1csConstraintSystem(cs.num_inputs, cs.num_aux, cs.constraints)
+    xd = dev(to_arr(x))
+    for side in range(3):
+        rp, ci, va = pcs.csr(side)
+        mat = ctx.sparse_matrix(F.name, cs.num_constraints, cs.num_variables + 1, rp, ci, va)
+        y = torch.zeros((cs.num_constraints, 8), dtype=torch.int32, device="cuda")
+        mat.matvec(xd, y)
+        want = [sum(co * x[i] for i, co in con[side]) % p for con in cs.constraints]
+        assert from_arr(host(y)) == want
+        y2 = torch.zeros_like(y)
+        mat.matvec(to_arr(x), y2)      # host assignment
+        assert torch.equal(y, y2)
+        mat.free()
+
+
+def _device_key(ctx, pk, G1, G2):
+    from crypto3_zk_b200.groth16 import ProvingKey, R1csConstraintSystem
+    pcs = R1csConstraintSystem(pk.cs.num_inputs, pk.cs.num_aux, pk.cs.constraints)
+    return ProvingKey(ctx, G1.name, G2.name, pcs, pk.alpha_g1, pk.beta_g1, pk.beta_g2, pk.delta_g1, pk.delta_g2,
+                      pk.A_query, pk.B_indices, pk.B_g2, pk.B_g1, pk.H_query, pk.L_query)
+
+
+@pytest.mark.parametrize("curve,kind,nc,ni", [("bn254", "field", 28, 3), ("bn254", "binary", 59, 4), ("bls12_381", "field", 13, 2)])
+def test_groth16_prove_vs_oracle(ctx, curve, kind, nc, ni):
+    """r1cs_gg_ppzksnark_prover::process (prover.hpp:73-158): witness map + the four MSMs (A, B on G2 and G1, H, L) and
+    the proof assembly on the device, bit-exact (affine) against the oracle's restatement and against the Groth16
+    relations in the exponent."""
+    from crypto3_zk_b200 import groth16 as dg
+    from oracle import curves, groth16
+    F, G1, G2 = ((fields.BN254_FR, curves.BN254_G1, curves.BN254_G2) if curve == "bn254" else
+                 (fields.BLS12_381_FR, curves.BLS12_381_G1, curves.BLS12_381_G2))
+    make = groth16.example_with_field_input if kind == "field" else groth16.example_with_binary_input
+    cs, primary, aux = make(F, nc, ni, seed=5)
+    t, alpha, beta, gamma, delta = fields.random_elements(F, 5, 21)
+    pk = groth16.generator(cs, G1, G2, F, t, alpha, beta, gamma, delta)
+    r, s = fields.random_elements(F, 2, 22)
+    want = groth16.prove(pk, primary, aux, r, s, G1, G2, F)
+    dpk = _device_key(ctx, pk, G1, G2)
+    # the witness map alone (r1cs_to_qap.hpp:219-325)
+    m, full, H = groth16.witness_map(pk.cs, primary, aux, F)
+    h = dg.witness_map(ctx, dpk, dev(to_arr([1] + full)))
+    assert from_arr(host(h)) == H[:m]
+    got = dg.prove(ctx, dpk, primary, aux, r, s)
+    assert got == want
+    a, b, c = groth16.proof_in_the_exponent(pk, primary, aux, r, s, F)
+    assert got[0] == G1.mul(G1.gen, a) and got[1] == G2.mul(G2.gen, b) and got[2] == G1.mul(G1.gen, c)
+    # zero randomness and a binary assignment exercise the 0/1 scalar paths of the MSM
+    assert dg.prove(ctx, dpk, primary, aux, 0, 0) == groth16.prove(pk, primary, aux, 0, 0, G1, G2, F)
