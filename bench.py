@@ -323,6 +323,119 @@ def lpc_sharded_extra(args, torch, ctx, dev, dist, rank, world):
                                            "collective": "all_to_all_single of (N-1)/N of the LDE output, all_gather of N roots", **out}}
 
 
+def groth16_extra(args, torch, ctx, dev):
+    """BASELINE configs[3]: r1cs_gg_ppzksnark prover on BN254, synthetic chain R1CS with domain 2^groth16_log
+    (#constraints = 2^k - n - 1, n = 10: SURVEY 8(d)); witness map + A / B(G2,G1) / H / L MSMs + assembly on the device.
+    The key holds synthetic points of the reference's query sizes, so the proof is not a valid proof - the work is."""
+    import numpy as np
+    from crypto3_zk_b200 import groth16 as dg, workloads as W
+    log_m, ni = args.groth16_log, 10
+    m = 1 << log_m
+    nc = m - ni - 1
+    t0 = time.perf_counter()
+    cs, sides, x = W.groth16_field_input_example("bn254_fr", nc, ni)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pk = W.groth16_synthetic_key(ctx, "bn254_g1", "bn254_g2", cs, sides)
+    torch.cuda.synchronize()
+    t_key = time.perf_counter() - t0
+    hx = torch.from_numpy(x.view(np.int32)).pin_memory()
+    xd = hx.to(dev)
+    r, s = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
+    h = dg.witness_map(ctx, pk, xd)
+    # the assignment satisfies the system, so A*B - C is divisible by Z: H has degree <= m - 2
+    h_ok = bool((h[m - 1] == 0).all().item()) and bool((h[m - 2] != 0).any().item())
+    wm_ms = time_cuda(torch, lambda: dg.witness_map(ctx, pk, xd), 3, warmup=1)
+    dg.prove(ctx, pk, None, None, r, s, x_device=xd)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        proof = dg.prove(ctx, pk, None, None, r, s, x_device=xd)
+    torch.cuda.synchronize()
+    prove_ms = (time.perf_counter() - t0) / 3 * 1e3
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dg.prove(ctx, pk, None, None, r, s, x_device=hx.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+    sc = rand_elems(torch, (m, 8), 5, dev)
+    parts = {"msm_A_g1": time_cuda(torch, lambda: ctx.multiexp(pk.A, sc[:pk.A.n]), 3),
+             "msm_B_g2": time_cuda(torch, lambda: ctx.multiexp(pk.B2, sc[:pk.B2.n]), 3),
+             "msm_B_g1": time_cuda(torch, lambda: ctx.multiexp(pk.B1, sc[:pk.B1.n]), 3),
+             "msm_H_g1": time_cuda(torch, lambda: ctx.multiexp(pk.H, sc[:pk.H.n]), 3),
+             "msm_L_g1": time_cuda(torch, lambda: ctx.multiexp(pk.L, sc[:pk.L.n]), 3)}
+    return {"ms_per_proof": prove_ms, "e2e_ms_host_assignment": e2e_ms, "witness_map_ms": wm_ms, "parts_ms_random_scalars": parts,
+            "domain": m, "constraints": nc, "variables": cs.num_variables, "inputs": ni,
+            "msm_sizes": {"A": pk.A.n, "B": pk.B2.n, "H": m - 1, "L": pk.L.n},
+            "h_degree_check": h_ok, "proof_x_limb": (proof[0][0] & 0xFFFFFFFF) if proof[0] else None,
+            "host_prep_s": {"r1cs_example": t_build, "synthetic_key": t_key},
+            "reference_published": "docs/perf.md:24-25: 84.01 s for 10^6 constraints on an i7-4770, 1 thread (other hardware)"}
+
+
+def placeholder_extra(args, torch, ctx, dev):
+    """BASELINE configs[4]: commitment phase of the Placeholder prover on a synthetic 2^placeholder_log-row Pallas
+    circuit (column shape of the reference's widest test circuit): lpc commit of the variable / permutation / quotient
+    batches (prover.hpp:141,170,202,213), then lpc proof_eval up to the end of the FRI commit phase (eval_polys,
+    combined Q, r rounds of fold + Merkle).  The fixed batch is committed once per circuit (preprocessor.hpp:481-489)."""
+    from crypto3_zk_b200 import workloads as W
+    from crypto3_zk_b200.fields import FIELD_BY_NAME, omega
+    from crypto3_zk_b200.lpc import FriParams, LpcCommitmentScheme
+    from crypto3_zk_b200.transcript import FiatShamirSequential
+    rows_log = args.placeholder_log
+    n = 1 << rows_log
+    F = FIELD_BY_NAME["pallas_fp"]
+    sizes = W.placeholder_batches()
+    cols = {k: rand_elems(torch, (cnt, n, 8), 300 + k, dev) for k, cnt in sizes.items()}
+    out = {"rows": n, "field": "pallas_fp", "batches": sizes,
+           "note": "fri_params(1, rows_log, lambda 40, expand_factor) as test/systems/plonk/placeholder/placeholder.cpp:231; "
+                   "every column opened at y, variable and permutation columns also at y*omega"}
+    for name, expand, hid in (("expand_factor_4_keccak512", 4, 2), ("expand_factor_3_keccak256", 3, 0)):
+        torch.cuda.empty_cache()
+        fri = FriParams.with_max_step_one(rows_log, 40, expand)
+        res = {}
+        for it in range(2):   # first pass warms tables and scratch
+            tr = FiatShamirSequential(0 if hid != 2 else 2, b"placeholder")
+            scheme = LpcCommitmentScheme(ctx, F.name, hid, fri)
+            for k in sizes:
+                scheme.append_to_batch(k, cols[k])
+            scheme.mark_batch_as_fixed(0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            scheme.commit(0)
+            torch.cuda.synchronize()
+            res["fixed_batch_commit_ms_once_per_circuit"] = (time.perf_counter() - t0) * 1e3
+            scheme.setup(tr, {0: [0] * sizes[0]})
+            t_commit = {}
+            for k, label in ((1, "variable"), (2, "permutation"), (3, "quotient")):
+                t0 = time.perf_counter()
+                tr(scheme.commit(k))
+                torch.cuda.synchronize()
+                t_commit[label] = (time.perf_counter() - t0) * 1e3
+            y = tr.challenge(F.p)
+            yw = y * omega(F, rows_log) % F.p
+            for k in sizes:
+                scheme.append_eval_point(k, y)
+            for k in (1, 2):
+                scheme.append_eval_point(k, yw)
+            # fixed-batch values at etha: evaluate them the same way eval_polys does, so the quotient is exact
+            co = scheme.ctx.ntt(F.name, cols[0].clone(), rows_log, inverse=True)
+            scheme._fixed_values = {0: [v[0] for v in ctx.poly_evaluate(F.name, co, n, [scheme._etha])]}
+            del co
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pe = scheme.proof_eval(tr)
+            torch.cuda.synchronize()
+            t_eval = (time.perf_counter() - t0) * 1e3
+            res.update({"commit_ms": t_commit, "proof_eval_commit_phase_ms": t_eval,
+                        "ms_per_proof_commitment_phase": sum(t_commit.values()) + t_eval,
+                        "fri_rounds": len(pe["fri"]["roots"]), "log_d0": fri.log_d0,
+                        "quotients_exact": all(r == 0 for r in pe["remainders"]),
+                        "final_polynomial_len": len(pe["fri"]["final_polynomial"])})
+            del scheme, pe
+        out[name] = res
+    return out
+
+
 def lpc_extra(args, torch, ctx, x, hbm_peak):
     from crypto3_zk_b200 import capi
     res = {}
@@ -345,6 +458,9 @@ def main():
     ap.add_argument("--log-out", type=int, default=23)
     ap.add_argument("--ntt-log", type=int, default=24)
     ap.add_argument("--msm-log", type=int, default=20)
+    ap.add_argument("--groth16-log", type=int, default=22)
+    ap.add_argument("--placeholder-log", type=int, default=20)
+    ap.add_argument("--no-flows", action="store_true", help="skip the configs[3]/[4] flows (Groth16 prover, Placeholder commitment phase)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -480,6 +596,15 @@ def main():
                 ex.update(extras(args, torch, ctx, dev, hbm_peak))
             except Exception as e:
                 ex["error"] = repr(e)
+            if not args.no_flows:
+                del x
+                for key, fn in (("groth16_bn254_2p%d" % args.groth16_log, groth16_extra),
+                                ("placeholder_commitment_phase_2p%d_pallas" % args.placeholder_log, placeholder_extra)):
+                    torch.cuda.empty_cache()
+                    try:
+                        ex[key] = fn(args, torch, ctx, dev)
+                    except Exception as e:
+                        ex[key] = {"error": repr(e)}
             line["extra"] = ex
     if world > 1 and not args.no_extras:
         del x, y

@@ -32,23 +32,16 @@ def _limbs(val, n):
 
 def _int_rows(vals, n=8):
     """list of integers -> [len, n] uint32 limb array"""
-    a = np.zeros((len(vals), n), dtype=np.uint32)
-    for i, v in enumerate(vals):
-        v = int(v)
-        for l in range(n):
-            a[i, l] = (v >> (32 * l)) & 0xFFFFFFFF
-    return a
+    blob = b"".join(int(v).to_bytes(4 * n, "little") for v in vals)
+    return np.frombuffer(blob, dtype=np.uint32).reshape(len(vals), n).copy()
 
 
 def _ints(arr):
     """[len, n] uint32 limb array -> list of integers"""
-    out = []
-    for row in np.asarray(arr, dtype=np.uint32).reshape(-1, arr.shape[-1]).tolist():
-        v = 0
-        for l, x in enumerate(row):
-            v |= x << (32 * l)
-        out.append(v)
-    return out
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.uint32).reshape(-1, arr.shape[-1]))
+    nb = 4 * a.shape[1]
+    raw = a.tobytes()
+    return [int.from_bytes(raw[i * nb:(i + 1) * nb], "little") for i in range(a.shape[0])]
 
 
 class _Buf:
