@@ -227,30 +227,77 @@ def extras(args, torch, ctx, dev, hbm_peak):
     return ex
 
 
-def msm_points(torch, ctx, np, log_m, first=0, count=None, seed=7):
-    """Synthetic distinct BLS12-381 G1 points P_i = A[i % 1024] + B[i // 1024], i in [first, first+count),
-    built on the device from two small tables of k*G."""
+def _kg_points(ctx, np, ks):
+    """k*G for each 256-bit scalar row of ks, through the product's own MSM entry point (one point per call)."""
     from crypto3_zk_b200.fields import CURVE_BY_NAME
-    nm, m = 1 << log_m, 1024
-    count = nm if count is None else count
-    assert first % m == 0
     C = CURVE_BY_NAME["bls12_381_g1"]
     gen = np.array([[(C.gen_x >> (32 * i)) & 0xFFFFFFFF for i in range(12)], [(C.gen_y >> (32 * i)) & 0xFFFFFFFF for i in range(12)]],
                    dtype=np.uint32).reshape(1, 2, 12)
     gb = ctx.msm_bases("bls12_381_g1", gen)
-    rng = np.random.Generator(np.random.PCG64(seed))
-    nbt = (nm + m - 1) // m
-    ks = rng.integers(0, 1 << 32, size=(m + nbt, 8), dtype=np.uint64).astype(np.uint32)
-    ks[:, 7] &= 0x0FFFFFFF
-    b0, b1 = first // m, (first + count + m - 1) // m
-    need = list(range(m)) + list(range(m + b0, m + b1))
-    tabs = np.zeros((len(need), 2, 12), dtype=np.uint32)
-    for j, i in enumerate(need):          # k_i * G through the product's own MSM entry point
-        pt = ctx.multiexp(gb, ks[i:i + 1])
+    tabs = np.zeros((len(ks), 2, 12), dtype=np.uint32)
+    for j in range(len(ks)):
+        pt = ctx.multiexp(gb, ks[j:j + 1])
         tabs[j, 0] = [(pt[0] >> (32 * k)) & 0xFFFFFFFF for k in range(12)]
         tabs[j, 1] = [(pt[1] >> (32 * k)) & 0xFFFFFFFF for k in range(12)]
     gb.free()
-    return ctx.grid_points("bls12_381_g1", count, tabs[:m], tabs[m:])
+    return tabs
+
+
+def _point_table(ctx, np, rng, count):
+    """`count` distinct points a_i*G + b_j*G: a grid over two sqrt(count)-sized tables of k*G (host array [count,2,12])"""
+    m = 32
+    while m * m < count:
+        m *= 2
+    ks = rng.integers(0, 1 << 32, size=(m + (count + m - 1) // m, 8), dtype=np.uint64).astype(np.uint32)
+    ks[:, 7] &= 0x0FFFFFFF
+    small = _kg_points(ctx, np, ks)
+    return ctx.grid_points("bls12_381_g1", count, small[:m], small[m:]).cpu().numpy().view(np.uint32).reshape(count, 2, 12)
+
+
+def msm_points(torch, ctx, np, log_m, first=0, count=None, seed=7):
+    """Synthetic distinct BLS12-381 G1 points P_i = A[i % m] + B[i // m], i in [first, first+count), built on the
+    device from two tables that are themselves grids over small tables of k*G (generate on the GPU)."""
+    nm = 1 << log_m
+    m = 1024 if log_m <= 22 else 8192
+    count = nm if count is None else count
+    assert first % m == 0
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nbt = (nm + m - 1) // m
+    ta = _point_table(ctx, np, rng, m)
+    tb = _point_table(ctx, np, rng, nbt)
+    b0, b1 = first // m, (first + count + m - 1) // m
+    return ctx.grid_points("bls12_381_g1", count, ta, tb[b0:b1])
+
+
+def msm_sweep_extra(args, torch, ctx, dev):
+    """BASELINE configs[2]: BLS12-381 G1 multiexp sweep over the sizes in --msm-sweep (random scalars, bases resident):
+    plain signed-digit Pippenger, and with the window table where the table fits in 24 GiB."""
+    import numpy as np
+    out = {}
+    for log_m in args.msm_sweep:
+        nm = 1 << log_m
+        try:
+            pts = msm_points(torch, ctx, np, log_m)
+            bases = ctx.msm_bases("bls12_381_g1", pts)
+            del pts
+            sc = rand_elems(torch, (nm, 8), 13, dev)
+            iters = 5 if log_m <= 22 else 2
+            e = {"ms": time_cuda(torch, lambda: ctx.multiexp(bases, sc), iters, warmup=1), "window_bits": max(2, min(20, log_m - 4))}
+            ct = max(8, min(22, log_m))
+            Wt = (255 + 1 + ct - 1) // ct
+            if nm * Wt * 96 <= (24 << 30):
+                bases.precompute(ct, 24 << 30)
+                e["ms_window_table"] = time_cuda(torch, lambda: ctx.multiexp(bases, sc), iters, warmup=1)
+                e["table_window_bits"] = ct
+            e["points_per_s"] = nm / (min(e["ms"], e.get("ms_window_table", e["ms"])) * 1e-3)
+            out["2p%d" % log_m] = e
+            bases.free()
+            del sc
+        except Exception as ex:   # a size that does not fit must not lose the others
+            out["2p%d" % log_m] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+    ctx.release_caches()   # the 2^26 run grew the MSM scratch to ~10 GB
+    return out
 
 
 def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
@@ -260,7 +307,7 @@ def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
     import numpy as np
     from crypto3_zk_b200.sharding import allgather_combine, shard_range
     out = {}
-    for log_m in (args.msm_log, args.msm_log + 2):
+    for log_m in args.msm_sharded:
         nm = 1 << log_m
         off, cnt = shard_range(nm // 1024, rank, world)
         off, cnt = off * 1024, cnt * 1024
@@ -277,7 +324,7 @@ def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 5
+        iters = 5 if log_m <= 22 else 2
         e0.record()
         for _ in range(iters):
             res = run()
@@ -458,6 +505,10 @@ def main():
     ap.add_argument("--log-out", type=int, default=23)
     ap.add_argument("--ntt-log", type=int, default=24)
     ap.add_argument("--msm-log", type=int, default=20)
+    ap.add_argument("--msm-sweep", type=lambda v: [int(t) for t in v.split(",") if t], default=[16, 18, 22, 24, 26],
+                    help="configs[2] sweep sizes (log2) timed at N=1 besides --msm-log")
+    ap.add_argument("--msm-sharded", type=lambda v: [int(t) for t in v.split(",") if t], default=[20, 22, 24, 26],
+                    help="fixed total sizes (log2) of the point-sharded MSM timed at N>1")
     ap.add_argument("--groth16-log", type=int, default=22)
     ap.add_argument("--placeholder-log", type=int, default=20)
     ap.add_argument("--no-flows", action="store_true", help="skip the configs[3]/[4] flows (Groth16 prover, Placeholder commitment phase)")
@@ -596,6 +647,11 @@ def main():
                 ex.update(extras(args, torch, ctx, dev, hbm_peak))
             except Exception as e:
                 ex["error"] = repr(e)
+            torch.cuda.empty_cache()
+            try:
+                ex["msm_g1_sweep_bls12_381"] = msm_sweep_extra(args, torch, ctx, dev)
+            except Exception as e:
+                ex["msm_g1_sweep_bls12_381"] = {"error": repr(e)}
             if not args.no_flows:
                 del x
                 for key, fn in (("groth16_bn254_2p%d" % args.groth16_log, groth16_extra),
