@@ -89,7 +89,7 @@ static void replay_pass(const NttPassParams &p) {
 #define H_R2(lh) H_ALL(ntt_phase_radix2<F>(p, smem.data(), lh, tid, nt))
 #define H_R4(lh) H_ALL(ntt_phase_radix4<F>(p, smem.data(), lh, tid, nt))
 #define H_S H_ALL(ntt_phase_store<F>(p, t, smem.data(), tid, nt))
-        ZKB_NTT_FOR_EACH_PHASE(H_L, H_PM, H_R2, H_R4, H_S, p.log_r, p.load_tab != nullptr)
+        ZKB_NTT_FOR_EACH_PHASE(H_L, H_PM, H_R2, H_R4, H_S, p.log_r, p.zero_levels, p.load_tab != nullptr)
     }
 }
 

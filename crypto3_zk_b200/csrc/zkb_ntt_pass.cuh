@@ -46,6 +46,10 @@ struct NttPassParams {
     int n_passes;
     int lr[ZKB_NTT_MAX_PASSES];   // log radix of every pass (for the FINAL digit reversal)
     uint64_t in_valid_elems;      // input indices (within the polynomial) >= this read as zero (zero-padded LDE)
+    int zero_levels;              // z: only the first R >> z rows of every tile are non-zero (in_valid_elems is that
+                                  // many whole rows).  A butterfly (a, b) -> (a + c b, a - c b) with b = 0 copies a, so
+                                  // the first z levels only replicate the live rows: the load/premul phase writes the
+                                  // replicas and the level loop starts z levels further down (no products for them).
     const void *load_tab;         // optional: in[i] *= load_tab[i & load_mask]   (Montgomery form)
     uint64_t load_mask;
     const void *store_tab;        // optional: out[o] *= store_tab[o & store_mask]
@@ -155,20 +159,23 @@ template <class F>
 ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem, uint32_t tid,
                                   uint32_t nthreads) {
     const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r;
-    const uint32_t total = R * C * 2;  // 16-byte units
+    const uint32_t L = R >> p.zero_levels;               // live rows (all of them unless zero_levels > 0)
+    const uint32_t total = L * C * 2;  // 16-byte units
     const u128 zero = {0, 0, 0, 0};
+    // with a coset pre-scale the premul phase writes the replicas (after scaling), otherwise the load does
+    const uint32_t copies = p.load_tab != nullptr ? 1u : (1u << p.zero_levels);
     for (uint32_t u = tid; u < total; u += nthreads) {
         uint32_t half, r, c;
         if (t.in_col_stride == 1) {      // runs of C elements along the column axis
             half = u & 1; c = (u >> 1) % C; r = u / (2 * C);
-        } else {                         // runs of R elements along the row axis
-            half = u & 1; r = (u >> 1) % R; c = u / (2 * R);
+        } else {                         // runs of L elements along the row axis
+            half = u & 1; r = (u >> 1) % L; c = u / (2 * L);
         }
         u128 v = zero;
         uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
         if (c < t.ncols && widx < p.in_valid_elems)
             v = p.in[2 * (t.in_base + r * t.in_row_stride + c * t.in_col_stride) + half];
-        smem[ntt_slot(p.log_r, half, r, c)] = v;
+        for (uint32_t k = 0; k < copies; k++) smem[ntt_slot(p.log_r, half, r + k * L, c)] = v;
     }
 }
 
@@ -177,14 +184,18 @@ template <class F>
 ZKB_HD void ntt_phase_premul(const NttPassParams &p, const NttTile &t, u128 *smem, uint32_t tid,
                                     uint32_t nthreads) {
     const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r;
-    for (uint32_t e = tid; e < R * C; e += nthreads) {
+    const uint32_t L = R >> p.zero_levels, copies = 1u << p.zero_levels;
+    for (uint32_t e = tid; e < L * C; e += nthreads) {
         uint32_t c = e % C, r = e / C;
         uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
-        if (c >= t.ncols || widx >= p.in_valid_elems) continue;
-        uint64_t idx = widx & p.load_mask;
         F v = ntt_ld_elem<F>(smem, p.log_r, r, c);
-        v = v * ntt_ld_tab<F>(p.load_tab, idx);
-        ntt_st_elem<F>(smem, p.log_r, r, c, v);
+        if (c < t.ncols && widx < p.in_valid_elems) {
+            uint64_t idx = widx & p.load_mask;
+            v = v * ntt_ld_tab<F>(p.load_tab, idx);
+        } else if (copies == 1) {
+            continue;
+        }
+        for (uint32_t k = 0; k < copies; k++) ntt_st_elem<F>(smem, p.log_r, r + k * L, c, v);
     }
 }
 
@@ -286,12 +297,12 @@ ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128
 
 // Sequence of phases shared by the kernel and the host replay.  `sync` is __syncthreads() on the
 // device and a no-op marker on the host (the host replays a phase for all threads before moving on).
-#define ZKB_NTT_FOR_EACH_PHASE(PHASE_LOAD, PHASE_PREMUL, PHASE_R2, PHASE_R4, PHASE_STORE, log_r, has_load_tab) \
+#define ZKB_NTT_FOR_EACH_PHASE(PHASE_LOAD, PHASE_PREMUL, PHASE_R2, PHASE_R4, PHASE_STORE, log_r, zero_levels, has_load_tab) \
     {                                                                                                   \
         PHASE_LOAD;                                                                                     \
         if (has_load_tab) { PHASE_PREMUL; }                                                             \
-        int _lh = (log_r)-1;                                                                            \
-        if ((log_r)&1) { PHASE_R2(_lh); _lh -= 1; }                                                     \
+        int _lh = (log_r)-1-(zero_levels);                                                              \
+        if ((_lh + 1)&1) { PHASE_R2(_lh); _lh -= 1; }                                                   \
         for (; _lh >= 1; _lh -= 2) { PHASE_R4(_lh); }                                                   \
         PHASE_STORE;                                                                                    \
     }
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 3) ntt_pass_kernel(const NttP
 #define ZKB_R2(lh) ntt_phase_radix2<F>(p, smem, lh, tid, nt); __syncthreads()
 #define ZKB_R4(lh) ntt_phase_radix4<F>(p, smem, lh, tid, nt); __syncthreads()
 #define ZKB_S ntt_phase_store<F>(p, t, smem, tid, nt)
-    ZKB_NTT_FOR_EACH_PHASE(ZKB_L, ZKB_PM, ZKB_R2, ZKB_R4, ZKB_S, p.log_r, p.load_tab != nullptr)
+    ZKB_NTT_FOR_EACH_PHASE(ZKB_L, ZKB_PM, ZKB_R2, ZKB_R4, ZKB_S, p.log_r, p.zero_levels, p.load_tab != nullptr)
 #undef ZKB_L
 #undef ZKB_PM
 #undef ZKB_R2

@@ -42,6 +42,17 @@ inline NttPlan ntt_make_plan(int log_n) {
     return pl;
 }
 
+// Zero-padded input (LDE): when the valid prefix is 2^v elements = 2^(v - log_row_stride) whole tile rows of the first
+// pass, the first z = log_r - (v - log_row_stride) butterfly levels of that pass only replicate the live rows.
+inline int ntt_zero_levels(uint64_t in_valid_elems, int log_row_stride, int log_r) {
+    if (in_valid_elems == 0 || (in_valid_elems & (in_valid_elems - 1))) return 0;
+    int v = 0;
+    while ((1ull << v) < in_valid_elems) v++;
+    int log_live = v - log_row_stride;
+    if (log_live < 0 || log_live >= log_r) return 0;
+    return log_r - log_live;
+}
+
 // Pointers to the tables one transform needs (device pointers in the runtime, host in the replay).
 struct NttTables {
     const void *tw;                              // master in-tile twiddles for this direction
@@ -70,6 +81,7 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
         q.load_tab = nullptr; q.load_mask = 0;
         q.store_tab = nullptr; q.store_mask = 0;
         q.in_valid_elems = N;
+        q.zero_levels = 0;
         q.log_m = 0; q.log_mprev = 0;
         if (p == 1) {
             q.mode = NTT_MODE_SINGLE;
@@ -77,6 +89,7 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
             q.in_poly_stride = in_poly_stride; q.out_poly_stride = out_poly_stride;
             q.tiles_per_poly = 0;
             q.in_valid_elems = in_valid_elems;
+            q.zero_levels = ntt_zero_levels(in_valid_elems, 0, q.log_r);
             q.load_tab = tb.load_tab; q.load_mask = tb.load_mask;
             q.store_tab = tb.store_tab; q.store_mask = tb.store_mask;
         } else if (i < p - 1) {
@@ -87,6 +100,7 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
             if (i == 0) {
                 q.in = (const u128 *)in; q.in_poly_stride = in_poly_stride;
                 q.in_valid_elems = in_valid_elems;
+                q.zero_levels = ntt_zero_levels(in_valid_elems, q.log_m, q.log_r);
                 q.load_tab = tb.load_tab; q.load_mask = tb.load_mask;
             } else {
                 q.in = (const u128 *)work; q.in_poly_stride = N;

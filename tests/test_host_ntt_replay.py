@@ -99,6 +99,17 @@ def test_zero_padded_input(libs, maxlogr, log_in, log_out):
         assert got[b] == a
 
 
+@pytest.mark.parametrize("maxlogr,log_in,log_out", [(8, 3, 6), (8, 7, 10), (3, 6, 9), (4, 9, 12), (8, 0, 5), (8, 8, 11)])
+def test_zero_padded_coset_input(libs, maxlogr, log_in, log_out):
+    """Zero-padded input with a coset pre-scale: the replicas of the live rows are written after the scaling."""
+    F = fields.BLS12_381_FR
+    polys = [fields.random_elements(F, 1 << log_in, 11 + b) for b in range(3)]
+    got = run(libs[maxlogr], F, log_out, polys, log_n_in=log_in, shift=F.g)
+    for b in range(3):
+        a = list(polys[b]) + [0] * ((1 << log_out) - (1 << log_in))
+        assert got[b] == oracle(F, log_out, a, shift=F.g)
+
+
 def test_ragged_batch(libs):
     F = fields.BN254_FR
     polys = [fields.random_elements(F, 16, b) for b in range(11)]   # 11 = 8 + 3 columns
