@@ -101,6 +101,18 @@ class MerkleTree:
         raw = bytes(buf)
         return [raw[i * self.digest_bytes:(i + 1) * self.digest_bytes] for i in range(depth)]
 
+    def paths(self, indices):
+        """Authentication paths of several leaves with one device gather (FRI query phase)."""
+        depth = self.leaves.bit_length() - 1
+        count = len(indices)
+        if count == 0 or depth == 0:
+            return [[] for _ in range(count)]
+        idx = (ctypes.c_uint64 * count)(*[int(i) for i in indices])
+        buf = (ctypes.c_uint8 * (count * depth * self.digest_bytes))()
+        capi.check(capi.lib().zkb_merkle_paths(self._ctx._h, self._h, count, idx, buf, None), self._ctx._h)
+        raw, db = bytes(buf), self.digest_bytes
+        return [[raw[(q * depth + d) * db:(q * depth + d + 1) * db] for d in range(depth)] for q in range(count)]
+
     def free(self):
         if self._h:
             capi.lib().zkb_merkle_free(self._h)
@@ -369,6 +381,20 @@ class Context:
         if keep_trees:
             tree_list = [MerkleTree(self, ctypes.c_void_p(trees[i]), root_list[i], db) for i in range(rounds)]
         return {"roots": root_list, "alphas": _ints(alphas), "final_polynomial": _ints(final), "trees": tree_list, "fs": fs}
+
+    # ------------------------------------------------------------------ grinding (proof_of_work.hpp:47-68)
+    def pow_grind(self, hash_id, state, mask=0xFFFF, start=0, stream=None):
+        """proof_of_work<TranscriptHash, uint32>::generate over a sequential Fiat-Shamir transcript whose current
+        digest is `state`: the smallest nonce >= start with (low32(H(H(state || be32(nonce)))) & mask) == 0."""
+        db = capi.lib().zkb_merkle_digest_bytes(hash_id)
+        state = bytes(state)
+        if len(state) != db:
+            raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "transcript state must be %d bytes" % db)
+        buf = (ctypes.c_uint8 * db).from_buffer_copy(state)
+        nonce = ctypes.c_uint32(0)
+        capi.check(capi.lib().zkb_pow_grind(self._h, hash_id, buf, int(start) & 0xFFFFFFFF, int(mask) & 0xFFFFFFFF,
+                                            ctypes.byref(nonce), stream), self._h)
+        return int(nonce.value)
 
     # ------------------------------------------------------------------ LPC opening side (eval_polys, combined Q)
     def poly_evaluate(self, field, polys, n, points, dfs=False, stream=None):

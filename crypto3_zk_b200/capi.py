@@ -22,7 +22,7 @@ SYMBOLS = [
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
     "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul",
     "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
-    "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec",
+    "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec", "zkb_pow_grind", "zkb_merkle_paths",
 ]
 POLY_COEFFICIENTS, POLY_DFS = 0, 1
 # int (*zkb_fri_challenge_fn)(void *user, uint32_t round, const uint8_t *root, uint32_t root_bytes, uint32_t count, uint32_t *alphas_out)
@@ -106,6 +106,8 @@ def lib():
     L.zkb_sparse_matrix_free.argtypes = [vp]
     L.zkb_sparse_matrix_free.restype = None
     L.zkb_sparse_matvec.argtypes = [vp, vp, vp, i, vp, vp]
+    L.zkb_merkle_paths.argtypes = [vp, vp, u32, ctypes.POINTER(u64), u8p, vp]
+    L.zkb_pow_grind.argtypes = [vp, i, u8p, u32, u32, u32p, vp]
     _lib = L
     return L
 

@@ -30,6 +30,51 @@ int ctx_scratch(zkb_ctx *ctx, const char *role, size_t bytes, void **out) {
     return ZKB_OK;
 }
 
+int ctx_tree_alloc(zkb_ctx *ctx, size_t bytes, void **out, size_t *cap) {
+    // best fit among the pooled buffers that are not more than twice the request
+    int best = -1;
+    for (size_t i = 0; i < ctx->tree_pool.size(); i++) {
+        size_t c = ctx->tree_pool[i].cap;
+        if (c >= bytes && c <= 2 * bytes + 4096 && (best < 0 || c < ctx->tree_pool[best].cap)) best = (int)i;
+    }
+    if (best >= 0) {
+        *out = ctx->tree_pool[best].p;
+        *cap = ctx->tree_pool[best].cap;
+        ctx->tree_pool_bytes -= *cap;
+        ctx->tree_pool.erase(ctx->tree_pool.begin() + best);
+        return ZKB_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {   // give the pooled buffers back to the driver and retry once
+        cudaGetLastError();
+        for (auto &b : ctx->tree_pool) cudaFree(b.p);
+        ctx->tree_pool.clear();
+        ctx->tree_pool_bytes = 0;
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, std::string("cudaMalloc merkle tree: ") + cudaGetErrorString(e));
+    }
+    *out = p;
+    *cap = bytes;
+    return ZKB_OK;
+}
+
+void ctx_tree_release(zkb_ctx *ctx, void *p, size_t cap) {
+    if (!p) return;
+    if (ctx->tree_pool_bytes + cap > ctx->scratch_limit || ctx->tree_pool.size() >= 64) {
+        cudaFree(p);
+        return;
+    }
+    zkb_ctx::Buf b;
+    b.p = p;
+    b.cap = cap;
+    ctx->tree_pool.push_back(b);
+    ctx->tree_pool_bytes += cap;
+}
+
 int ctx_table(zkb_ctx *ctx, const std::string &key, size_t bytes, void **out, bool *created) {
     auto it = ctx->tables.find(key);
     if (it != ctx->tables.end()) {
@@ -128,8 +173,12 @@ int zkb_ctx_release_caches(zkb_ctx *ctx) {
         if (kv.second.p) cudaFree(kv.second.p);
     for (auto &kv : ctx->tables)
         if (kv.second.p) cudaFree(kv.second.p);
+    for (auto &b : ctx->tree_pool)
+        if (b.p) cudaFree(b.p);
     ctx->scratch.clear();
     ctx->tables.clear();
+    ctx->tree_pool.clear();
+    ctx->tree_pool_bytes = 0;
     return ZKB_OK;
 }
 

@@ -23,6 +23,7 @@ struct zkb_merkle_tree {
     int digest_bytes;
     uint64_t leaves;
     uint8_t *d_nodes;  // level 0 (leaf digests) first, then each parent level; 2*leaves-1 digests
+    size_t nodes_cap;  // capacity of d_nodes (it goes back to the context's tree pool)
 };
 
 // ------------------------------------------------------------------------------------ Keccak-f[1600]
@@ -252,6 +253,88 @@ __global__ void __launch_bounds__(128) node_hash_sha256_kernel(uint64_t parents,
     for (int k = 0; k < 8; k++) parent[i * 8 + k] = __byte_perm(h[k], 0, 0x0123);
 }
 
+// ------------------------------------------------------------------------------------ grinding
+// proof_of_work<TranscriptHash, uint32>::generate (zk/commitments/detail/polynomial/proof_of_work.hpp:47-68):
+// find a nonce with (int_challenge(transcript + be32(nonce)) & mask) == 0, where for the sequential Fiat-Shamir
+// transcript (zk/transcript/fiat_shamir.hpp:152-164,190-199) absorbing is state' = H(state || bytes) and
+// int_challenge<uint32> is the low 32 bits of the big-endian integer H(state').  The reference walks the nonces
+// one by one from a random start; here every thread tries one nonce and the smallest hit of the launch wins.
+struct PowState {
+    uint64_t lanes[8];   // transcript state: digest bytes as little-endian 64-bit lanes (keccak) / big-endian words packed (sha)
+};
+
+template <int RATE_LANES, int DIGEST_LANES>
+__device__ __forceinline__ uint32_t pow_try_keccak(const PowState &st, uint32_t nonce) {
+    uint64_t a[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = 0;
+#pragma unroll
+    for (int i = 0; i < DIGEST_LANES; i++) a[i] = st.lanes[i];
+    // the four nonce bytes (most significant first) follow the state; then the 0x01 pad byte
+    a[DIGEST_LANES] = (uint64_t)__byte_perm(nonce, 0, 0x0123) | (0x01ull << 32);
+    a[RATE_LANES - 1] ^= 0x8000000000000000ull;
+    keccak_f1600(a);
+#pragma unroll
+    for (int i = DIGEST_LANES; i < 25; i++) a[i] = 0;
+    a[DIGEST_LANES] = 0x01ull;
+    a[RATE_LANES - 1] ^= 0x8000000000000000ull;
+    keccak_f1600(a);
+    // last four digest bytes, read as a big-endian integer
+    return __byte_perm((uint32_t)(a[DIGEST_LANES - 1] >> 32), 0, 0x0123);
+}
+
+__device__ __forceinline__ uint32_t pow_try_sha256(const PowState &st, uint32_t nonce) {
+    uint32_t h[8], w[16];
+    sha256_init(h);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { w[2 * i] = (uint32_t)(st.lanes[i] >> 32); w[2 * i + 1] = (uint32_t)st.lanes[i]; }
+    w[8] = nonce;
+    w[9] = 0x80000000u;
+#pragma unroll
+    for (int i = 10; i < 15; i++) w[i] = 0;
+    w[15] = 36 * 8;
+    sha256_compress(h, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = h[i];
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = 256;
+    sha256_init(h);
+    sha256_compress(h, w);
+    return h[7];
+}
+
+template <int HASH>
+__global__ void __launch_bounds__(256) pow_grind_kernel(PowState st, uint64_t base, uint64_t count, uint32_t mask,
+                                                        unsigned long long *__restrict__ found) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t nonce = (uint32_t)(base + i);
+    uint32_t r;
+    if (HASH == ZKB_HASH_KECCAK_256) r = pow_try_keccak<17, 4>(st, nonce);
+    else if (HASH == ZKB_HASH_KECCAK_512) r = pow_try_keccak<9, 8>(st, nonce);
+    else r = pow_try_sha256(st, nonce);
+    if ((r & mask) == 0) atomicMin(found, (unsigned long long)(base + i));
+}
+
+// ------------------------------------------------------------------------------------ query phase: path gather
+// out[q][d] = sibling digest of leaf indices[q] at tree level d (16-byte units; digests are 32 or 64 bytes)
+__global__ void __launch_bounds__(256) merkle_paths_kernel(const uint4 *__restrict__ nodes, uint64_t leaves, int depth, int units,
+                                                           uint32_t count, const uint64_t *__restrict__ indices,
+                                                           uint4 *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = (uint64_t)count * depth * units;
+    if (i >= total) return;
+    uint32_t u = (uint32_t)(i % units);
+    uint32_t d = (uint32_t)((i / units) % depth);
+    uint32_t q = (uint32_t)(i / ((uint64_t)units * depth));
+    // level d starts after leaves + leaves/2 + .. + leaves/2^(d-1) = 2 leaves (1 - 2^-d) digests
+    uint64_t level_start = 2 * leaves - (2 * leaves >> d);
+    uint64_t idx = (indices[q] >> d) ^ 1;
+    out[i] = nodes[(level_start + idx) * units + u];
+}
+
 // ------------------------------------------------------------------------------------ host driver
 static int digest_bytes_of(int hash) {
     switch (hash) {
@@ -272,12 +355,11 @@ int zkb::merkle_build_device(zkb_ctx *ctx, int hash, int log_d, int fri_step, ui
     uint8_t *nodes = nullptr;
     size_t bytes = (size_t)(2 * leaves - 1) * db;
     bool keep = tree_out != nullptr;
+    size_t nodes_cap = 0;
     if (keep) {
-        cudaError_t e = cudaMalloc((void **)&nodes, bytes);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, "cudaMalloc merkle tree");
-        }
+        void *p;
+        ZKB_TRY(ctx_tree_alloc(ctx, bytes, &p, &nodes_cap));
+        nodes = (uint8_t *)p;
     } else {
         void *p;
         ZKB_TRY(ctx_scratch(ctx, "merkle_nodes", bytes, &p));
@@ -316,7 +398,7 @@ int zkb::merkle_build_device(zkb_ctx *ctx, int hash, int log_d, int fri_step, ui
         if (ke == cudaSuccess) ke = cudaStreamSynchronize(st);
     }
     if (ke != cudaSuccess) {
-        if (keep) cudaFree(nodes);
+        if (keep) ctx_tree_release(ctx, nodes, nodes_cap);
         return ctx_fail(ctx, ZKB_ERR_CUDA, std::string("merkle build: ") + cudaGetErrorString(ke));
     }
     if (keep) {
@@ -326,6 +408,7 @@ int zkb::merkle_build_device(zkb_ctx *ctx, int hash, int log_d, int fri_step, ui
         t->digest_bytes = db;
         t->leaves = leaves;
         t->d_nodes = nodes;
+        t->nodes_cap = nodes_cap;
         *tree_out = t;
     }
     return ZKB_OK;
@@ -340,7 +423,7 @@ void zkb_merkle_free(zkb_merkle_tree *t) {
     if (!t) return;
     if (t->d_nodes) {
         cudaSetDevice(t->ctx->device);
-        cudaFree(t->d_nodes);
+        zkb::ctx_tree_release(t->ctx, t->d_nodes, t->nodes_cap);
     }
     delete t;
 }
@@ -356,6 +439,34 @@ int zkb_merkle_path(zkb_ctx *ctx, const zkb_merkle_tree *t, uint64_t index, uint
         level += n * t->digest_bytes;
         index >>= 1;
     }
+    return ZKB_OK;
+}
+
+int zkb_merkle_paths(zkb_ctx *ctx, const zkb_merkle_tree *t, uint32_t count, const uint64_t *indices, uint8_t *paths_out,
+                     void *stream) {
+    if (!ctx || !t || (count && (!indices || !paths_out))) return ZKB_ERR_INVALID_ARGUMENT;
+    for (uint32_t q = 0; q < count; q++)
+        if (indices[q] >= t->leaves) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_merkle_paths: leaf index out of range");
+    int depth = 0;
+    for (uint64_t n = t->leaves; n > 1; n >>= 1) depth++;
+    if (count == 0 || depth == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int units = t->digest_bytes / 16;
+    size_t out_bytes = (size_t)count * depth * t->digest_bytes, idx_bytes = (size_t)count * 8;
+    void *p;
+    const size_t idx_pad = (idx_bytes + 15) & ~(size_t)15;
+    ZKB_TRY(ctx_scratch(ctx, "merkle_paths", idx_pad + out_bytes, &p));
+    uint64_t *d_idx = (uint64_t *)p;
+    uint4 *d_out = (uint4 *)((char *)p + idx_pad);
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d_idx, indices, idx_bytes, cudaMemcpyHostToDevice, st));
+    uint64_t total = (uint64_t)count * depth * units;
+    merkle_paths_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4 *)t->d_nodes, t->leaves, depth, units, count,
+                                                                       d_idx, d_out);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(paths_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
     return ZKB_OK;
 }
 
@@ -436,6 +547,49 @@ int zkb_lpc_commit(zkb_ctx *ctx, int field, int hash, int log_n_in, int log_n_ou
     ZKB_TRY(ctx_scratch(ctx, "lpc_ext", ob, &ext));
     ZKB_TRY(lde_device(ctx, field, log_n_in, log_n_out, batch, din, ext, st));
     return merkle_build(ctx, hash, log_n_out, fri_step, batch, ext, root_out, tree_out, st);
+}
+
+int zkb_pow_grind(zkb_ctx *ctx, int hash, const uint8_t *state, uint32_t start, uint32_t mask, uint32_t *nonce_out,
+                  void *stream) {
+    if (!ctx || !state || !nonce_out || !digest_bytes_of(hash)) return ZKB_ERR_INVALID_ARGUMENT;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int db = digest_bytes_of(hash);
+    PowState ps;
+    for (int i = 0; i < 8; i++) ps.lanes[i] = 0;
+    for (int i = 0; i < db / 8; i++) {
+        uint64_t v = 0;
+        if (hash == ZKB_HASH_SHA2_256) for (int b = 0; b < 8; b++) v = (v << 8) | state[8 * i + b];           // two big-endian words
+        else for (int b = 7; b >= 0; b--) v = (v << 8) | state[8 * i + b];                                      // little-endian lane
+        ps.lanes[i] = v;
+    }
+    void *p;
+    ZKB_TRY(ctx_scratch(ctx, "pow_found", 8, &p));
+    unsigned long long *d_found = (unsigned long long *)p, h_found = ~0ull;
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d_found, &h_found, 8, cudaMemcpyHostToDevice, st));
+    // ascending chunks, so the first chunk with a hit holds the smallest nonce >= start
+    uint64_t base = start, chunk = 1ull << 20;
+    while (base <= 0xffffffffull) {
+        uint64_t count = chunk;
+        if (base + count > 0x100000000ull) count = 0x100000000ull - base;
+        unsigned blocks = (unsigned)((count + 255) / 256);
+        switch (hash) {
+            case ZKB_HASH_KECCAK_256: pow_grind_kernel<ZKB_HASH_KECCAK_256><<<blocks, 256, 0, st>>>(ps, base, count, mask, d_found); break;
+            case ZKB_HASH_KECCAK_512: pow_grind_kernel<ZKB_HASH_KECCAK_512><<<blocks, 256, 0, st>>>(ps, base, count, mask, d_found); break;
+            default: pow_grind_kernel<ZKB_HASH_SHA2_256><<<blocks, 256, 0, st>>>(ps, base, count, mask, d_found); break;
+        }
+        ctx->launches++;
+        ZKB_CUDA_OK(ctx, cudaGetLastError());
+        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(&h_found, d_found, 8, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if (h_found != ~0ull) {
+            *nonce_out = (uint32_t)h_found;
+            return ZKB_OK;
+        }
+        base += count;
+        if (chunk < (1ull << 26)) chunk <<= 2;
+    }
+    return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "zkb_pow_grind: no 32-bit nonce at or above `start` satisfies the mask");
 }
 
 }  // extern "C"

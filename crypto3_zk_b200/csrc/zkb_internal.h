@@ -21,6 +21,10 @@ struct zkb_ctx {
     std::map<std::string, Buf> scratch;
     // cached device tables (twiddles, coset powers), keyed by a descriptive string
     std::map<std::string, Buf> tables;
+    // buffers of freed Merkle trees, reused by the next kept tree: a prover builds and drops trees of the same few
+    // sizes for every proof, and cudaMalloc / cudaFree cost milliseconds and synchronise the device
+    std::vector<Buf> tree_pool;
+    size_t tree_pool_bytes = 0;
     // copy streams + events of the host-buffer pipeline (created on first use, see host_pipeline())
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -31,6 +35,9 @@ namespace zkb {
 int ctx_fail(zkb_ctx *ctx, int status, const std::string &msg);
 // returns a device buffer of at least `bytes` (reallocates when too small)
 int ctx_scratch(zkb_ctx *ctx, const char *role, size_t bytes, void **out);
+// device memory of a kept Merkle tree: taken from / returned to ctx->tree_pool (bounded by the scratch limit)
+int ctx_tree_alloc(zkb_ctx *ctx, size_t bytes, void **out, size_t *cap);
+void ctx_tree_release(zkb_ctx *ctx, void *p, size_t cap);
 // looks a table up; *created is set when the caller has to fill it
 int ctx_table(zkb_ctx *ctx, const std::string &key, size_t bytes, void **out, bool *created);
 

@@ -7,23 +7,28 @@ What runs where:
   proof_eval()         theta powers on the host; per unique point zkb_poly_lincomb + zkb_poly_div_linear;
                        from_coefficients + resize to D[0] = one zero-padded NTT; then zkb_fri_commit_phase
                        (lpc.hpp:113-200, basic_fri.hpp:706-737)
-The query phase, grinding and proof marshalling are not part of the hot path and are not built:
-proof_eval returns the evaluation table z, the combined Q on D[0] and the commit-phase outputs
-(fri_roots, alphas, fs, fri_trees, final_polynomial) that the reference's query phase starts from.
+  grinding             zkb_pow_grind: every thread tries one nonce                                   (proof_of_work.hpp:47-68)
+  query phase          challenges and index recurrences on the host; the opened values by one zkb_poly_evaluate
+                       per batch over all query points, the round values by one gather from the retained fs,
+                       every tree's lambda paths by one zkb_merkle_paths                            (basic_fri.hpp:749-915)
+proof_eval returns the evaluation table z, the combined Q on D[0], the commit-phase outputs and - with query=True -
+the complete lpc proof {z, fri_proof} in the data model of oracle/fri_query.py.  Proof marshalling is not built.
 Polynomials are polynomial_dfs values: evaluations on the 2^k subgroup, canonical uint32 limbs, torch CUDA tensors.
 """
 import numpy as np
 
 from . import capi
 from .api import _int_rows
-from .fields import FIELD_BY_NAME
+from .fields import FIELD_BY_NAME, omega
 
 
 class FriParams:
     """commitments::detail::basic_batched_fri::params_type (basic_fri.hpp:151-183): r = max degree log,
     D[i] of size 2^(r + expand_factor - i) (calculate_domain_set), step_list summing to r."""
 
-    def __init__(self, step_list, degree_log, lambda_=40, expand_factor=2):
+    def __init__(self, step_list, degree_log, lambda_=40, expand_factor=2, use_grinding=False, grinding_parameter=0xFFFF):
+        self.use_grinding = bool(use_grinding)
+        self.grinding_parameter = int(grinding_parameter)
         self.step_list = [int(s) for s in step_list]
         self.r = sum(self.step_list)
         self.degree_log = int(degree_log)
@@ -34,11 +39,11 @@ class FriParams:
             raise ValueError("sum(step_list) exceeds log2 |D[0]|")
 
     @staticmethod
-    def with_max_step_one(degree_log, lambda_=40, expand_factor=2):
+    def with_max_step_one(degree_log, lambda_=40, expand_factor=2, use_grinding=False, grinding_parameter=0xFFFF):
         """params_type(max_step = 1, degree_log, lambda, expand_factor) (basic_fri.hpp:150-166), the constructor the
         reference's Placeholder tests use (test/systems/plonk/placeholder/placeholder.cpp:231): r = degree_log - 1
         rounds of step 1 (generate_random_step_list is deterministic for max_step = 1)."""
-        return FriParams([1] * (degree_log - 1), degree_log, lambda_, expand_factor)
+        return FriParams([1] * (degree_log - 1), degree_log, lambda_, expand_factor, use_grinding, grinding_parameter)
 
 
 class LpcCommitmentScheme:
@@ -130,8 +135,10 @@ class LpcCommitmentScheme:
         return out
 
     # ---- proof_eval up to the end of the FRI commit phase (lpc.hpp:113-200)
-    def proof_eval(self, transcript, keep_trees=False, keep_fs=False):
+    def proof_eval(self, transcript, keep_trees=False, keep_fs=False, query=False):
         import torch
+        if query:
+            keep_trees = keep_fs = True
         p = self.F.p
         self.eval_polys()
         for k in sorted(self._trees):
@@ -190,8 +197,132 @@ class LpcCommitmentScheme:
             self.F.name, self.hash_id, q_d0[0], self.fri.log_d0, self.fri.step_list,
             lambda rnd, root, count: (transcript(root), [transcript.challenge(p) for _ in range(count)])[1],
             keep_trees=keep_trees, keep_fs=keep_fs)
-        return {"z": self.z, "theta": theta, "combined_Q_normal": combined, "combined_Q": q_d0[0],
-                "remainders": remainders, "fri": fri}
+        out = {"z": self.z, "theta": theta, "combined_Q_normal": combined, "combined_Q": q_d0[0],
+               "remainders": remainders, "fri": fri}
+        if query:
+            out["proof"] = {"z": self.z, "fri_proof": self._query_phase(transcript, fri)}
+        return out
+
+    # ---- grinding + query phase of zk::algorithms::proof_eval<FRI> (basic_fri.hpp:743-915)
+    def _domain_index(self, x, log_n):
+        """index of x in the 2^log_n subgroup (the reference searches linearly, basic_fri.hpp:780-786): bit by bit,
+        bit i of the exponent is set iff (x w^-e)^(2^(log_n-1-i)) != 1"""
+        p = self.F.p
+        w_inv = pow(omega(self.F, log_n), p - 2, p)
+        e = 0
+        for i in range(log_n):
+            if pow(x * pow(w_inv, e, p) % p, 1 << (log_n - 1 - i), p) != 1:
+                e |= 1 << i
+        return e
+
+    @staticmethod
+    def _s_indices(x_index, domain_size, fri_step):
+        """index pairs of calculate_s (basic_fri.hpp:583-617)"""
+        half = domain_size // 2
+        idx = [x_index]
+        base, prev = domain_size // 4, 1
+        while len(idx) < (1 << fri_step) // 2:
+            idx += [(base + idx[j]) % domain_size for j in range(prev)]
+            base //= 2
+            prev <<= 1
+        return [(a, (a + half) % domain_size) for a in idx]
+
+    @staticmethod
+    def _folded_index(x_index, domain_size, fri_step):
+        for _ in range(fri_step):
+            domain_size //= 2
+            x_index %= domain_size
+        return x_index
+
+    def _query_phase(self, transcript, fri):
+        import torch
+        F, p, steps, log_d0 = self.F, self.F.p, self.fri.step_list, self.fri.log_d0
+        if steps[-1] != 1:
+            raise ValueError("step_list must end with 1 (check_step_list, basic_fri.hpp:544-571)")
+        proof = {"fri_roots": fri["roots"], "final_polynomial": fri["final_polynomial"], "proof_of_work": None}
+        if self.fri.use_grinding:
+            nonce = self.ctx.pow_grind(transcript.hash_id, transcript.state, self.fri.grinding_parameter)
+            transcript(nonce.to_bytes(4, "big"))
+            transcript.int_challenge(32)
+            proof["proof_of_work"] = nonce
+        lam, d0 = self.fri.lambda_, 1 << log_d0
+        # the challenges do not depend on anything opened, so draw them all and batch the device work
+        x_idx0 = []
+        for _ in range(lam):
+            x = pow(transcript.challenge(p), (p - 1) // d0, p)
+            x_idx0.append(self._domain_index(x, log_d0))
+        w0 = omega(F, log_d0)
+        init_pairs = [[(min(a, b), max(a, b)) for a, b in self._s_indices(xi, d0, steps[0])] for xi in x_idx0]
+        flat = sorted({i for pairs in init_pairs for pr in pairs for i in pr})
+        pos = {i: n for n, i in enumerate(flat)}
+        pts = [pow(w0, i, p) for i in flat]
+        initial = [dict() for _ in range(lam)]
+        leaf0 = [self._folded_index(xi, d0, steps[0]) for xi in x_idx0]
+        for k in sorted(self._polys):
+            co, n = self._coeffs[k]
+            if n == d0:    # already on D[0]: the values themselves (basic_fri.hpp:812-818)
+                batch, _ = self._batch_tensor(k)
+                sel = batch[:, torch.tensor(flat, device=batch.device)].cpu().numpy().view(np.uint32)
+                vals = [[int.from_bytes(sel[i, j].tobytes(), "little") for j in range(len(flat))] for i in range(sel.shape[0])]
+            else:          # evaluate the coefficient form at the 2 lambda points (:819-834)
+                vals = self.ctx.poly_evaluate(F.name, co, n, pts)
+            paths = self._trees[k].paths(leaf0)
+            root = self._trees[k].root()
+            for q in range(lam):
+                initial[q][k] = {"values": [[[v[pos[a]], v[pos[b]]] for a, b in init_pairs[q]] for v in vals],
+                                 "p": {"index": leaf0[q], "path": paths[q], "root": root}}
+        # round proofs: paths from every fri tree, y from the retained fs (one gather), final round from final_polynomial
+        fs, fs_off, acc, off = fri["fs"], [], log_d0, 0
+        for s_ in steps:
+            acc -= s_
+            fs_off.append((off, acc))
+            off += 1 << acc
+        rounds = [[None] * len(steps) for _ in range(lam)]
+        gather = []
+        t = 0
+        xs = list(x_idx0)
+        for i, s_ in enumerate(steps):
+            size_t = 1 << (log_d0 - t)
+            xs = [xi % size_t for xi in xs]
+            leaves = [self._folded_index(xi, size_t, s_) for xi in xs]
+            paths = fri["trees"][i].paths(leaves)
+            t += s_
+            size_n = 1 << (log_d0 - t)
+            for q in range(lam):
+                rp = {"p": {"index": leaves[q], "path": paths[q], "root": fri["roots"][i]}}
+                if i < len(steps) - 1:
+                    xq = xs[q] % size_n
+                    pairs = [(min(a, b), max(a, b)) for a, b in self._s_indices(xq, size_n, steps[i + 1])]
+                    rp["y"] = [[None, None] for _ in pairs]
+                    for j, (a, b) in enumerate(pairs):
+                        gather.append((fs_off[i][0] + a, rp["y"][j], 0))
+                        gather.append((fs_off[i][0] + b, rp["y"][j], 1))
+                else:
+                    size_p = 1 << (log_d0 - t + 1)               # D[t-1]
+                    xq = xs[q] % size_p
+                    x = pow(omega(F, log_d0 - t + 1), xq, p)
+                    x = x * x % p
+                    ind = 0 if xq % (size_p // 2) < size_p // 4 else 1
+                    y = [[0, 0]]
+                    y[0][ind] = _horner(fri["final_polynomial"], x, p)
+                    y[0][1 - ind] = _horner(fri["final_polynomial"], (p - x) % p, p)
+                    rp["y"] = y
+                rounds[q][i] = rp
+            if i < len(steps) - 1:
+                xs = [xi % size_n for xi in xs]
+        if gather:
+            sel = fs[torch.tensor([g[0] for g in gather], device=fs.device)].cpu().numpy().view(np.uint32)
+            for n_, (_, tgt, slot) in enumerate(gather):
+                tgt[slot] = int.from_bytes(sel[n_].tobytes(), "little")
+        proof["query_proofs"] = [{"initial_proof": initial[q], "round_proofs": rounds[q]} for q in range(lam)]
+        return proof
+
+
+def _horner(coeffs, x, p):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % p
+    return acc
 
 
 def host_poly(vals):

@@ -77,6 +77,7 @@ HASH_BY_ID = {0: keccak256, 1: sha256, 2: keccak512}
 
 class FiatShamirSequential:
     def __init__(self, hash_id=0, init=b"\x00"):
+        self.hash_id = hash_id
         self._h = HASH_BY_ID[hash_id]
         self.state = self._h(bytes(init))
 
@@ -88,6 +89,12 @@ class FiatShamirSequential:
     def challenge(self, modulus):
         self.state = self._h(self.state)
         return int.from_bytes(self.state, "big") % int(modulus)
+
+    def int_challenge(self, bits=32):
+        """int_challenge<Integral> (fiat_shamir.hpp:190-199): state = H(state); the low `bits` bits of the digest
+        read as a big-endian integer."""
+        self.state = self._h(self.state)
+        return int.from_bytes(self.state, "big") & ((1 << bits) - 1)
 
     def challenges(self, modulus, count):
         return [self.challenge(modulus) for _ in range(count)]

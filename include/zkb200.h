@@ -151,6 +151,10 @@ uint64_t zkb_merkle_leaves(const zkb_merkle_tree *tree);
 /* authentication path of leaf `index`: `depth` sibling digests, leaf level first
  * (containers::merkle_proof<Hash,2>(tree, index), basic_fri.hpp:526-531) */
 int zkb_merkle_path(zkb_ctx *ctx, const zkb_merkle_tree *tree, uint64_t index, uint8_t *path_out);
+/* the paths of `count` leaves at once (the FRI query phase opens lambda leaves per tree, basic_fri.hpp:846-862):
+ * one gather kernel and one copy; paths_out: host, count x depth digests */
+int zkb_merkle_paths(zkb_ctx *ctx, const zkb_merkle_tree *tree, uint32_t count, const uint64_t *indices, uint8_t *paths_out,
+                     void *stream);
 void zkb_merkle_free(zkb_merkle_tree *tree);
 
 /* ---- FRI commit phase: zk::algorithms::proof_eval<FRI>, "Commit phase" ---------------------------- */
@@ -173,6 +177,16 @@ int zkb_fri_commit_phase(zkb_ctx *ctx, int field, int hash, int log_n, const voi
                          uint32_t rounds, zkb_fri_challenge_fn challenge, void *user, uint8_t *roots_out,
                          zkb_merkle_tree **trees_out, void *fs_device_out, uint32_t *alphas_out, uint32_t *final_poly_out,
                          void *stream);
+
+/* ---- grinding: proof_of_work<TranscriptHash, std::uint32_t>::generate ------------------------------------- */
+/* zk/commitments/detail/polynomial/proof_of_work.hpp:47-68 over fiat_shamir_heuristic_sequential
+ * (zk/transcript/fiat_shamir.hpp:152-164 absorb, :190-199 int_challenge): the smallest nonce >= start such that
+ * (low32(H(H(state || be32(nonce)))) & mask) == 0.  `state` is the transcript's current digest (host,
+ * zkb_merkle_digest_bytes(hash) bytes).  The reference starts from std::rand() and walks upwards one hash pair at a
+ * time; any nonce that passes verifies (proof_of_work.hpp:70-78), the caller then absorbs be32(nonce) and draws the
+ * int_challenge on its own transcript exactly as :64-66 does.  ZKB_ERR_UNSUPPORTED if no nonce in [start, 2^32) passes. */
+int zkb_pow_grind(zkb_ctx *ctx, int hash, const uint8_t *state, uint32_t start, uint32_t mask, uint32_t *nonce_out,
+                  void *stream);
 
 /* ---- opening side of the LPC scheme: eval_polys and the combined quotient Q ------------------------- */
 typedef enum { ZKB_POLY_COEFFICIENTS = 0, ZKB_POLY_DFS = 1 } zkb_poly_form;

@@ -90,3 +90,13 @@ class FiatShamirSequential:
     def challenge(self, field):
         self.state = self.h(self.state)
         return int.from_bytes(self.state, "big") % field.p
+
+    def int_challenge(self, bits=32):
+        """int_challenge<Integral> (fiat_shamir.hpp:190-199): state = H(state); raw_result &= ~Integral(0)."""
+        self.state = self.h(self.state)
+        return int.from_bytes(self.state, "big") & ((1 << bits) - 1)
+
+    def copy(self):
+        t = FiatShamirSequential(self.h)
+        t.state = self.state
+        return t

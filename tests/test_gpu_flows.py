@@ -40,6 +40,7 @@ class OracleTranscript:
 
     def __init__(self, h, F, init=b"\x00"):
         self.t, self.F = hashes.FiatShamirSequential(h, init), F
+        self.hash_id = [k for k, v in HASHES.items() if v is h][0]
 
     def __call__(self, data):
         self.t.absorb(data)
@@ -47,6 +48,13 @@ class OracleTranscript:
     def challenge(self, modulus):
         assert modulus == self.F.p
         return self.t.challenge(self.F)
+
+    def int_challenge(self, bits=32):
+        return self.t.int_challenge(bits)
+
+    @property
+    def state(self):
+        return self.t.state
 
 
 @pytest.mark.parametrize("hid", [0, 1, 2], ids=["keccak256", "sha256", "keccak512"])
@@ -215,6 +223,98 @@ def test_lpc_scheme_flow_vs_oracle(ctx, F, hid):
     assert got["fri"]["roots"] == want["roots"]
     assert got["fri"]["alphas"] == want["alphas"]
     assert got["fri"]["final_polynomial"] == want["final_polynomial"]
+
+
+# ------------------------------------------------------------------------------------------ query phase
+@pytest.mark.parametrize("hid", [0, 1, 2], ids=["keccak256", "sha256", "keccak512"])
+@pytest.mark.parametrize("mask", [0xFF, 0xFFF, 0x3FFFFF])
+def test_pow_grind_vs_oracle(ctx, hid, mask):
+    """proof_of_work<Hash, uint32>::generate (proof_of_work.hpp:47-68): smallest passing nonce, any start"""
+    from oracle import fri_query
+    h = HASHES[hid]
+    t = hashes.FiatShamirSequential(h, b"grind-%d" % mask)
+    nonce = ctx.pow_grind(hid, t.state, mask)
+    assert fri_query.pow_verify(t.copy(), nonce, mask)
+    if mask <= 0xFFF:
+        assert nonce == fri_query.pow_generate(t.copy(), mask)
+        nxt = ctx.pow_grind(hid, t.state, mask, start=nonce + 1)
+        assert nxt > nonce and nxt == fri_query.pow_generate(t.copy(), mask, nonce + 1)
+    else:   # the oracle walk would take minutes: check minimality on a window below the hit instead
+        lo = max(0, nonce - 300)
+        for cand in range(lo, nonce):
+            assert not fri_query.pow_verify(t.copy(), cand, mask)
+
+
+def test_merkle_paths_vs_single_path(ctx):
+    F, h = fields.PALLAS_FQ, hashes.keccak256
+    polys = [fields.random_elements(F, 256, 3 + i) for i in range(2)]
+    levels, _ = fri.precommit(polys, F, 256, 2, h)
+    tree = ctx.merkle_commit(F.name, 0, dev(to_arr([v for c in polys for v in c]).reshape(2, 256, 8)), 8, 2, keep_tree=True)
+    idx = [0, 1, 63, 17, 17, 40]
+    got = tree.paths(idx)
+    assert got == [tree.path(i) for i in idx] == [fri.merkle_proof(levels, i) for i in idx]
+    with pytest.raises(Exception):
+        tree.paths([64])
+    assert tree.paths([]) == []
+
+
+@pytest.mark.parametrize("F,hid,steps,degree_log,expand,grind,sizes", [
+    (fields.PALLAS_FQ, 0, [1, 1, 1], 4, 2, False, (16, 16, 16)),
+    (fields.PALLAS_FP, 2, [2, 1, 1], 5, 2, True, (32, 32, 16)),
+    (fields.BLS12_381_FR, 1, [3, 1], 5, 2, True, (32, 128, 32)),
+    (fields.BN254_FR, 0, [1, 2, 2, 1], 7, 1, False, (128, 64, 128)),
+], ids=["steps111", "steps211-grind-k512", "steps31-grind-sha-d0poly", "steps1221"])
+def test_lpc_full_proof_vs_oracle(ctx, F, hid, steps, degree_log, expand, grind, sizes):
+    """Complete lpc proof (lpc.hpp:113-200 -> basic_fri.hpp:670-923: commit phase, grinding, query phase) from the
+    device path: identical to the oracle prover's proof, accepted by the oracle verifier (basic_fri.hpp:932-1150,
+    lpc.hpp:202-263), rejected once tampered.  Batches mix polynomial sizes, one batch may already live on D[0]."""
+    from crypto3_zk_b200.lpc import FriParams, LpcCommitmentScheme
+    from oracle import fri_query
+    h, p, lam = HASHES[hid], F.p, 5
+    d0 = 1 << (degree_log + expand)
+    def rnd(size, seed):   # evaluations of a polynomial of degree <= max_degree, possibly on a larger domain
+        n0 = min(size, 1 << degree_log)
+        v = fields.random_elements(F, n0, seed)
+        return v if n0 == size else ntt.dfs_resize(v, F, size)
+
+    polys = {0: [rnd(sizes[0], 1 + i) for i in range(2)],
+             1: [rnd(sizes[1], 10 + i) for i in range(3)],
+             4: [rnd(sizes[2], 20)]}
+    y = fields.random_elements(F, 1, 77)[0]
+    yw = y * F.omega(degree_log) % p
+    points = {0: [[y], [y]], 1: [[y], [y, yw], [yw]], 4: [[y]]}
+    params = fri_query.FriParams(F, steps, degree_log, lam, expand, grind, 0x3FF)
+    tr = hashes.FiatShamirSequential(h, b"\x07")
+    etha = tr.challenge(F)
+    trees = {k: fri.precommit(polys[k], F, d0, steps[0], h)[0] for k in polys}
+    fixed_values = {0: [lpc.poly_eval(ntt.dfs_coefficients(q, F), etha, p) for q in polys[0]]}
+    tp = tr.copy()
+    want = fri_query.lpc_proof_eval(polys, points, trees, params, tp, h, (0,), etha, fixed_values)
+    # ---- device
+    scheme = LpcCommitmentScheme(ctx, F.name, hid, FriParams(steps, degree_log, lam, expand, grind, 0x3FF))
+    t2 = OracleTranscript(h, F, b"\x07")
+    for k in polys:
+        nk = len(polys[k][0])
+        scheme.append_to_batch(k, dev(to_arr([v for c in polys[k] for v in c]).reshape(len(polys[k]), nk, 8)))
+    scheme.mark_batch_as_fixed(0)
+    scheme.setup(t2, fixed_values)
+    commitments = {k: scheme.commit(k) for k in polys}
+    assert commitments == {k: trees[k][-1][0] for k in trees}
+    for k in points:
+        for i, pts in enumerate(points[k]):
+            for x in pts:
+                scheme.append_eval_point(k, x, poly=i)
+    got = scheme.proof_eval(t2, query=True)["proof"]
+    assert got["z"] == want["z"]
+    gf, wf = got["fri_proof"], want["fri_proof"]
+    assert gf["fri_roots"] == wf["fri_roots"] and gf["final_polynomial"] == wf["final_polynomial"]
+    assert gf["proof_of_work"] == wf["proof_of_work"]
+    assert gf["query_proofs"] == wf["query_proofs"]
+    assert t2.state == tp.state
+    tv = tr.copy()
+    assert fri_query.lpc_verify_eval(got, points, commitments, params, tv, h, (0,), etha, fixed_values)
+    bad = {"z": got["z"], "fri_proof": dict(gf, final_polynomial=[(gf["final_polynomial"][0] + 1) % p] + gf["final_polynomial"][1:])}
+    assert not fri_query.lpc_verify_eval(bad, points, commitments, params, tr.copy(), h, (0,), etha, fixed_values)
 
 
 # ------------------------------------------------------------------------------------------ Groth16 (config #4)
