@@ -224,6 +224,16 @@ def extras(args, torch, ctx, dev, hbm_peak):
             "kind": "port", "sample": "2^%d of the 2^%d points, BDLO12 bucket MSM, chunks = threads" % (ns.bit_length() - 1, log_m)}
     bases.free()
     del pts, sc
+    # ---- grinding (proof_of_work.hpp:47-68), keccak-256 transcript: expected 2^bits nonce trials of two hashes each
+    from crypto3_zk_b200.transcript import FiatShamirSequential
+    gr = {}
+    for bits in (16, 24):
+        tr = FiatShamirSequential(0, b"bench-grind-%d" % bits)
+        ctx.pow_grind(0, tr.state, (1 << bits) - 1)
+        t0 = time.perf_counter()
+        nonce = ctx.pow_grind(0, tr.state, (1 << bits) - 1)
+        gr["mask_bits_%d" % bits] = {"ms": (time.perf_counter() - t0) * 1e3, "nonce": nonce}
+    ex["pow_grind_keccak256"] = gr
     return ex
 
 
@@ -470,11 +480,17 @@ def placeholder_extra(args, torch, ctx, dev):
             del co
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            pe = scheme.proof_eval(tr)
+            pe = scheme.proof_eval(tr, query=True)
             torch.cuda.synchronize()
-            t_eval = (time.perf_counter() - t0) * 1e3
+            t_all = (time.perf_counter() - t0) * 1e3
+            t_query = scheme.timings["query_phase_ms"]
+            t_eval = t_all - t_query
+            fp = pe["proof"]["fri_proof"]
             res.update({"commit_ms": t_commit, "proof_eval_commit_phase_ms": t_eval,
+                        "proof_eval_query_phase_ms": t_query, "queries": len(fp["query_proofs"]),
+                        "merkle_paths_opened": sum(len(q["initial_proof"]) + len(q["round_proofs"]) for q in fp["query_proofs"]),
                         "ms_per_proof_commitment_phase": sum(t_commit.values()) + t_eval,
+                        "ms_per_proof_with_query_phase": sum(t_commit.values()) + t_all,
                         "fri_rounds": len(pe["fri"]["roots"]), "log_d0": fri.log_d0,
                         "quotients_exact": all(r == 0 for r in pe["remainders"]),
                         "final_polynomial_len": len(pe["fri"]["final_polynomial"])})

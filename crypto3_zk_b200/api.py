@@ -412,6 +412,22 @@ class Context:
         flat = _ints(out.reshape(-1, 8))
         return [flat[i * len(points):(i + 1) * len(points)] for i in range(batch)]
 
+    def poly_evaluate_pm(self, field, polys, n, points, stream=None):
+        """Values of coefficient-form device polynomials at z and -z for every point (FRI query phase,
+        basic_fri.hpp:819-834).  Returns a list (per polynomial) of lists (per point) of (f(z), f(-z))."""
+        fid = _field_id(field)
+        b = _Buf(polys)
+        if b.mem != capi.MEM_DEVICE:
+            raise ValueError("poly_evaluate_pm works on device tensors")
+        batch = b.nbytes // (n * 32)
+        pts = np.ascontiguousarray(_int_rows(points))
+        out = np.zeros((batch, len(points), 2, 8), dtype=np.uint32)
+        capi.check(capi.lib().zkb_poly_evaluate_pm(self._h, fid, n, batch, b.ptr, len(points), capi.u32_ptr(pts),
+                                                   capi.u32_ptr(out), _stream_ptr(polys, stream)), self._h)
+        flat = _ints(out.reshape(-1, 8))
+        k = len(points)
+        return [[(flat[2 * (i * k + j)], flat[2 * (i * k + j) + 1]) for j in range(k)] for i in range(batch)]
+
     def poly_lincomb(self, field, polys, n, scalars, constant=None, out=None, accumulate=False, stream=None):
         """out[i] (+)= sum_j scalars[j] polys[j][i] - [i == 0] constant on device tensors (lpc.hpp:139-153)."""
         fid = _field_id(field)

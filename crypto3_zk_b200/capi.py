@@ -22,7 +22,7 @@ SYMBOLS = [
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
     "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul",
     "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
-    "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec", "zkb_pow_grind", "zkb_merkle_paths",
+    "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec", "zkb_pow_grind", "zkb_merkle_paths", "zkb_poly_evaluate_pm",
 ]
 POLY_COEFFICIENTS, POLY_DFS = 0, 1
 # int (*zkb_fri_challenge_fn)(void *user, uint32_t round, const uint8_t *root, uint32_t root_bytes, uint32_t count, uint32_t *alphas_out)
@@ -100,6 +100,7 @@ def lib():
     L.zkb_fri_commit_phase.argtypes = [vp, i, i, i, vp, i, u32p, u32, FRI_CHALLENGE_FN, vp, u8p, ctypes.POINTER(vp), vp,
                                        u32p, u32p, vp]
     L.zkb_poly_evaluate.argtypes = [vp, i, i, u64, u32, vp, i, u32, u32p, u32p, vp]
+    L.zkb_poly_evaluate_pm.argtypes = [vp, i, u64, u32, vp, u32, u32p, u32p, vp]
     L.zkb_poly_lincomb.argtypes = [vp, i, u64, u32, vp, u32p, u32p, vp, i, vp]
     L.zkb_poly_div_linear.argtypes = [vp, i, u64, vp, u32p, vp, u32p, vp]
     L.zkb_sparse_matrix_create.argtypes = [vp, i, u64, u64, ctypes.POINTER(u64), u32p, u32p, vp, ctypes.POINTER(vp)]

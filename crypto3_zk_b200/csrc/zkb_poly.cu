@@ -67,7 +67,7 @@ struct EvalPoints {
 template <class P>
 __global__ void __launch_bounds__(ZKB_POLY_THREADS) poly_eval_segments_kernel(const Fp<P> *coeffs, uint64_t n, uint64_t poly_stride,
                                                                               uint64_t seg_len, uint32_t segs, EvalPoints<Fp<P>> pts,
-                                                                              int scale_by_start, Fp<P> *partial) {
+                                                                              int scale_by_start, int paired, Fp<P> *partial) {
     typedef Fp<P> F;
     __shared__ F sh[ZKB_POLY_THREADS];
     const uint32_t seg = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
@@ -87,26 +87,38 @@ __global__ void __launch_bounds__(ZKB_POLY_THREADS) poly_eval_segments_kernel(co
                 if (p < pts.count) acc[p] = acc[p] * pts.z256[p] + v;
         }
     }
+    // paired: also the value at -z.  A lane's coefficients k = start + t + 256 m all have the parity of t (segments start
+    // at multiples of 256), and (-z)^256 = z^256, so the Horner pass above is shared: only the lane weights change sign.
+    const int slots = paired ? 2 * ZKB_POLY_MAXPTS : ZKB_POLY_MAXPTS;
     for (int p = 0; p < pts.count; p++) {
         F zt = pts.z[p].pow_u64(t);                 // Montgomery
-        F s = block_sum<F>(acc[p] * zt, sh);
+        F term = acc[p] * zt;
+        F s = block_sum<F>(term, sh);
+        F s2 = F::zero();
+        if (paired) s2 = block_sum<F>((t & 1) ? term.neg() : term, sh);
         if (t == 0) {
-            if (scale_by_start) s = s * pts.z[p].pow_u64(start);
-            partial[((uint64_t)b * segs + seg) * ZKB_POLY_MAXPTS + p] = s;
+            if (scale_by_start) {
+                F zs = pts.z[p].pow_u64(start);
+                s = s * zs;
+                if (paired) s2 = s2 * zs;           // start is even: (-z)^start = z^start
+            }
+            partial[((uint64_t)b * segs + seg) * slots + p] = s;
+            if (paired) partial[((uint64_t)b * segs + seg) * slots + ZKB_POLY_MAXPTS + p] = s2;
         }
     }
 }
 
 template <class P>
 __global__ void poly_eval_reduce_kernel(const Fp<P> *partial, uint32_t segs, uint32_t batch, int count, uint32_t npoints_total,
-                                        uint32_t point0, Fp<P> *out) {
+                                        uint32_t point0, int paired, Fp<P> *out) {
     typedef Fp<P> F;
+    const int per = paired ? 2 : 1, slots = per * ZKB_POLY_MAXPTS;
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= batch * (uint32_t)count) return;
-    uint32_t b = idx / count, p = idx % count;
+    if (idx >= batch * (uint32_t)count * per) return;
+    uint32_t b = idx / (count * per), r = idx % (count * per), p = r / per, neg = r % per;
     F s = F::zero();
-    for (uint32_t g = 0; g < segs; g++) s = s + partial[((uint64_t)b * segs + g) * ZKB_POLY_MAXPTS + p];
-    out[(uint64_t)b * npoints_total + point0 + p] = s;
+    for (uint32_t g = 0; g < segs; g++) s = s + partial[((uint64_t)b * segs + g) * slots + neg * ZKB_POLY_MAXPTS + p];
+    out[((uint64_t)b * npoints_total + point0 + p) * per + neg] = s;   // paired: [b][point][z, -z]
 }
 
 static void pick_segments(uint64_t n, uint32_t batch, int sm_count, uint64_t *seg_len, uint32_t *segs) {
@@ -123,14 +135,15 @@ static void pick_segments(uint64_t n, uint32_t batch, int sm_count, uint64_t *se
 
 template <class P>
 static int poly_evaluate_t(zkb_ctx *ctx, uint64_t n, uint32_t batch, const void *d_coeffs, uint32_t npoints,
-                           const uint32_t *points, uint32_t *out, cudaStream_t st) {
+                           const uint32_t *points, uint32_t *out, int paired, cudaStream_t st) {
     typedef Fp<P> F;
+    const int per = paired ? 2 : 1;
     uint64_t seg_len;
     uint32_t segs;
     pick_segments(n, batch, ctx->sm_count, &seg_len, &segs);
     void *partial, *dout;
-    ZKB_TRY(ctx_scratch(ctx, "eval_partial", (size_t)batch * segs * ZKB_POLY_MAXPTS * sizeof(F), &partial));
-    ZKB_TRY(ctx_scratch(ctx, "eval_out", (size_t)batch * npoints * sizeof(F), &dout));
+    ZKB_TRY(ctx_scratch(ctx, "eval_partial", (size_t)batch * segs * per * ZKB_POLY_MAXPTS * sizeof(F), &partial));
+    ZKB_TRY(ctx_scratch(ctx, "eval_out", (size_t)batch * npoints * per * sizeof(F), &dout));
     for (uint32_t p0 = 0; p0 < npoints; p0 += ZKB_POLY_MAXPTS) {
         EvalPoints<F> pts;
         pts.count = npoints - p0 < ZKB_POLY_MAXPTS ? (int)(npoints - p0) : ZKB_POLY_MAXPTS;
@@ -148,13 +161,13 @@ static int poly_evaluate_t(zkb_ctx *ctx, uint64_t n, uint32_t batch, const void 
             }
         }
         dim3 grid(segs, batch);
-        poly_eval_segments_kernel<P><<<grid, ZKB_POLY_THREADS, 0, st>>>((const F *)d_coeffs, n, n, seg_len, segs, pts, 1, (F *)partial);
-        uint32_t total = batch * (uint32_t)pts.count;
-        poly_eval_reduce_kernel<P><<<(total + 127) / 128, 128, 0, st>>>((const F *)partial, segs, batch, pts.count, npoints, p0, (F *)dout);
+        poly_eval_segments_kernel<P><<<grid, ZKB_POLY_THREADS, 0, st>>>((const F *)d_coeffs, n, n, seg_len, segs, pts, 1, paired, (F *)partial);
+        uint32_t total = batch * (uint32_t)pts.count * per;
+        poly_eval_reduce_kernel<P><<<(total + 127) / 128, 128, 0, st>>>((const F *)partial, segs, batch, pts.count, npoints, p0, paired, (F *)dout);
         ctx->launches += 2;
         ZKB_CUDA_OK(ctx, cudaGetLastError());
     }
-    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(out, dout, (size_t)batch * npoints * sizeof(F), cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(out, dout, (size_t)batch * npoints * per * sizeof(F), cudaMemcpyDeviceToHost, st));
     ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
     return ZKB_OK;
 }
@@ -402,8 +415,8 @@ static int spmv_t(zkb_ctx *ctx, const zkb_sparse_matrix *m, const void *dx, void
 }
 
 static int poly_evaluate_dispatch(zkb_ctx *ctx, int field, uint64_t n, uint32_t batch, const void *d, uint32_t npoints,
-                                  const uint32_t *points, uint32_t *out, cudaStream_t st) {
-    ZKB_DISPATCH_FR(field, poly_evaluate_t, ctx, n, batch, d, npoints, points, out, st)
+                                  const uint32_t *points, uint32_t *out, int paired, cudaStream_t st) {
+    ZKB_DISPATCH_FR(field, poly_evaluate_t, ctx, n, batch, d, npoints, points, out, paired, st)
 }
 static int poly_lincomb_dispatch(zkb_ctx *ctx, int field, uint64_t n, uint32_t batch, const void *d, const uint32_t *sc,
                                  const uint32_t *c, void *out, int acc, cudaStream_t st) {
@@ -450,7 +463,17 @@ int zkb_poly_evaluate(zkb_ctx *ctx, int field, int form, uint64_t n, uint32_t ba
         ZKB_TRY(ntt_device(ctx, field, log_n, batch, d, coef, 1, nullptr, n, n, st));
         d = coef;
     }
-    return poly_evaluate_dispatch(ctx, field, n, batch, d, npoints, points, out, st);
+    return poly_evaluate_dispatch(ctx, field, n, batch, d, npoints, points, out, 0, st);
+}
+
+int zkb_poly_evaluate_pm(zkb_ctx *ctx, int field, uint64_t n, uint32_t batch, const void *polys_device, uint32_t npoints,
+                         const uint32_t *points, uint32_t *out, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!is_fr(field) || n == 0 || !polys_device || !points || !out)
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_poly_evaluate_pm: bad arguments");
+    if (batch == 0 || npoints == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return poly_evaluate_dispatch(ctx, field, n, batch, polys_device, npoints, points, out, 1, (cudaStream_t)stream);
 }
 
 int zkb_poly_lincomb(zkb_ctx *ctx, int field, uint64_t n, uint32_t batch, const void *polys_device, const uint32_t *scalars,

@@ -58,6 +58,7 @@ class LpcCommitmentScheme:
         self._etha = None
         self._fixed_values = None
         self.z = {}
+        self.timings = {}
 
     # ---- polys_evaluator interface (batched_commitment.hpp:196-250)
     def append_to_batch(self, index, poly):
@@ -200,7 +201,10 @@ class LpcCommitmentScheme:
         out = {"z": self.z, "theta": theta, "combined_Q_normal": combined, "combined_Q": q_d0[0],
                "remainders": remainders, "fri": fri}
         if query:
+            import time
+            t0 = time.perf_counter()
             out["proof"] = {"z": self.z, "fri_proof": self._query_phase(transcript, fri)}
+            self.timings["query_phase_ms"] = (time.perf_counter() - t0) * 1e3
         return out
 
     # ---- grinding + query phase of zk::algorithms::proof_eval<FRI> (basic_fri.hpp:743-915)
@@ -253,7 +257,9 @@ class LpcCommitmentScheme:
             x_idx0.append(self._domain_index(x, log_d0))
         w0 = omega(F, log_d0)
         init_pairs = [[(min(a, b), max(a, b)) for a, b in self._s_indices(xi, d0, steps[0])] for xi in x_idx0]
-        flat = sorted({i for pairs in init_pairs for pr in pairs for i in pr})
+        # every pair is (i, i + |D0|/2): the points z = w^i and -z, which zkb_poly_evaluate_pm opens in one pass
+        half0 = d0 // 2
+        flat = sorted({a for pairs in init_pairs for a, _ in pairs})
         pos = {i: n for n, i in enumerate(flat)}
         pts = [pow(w0, i, p) for i in flat]
         initial = [dict() for _ in range(lam)]
@@ -262,14 +268,16 @@ class LpcCommitmentScheme:
             co, n = self._coeffs[k]
             if n == d0:    # already on D[0]: the values themselves (basic_fri.hpp:812-818)
                 batch, _ = self._batch_tensor(k)
-                sel = batch[:, torch.tensor(flat, device=batch.device)].cpu().numpy().view(np.uint32)
-                vals = [[int.from_bytes(sel[i, j].tobytes(), "little") for j in range(len(flat))] for i in range(sel.shape[0])]
+                idx = [i for a in flat for i in (a, a + half0)]
+                sel = batch[:, torch.tensor(idx, device=batch.device)].cpu().numpy().view(np.uint32)
+                vals = [[(int.from_bytes(sel[i, 2 * j].tobytes(), "little"), int.from_bytes(sel[i, 2 * j + 1].tobytes(), "little"))
+                         for j in range(len(flat))] for i in range(sel.shape[0])]
             else:          # evaluate the coefficient form at the 2 lambda points (:819-834)
-                vals = self.ctx.poly_evaluate(F.name, co, n, pts)
+                vals = self.ctx.poly_evaluate_pm(F.name, co, n, pts)
             paths = self._trees[k].paths(leaf0)
             root = self._trees[k].root()
             for q in range(lam):
-                initial[q][k] = {"values": [[[v[pos[a]], v[pos[b]]] for a, b in init_pairs[q]] for v in vals],
+                initial[q][k] = {"values": [[list(v[pos[a]]) for a, _ in init_pairs[q]] for v in vals],
                                  "p": {"index": leaf0[q], "path": paths[q], "root": root}}
         # round proofs: paths from every fri tree, y from the retained fs (one gather), final round from final_polynomial
         fs, fs_off, acc, off = fri["fs"], [], log_d0, 0

@@ -196,6 +196,12 @@ typedef enum { ZKB_POLY_COEFFICIENTS = 0, ZKB_POLY_DFS = 1 } zkb_poly_form;
  * points: host, npoints elements; out: host, [batch][npoints] elements. */
 int zkb_poly_evaluate(zkb_ctx *ctx, int field, int form, uint64_t n, uint32_t batch, const void *polys, int mem,
                       uint32_t npoints, const uint32_t *points, uint32_t *out, void *stream);
+/* The FRI query phase opens every polynomial at the pairs (s, -s) of lambda query cosets
+ * (basic_fri.hpp:819-834: `g_coeffs[k][polynomial_index].evaluate(s0)` / `.evaluate(s1)`): values of the coefficient-form
+ * polynomials (device) at z and at -z for every point with ONE pass over the coefficients per four points.
+ * out: host, [batch][npoints][2] elements (value at z, value at -z). */
+int zkb_poly_evaluate_pm(zkb_ctx *ctx, int field, uint64_t n, uint32_t batch, const void *polys_device, uint32_t npoints,
+                         const uint32_t *points, uint32_t *out, void *stream);
 /* numerator of one point of lpc::proof_eval's combined Q (zk/commitments/polynomial/lpc.hpp:139-153, 163-176):
  * out[i] (+)= sum_j scalars[j] * polys[j][i] - [i == 0] * constant, with scalars[j] = theta^k for the polynomials
  * opened at the point and 0 for the others (skipped), constant = sum_j theta^k z_j (NULL = 0).

@@ -130,6 +130,17 @@ def test_poly_evaluate_vs_oracle(ctx, F, n, batch, npts):
     assert ctx.poly_evaluate(F.name, dev(a), n, pts) == want
 
 
+@pytest.mark.parametrize("n,batch,npts", [(1, 1, 1), (5, 2, 3), (255, 2, 4), (256, 1, 5), (1000, 3, 2), (5000, 2, 9), (70000, 2, 6)])
+def test_poly_evaluate_pm_vs_oracle(ctx, n, batch, npts):
+    """values at z and -z from one pass (query phase openings, basic_fri.hpp:819-834)"""
+    F = fields.PALLAS_FP
+    polys = [fields.random_elements(F, n, 31 + b) for b in range(batch)]
+    pts = fields.random_elements(F, npts, 5)
+    got = ctx.poly_evaluate_pm(F.name, dev(to_arr([v for c in polys for v in c]).reshape(batch, n, 8)), n, pts)
+    want = [[(lpc.poly_eval(c, z, F.p), lpc.poly_eval(c, (F.p - z) % F.p, F.p)) for z in pts] for c in polys]
+    assert got == want
+
+
 def test_poly_evaluate_dfs_and_large(ctx):
     """polynomial_dfs::evaluate = coefficients() then the value; 2^20-sized columns against Horner on the CPU."""
     F = fields.PALLAS_FQ
