@@ -95,7 +95,7 @@ static void replay_pass(const NttPassParams &p) {
 
 template <class P>
 static int host_ntt(int log_n, int log_n_in, int inverse, const uint32_t *shift, uint32_t batch,
-                    const uint32_t *in, uint32_t *out) {
+                    const uint32_t *in, uint32_t *out, const uint32_t *known_src = nullptr, int known_log = 0) {
     typedef Fp<P> F;
     if (log_n > P::TWO_ADICITY || log_n < 1) return 2;
     const uint64_t N = 1ull << log_n, Nin = 1ull << log_n_in;
@@ -140,9 +140,31 @@ static int host_ntt(int log_n, int log_n_in, int inverse, const uint32_t *shift,
         tb.store_tab = cos.data(); tb.store_mask = 0;
     }
     std::vector<F> work((size_t)N * batch);
-    auto passes = ntt_build_passes(pl, tb, in, out, work.data(), batch, Nin, N, Nin);
+    // poison the work buffer: a pass that reads something the known-output path never stored would show up
+    memset(work.data(), 0xA5, work.size() * sizeof(F));
+    auto passes = ntt_build_passes(pl, tb, in, out, work.data(), batch, Nin, N, Nin, known_src, known_log, Nin);
     for (auto &q : passes) replay_pass<P>(q);
     return 0;
+}
+
+// polynomial_dfs::resize as lde_device runs it: inverse transform, then the zero-padded forward transform whose
+// outputs at multiples of the blow-up are taken from the input evaluations
+template <class P>
+static int host_lde(int log_in, int log_out, uint32_t batch, const uint32_t *in, uint32_t *out) {
+    std::vector<uint32_t> coef((size_t)batch << log_in << 3);
+    int rc = host_ntt<P>(log_in, log_in, 1, nullptr, batch, in, coef.data());
+    if (rc) return rc;
+    return host_ntt<P>(log_out, log_in, 0, nullptr, batch, coef.data(), out, in, log_out - log_in);
+}
+
+extern "C" int zkb_host_lde(int field_id, int log_in, int log_out, uint32_t batch, const uint32_t *in, uint32_t *out) {
+    switch (field_id) {
+        case 0: return host_lde<params::Bls12381Fr>(log_in, log_out, batch, in, out);
+        case 1: return host_lde<params::Bn254Fr>(log_in, log_out, batch, in, out);
+        case 2: return host_lde<params::PallasFp>(log_in, log_out, batch, in, out);
+        case 3: return host_lde<params::PallasFq>(log_in, log_out, batch, in, out);
+    }
+    return 1;
 }
 
 extern "C" int zkb_host_ntt(int field_id, int log_n, int log_n_in, int inverse, const uint32_t *shift,

@@ -57,7 +57,8 @@ int ctx_table(zkb_ctx *ctx, const std::string &key, size_t bytes, void **out, bo
 
 // device-pointer level entry points used across translation units
 int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
-               const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st);
+               const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st,
+               const void *known_src = nullptr, int known_log = 0, uint64_t known_poly_stride = 0);
 int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
                cudaStream_t st);
 // one FRI fold on device buffers (alpha: host, canonical limbs)

@@ -112,7 +112,8 @@ static int ntt_launch(zkb_ctx *ctx, const NttPassParams &q, cudaStream_t st) {
 
 template <class P>
 static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
-                        const uint32_t *shift, uint64_t in_poly_stride, uint64_t in_valid, cudaStream_t st) {
+                        const uint32_t *shift, uint64_t in_poly_stride, uint64_t in_valid, cudaStream_t st,
+                        const void *known_src, int known_log, uint64_t known_poly_stride) {
     typedef Fp<P> F;
     if (log_n > P::TWO_ADICITY) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n exceeds the two-adicity");
     const uint64_t N = 1ull << log_n;
@@ -134,7 +135,8 @@ static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_i
         uint32_t nb = batch - b0 < chunk ? batch - b0 : chunk;
         const char *cin = (const char *)d_in + (size_t)b0 * in_poly_stride * sizeof(F);
         char *cout = (char *)d_out + (size_t)b0 * poly_bytes;
-        auto passes = ntt_build_passes(pl, tb, cin, cout, work, nb, in_poly_stride, N, in_valid);
+        const char *ksrc = known_src ? (const char *)known_src + (size_t)b0 * known_poly_stride * sizeof(F) : nullptr;
+        auto passes = ntt_build_passes(pl, tb, cin, cout, work, nb, in_poly_stride, N, in_valid, ksrc, known_log, known_poly_stride);
         for (auto &q : passes) ZKB_TRY(ntt_launch<P>(ctx, q, st));
     }
     return ZKB_OK;
@@ -152,7 +154,8 @@ static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_i
 namespace zkb {
 
 int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
-               const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st) {
+               const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st,
+               const void *known_src, int known_log, uint64_t known_poly_stride) {
     if (batch == 0) return ZKB_OK;
     if (log_n == 0) {  // size-1 transform is the identity (a coset shift g^0 = 1, 1/n = 1)
         if (d_in != d_out)
@@ -160,7 +163,7 @@ int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d
         return ZKB_OK;
     }
     ZKB_DISPATCH_NTT_FIELD(field, ntt_device_t, ctx, log_n, batch, d_in, d_out, inverse, coset_shift, in_poly_stride,
-                           in_valid_elems, st)
+                           in_valid_elems, st, known_src, known_log, known_poly_stride)
 }
 
 int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
@@ -184,7 +187,8 @@ int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t ba
         const char *cin = (const char *)d_in + (size_t)b0 * Nin * 32;
         char *cout = (char *)d_out + (size_t)b0 * Nout * 32;
         ZKB_TRY(ntt_device(ctx, field, log_n_in, nb, cin, coef, 1, nullptr, Nin, Nin, st));
-        ZKB_TRY(ntt_device(ctx, field, log_n_out, nb, coef, cout, 0, nullptr, Nin, Nin, st));
+        // out[8 i] (blow-up 8) are the input evaluations: the forward transform neither computes nor stores them
+        ZKB_TRY(ntt_device(ctx, field, log_n_out, nb, coef, cout, 0, nullptr, Nin, Nin, st, cin, log_n_out - log_n_in, Nin));
     }
     return ZKB_OK;
 }

@@ -55,6 +55,14 @@ struct NttPassParams {
     const void *store_tab;        // optional: out[o] *= store_tab[o & store_mask]
     uint64_t store_mask;
     const void *tw;               // master twiddles w_{2^ZKB_NTT_TW_LOG}^j (direction specific)
+    // LDE: the outputs at multiples of 2^known_log are the input evaluations themselves (the coset of index 0 of the
+    // larger domain is the smaller domain), out[poly][j 2^known_log] = known_src[poly][j].  Such outputs have
+    // k_1 = 0 mod 2^known_log, so they are never computed: pass 1 does not store those rows, the middle passes skip
+    // the tiles of those k_1, and the last pass leaves their column out and copies it from known_src.
+    int known_log;                // 0 = off; otherwise 3 <= known_log <= lr[0]
+    int known_k1_shift;           // middle pass: k_1 = q >> known_k1_shift
+    const u128 *known_src;
+    uint64_t known_poly_stride;
 };
 
 // shared-memory layout: two planes (low/high 16 bytes of every element), [row][C+1] 16-byte slots,
@@ -80,11 +88,17 @@ struct NttTile {
     uint64_t in_row_stride, in_col_stride, out_row_stride, out_col_stride;
     uint64_t in_tab_base, out_tab_base;         // offsets within the polynomial (for the tables)
     uint32_t ncols;                             // valid columns
+    uint32_t skip_col0;                         // 1: column 0 of this FINAL tile is known: loaded as zeros, stored from known_src
+                                                // (its butterflies still run: a 7-column task map breaks the conflict-free
+                                                // quarter-warp shared-memory pattern and measured slower)
+    uint64_t poly;
 };
 
 ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
     NttTile t;
     const uint32_t C = ZKB_NTT_C;
+    t.skip_col0 = 0;
+    t.poly = 0;
     if (p.mode == NTT_MODE_SINGLE) {
         // columns = polynomials of the batch
         uint64_t b0 = tile * C;
@@ -100,9 +114,18 @@ ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
     uint64_t poly = tile / p.tiles_per_poly;
     uint64_t tt = tile % p.tiles_per_poly;
     t.ncols = C;
+    t.poly = poly;
     if (p.mode == NTT_MODE_STRIDED) {
         uint64_t blocks = (1ull << p.log_m) / C;       // column blocks per row group
         uint64_t q = tt / blocks, cb = tt % blocks;
+        if (p.known_log > 0 && p.log_mprev < p.log_n) {
+            // middle pass: the tiles of k_1 = 0 mod 2^known_log are not part of the grid
+            uint64_t per_k1 = blocks << p.known_k1_shift;
+            uint64_t k1p = tt / per_k1, rest = tt % per_k1;
+            uint64_t k1 = k1p + k1p / ((1ull << p.known_log) - 1) + 1;
+            q = (k1 << p.known_k1_shift) + rest / blocks;
+            cb = rest % blocks;
+        }
         uint64_t off = (q << p.log_mprev) + cb * C;
         t.in_tab_base = off; t.out_tab_base = off;
         t.in_base = poly * p.in_poly_stride + off;
@@ -125,6 +148,7 @@ ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
         t.out_base = poly * p.out_poly_stride + out_off;
         t.in_row_stride = 1; t.in_col_stride = 1ull << p.log_m;
         t.out_row_stride = 1ull << (p.log_n - p.log_r); t.out_col_stride = 1;
+        if (p.known_log > 0 && ((kb * C) & ((1ull << p.known_log) - 1)) == 0) t.skip_col0 = 1;
     }
     return t;
 }
@@ -173,7 +197,7 @@ ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem,
         }
         u128 v = zero;
         uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
-        if (c < t.ncols && widx < p.in_valid_elems)
+        if (c < t.ncols && c >= t.skip_col0 && widx < p.in_valid_elems)
             v = p.in[2 * (t.in_base + r * t.in_row_stride + c * t.in_col_stride) + half];
         for (uint32_t k = 0; k < copies; k++) smem[ntt_slot(p.log_r, half, r + k * L, c)] = v;
     }
@@ -276,15 +300,24 @@ ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128
                 half = u & 1; k = (u >> 1) % R; c = u / (2 * R);
             }
             if (c >= t.ncols) continue;
-            p.out[2 * (t.out_base + k * t.out_row_stride + c * t.out_col_stride) + half] =
-                smem[ntt_slot(p.log_r, half, brev(k, p.log_r), c)];
+            u128 v;
+            if (c < t.skip_col0) {   // known output: the input evaluation at (output index) >> known_log
+                uint64_t o = t.out_tab_base + k * t.out_row_stride;
+                v = p.known_src[2 * (t.poly * p.known_poly_stride + (o >> p.known_log)) + half];
+            } else {
+                v = smem[ntt_slot(p.log_r, half, brev(k, p.log_r), c)];
+            }
+            p.out[2 * (t.out_base + k * t.out_row_stride + c * t.out_col_stride) + half] = v;
         }
         return;
     }
+    // first pass of a transform with known outputs: rows k_1 = 0 mod 2^known_log are never read again
+    const bool kskip = p.known_log > 0 && p.mode == NTT_MODE_STRIDED && p.log_mprev == p.log_n;
+    const uint32_t kmask = kskip ? (1u << p.known_log) - 1 : 0u;
     for (uint32_t e = tid; e < R * C; e += nthreads) {
         uint32_t k, c;
         if (t.out_col_stride == 1) { c = e % C; k = e / C; } else { k = e % R; c = e / R; }
-        if (c >= t.ncols) continue;
+        if (c >= t.ncols || (kskip && (k & kmask) == 0)) continue;
         uint64_t off = k * t.out_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.out_col_stride);
         F v = ntt_ld_elem<F>(smem, p.log_r, brev(k, p.log_r), c);
         v = v * ntt_ld_tab<F>(p.store_tab, (t.out_tab_base + off) & p.store_mask);

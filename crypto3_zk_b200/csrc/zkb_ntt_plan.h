@@ -66,10 +66,14 @@ struct NttTables {
 inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttTables &tb, const void *in,
                                                    void *out, void *work, uint32_t batch,
                                                    uint64_t in_poly_stride, uint64_t out_poly_stride,
-                                                   uint64_t in_valid_elems) {
+                                                   uint64_t in_valid_elems, const void *known_src = nullptr,
+                                                   int known_log = 0, uint64_t known_poly_stride = 0) {
     std::vector<NttPassParams> v;
     const uint64_t N = 1ull << pl.log_n;
     const int p = pl.n_passes;
+    // known outputs (see NttPassParams::known_log): multi-pass plans whose first radix covers the period, a whole
+    // number of periods per column block of the last pass, and no post-scale on the last pass
+    if (!(known_src && p >= 2 && known_log >= 3 && known_log <= pl.lr[0] && tb.store_tab == nullptr)) known_log = 0;
     for (int i = 0; i < p; i++) {
         NttPassParams q;
         q.batch = batch;
@@ -82,6 +86,8 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
         q.store_tab = nullptr; q.store_mask = 0;
         q.in_valid_elems = N;
         q.zero_levels = 0;
+        q.known_log = known_log; q.known_k1_shift = 0;
+        q.known_src = (const u128 *)known_src; q.known_poly_stride = known_poly_stride;
         q.log_m = 0; q.log_mprev = 0;
         if (p == 1) {
             q.mode = NTT_MODE_SINGLE;
@@ -97,6 +103,10 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
             q.log_m = pl.log_m(i + 1);
             q.log_mprev = pl.log_m(i);
             q.tiles_per_poly = N >> (q.log_r + 3);   // / (R * C), C = 8
+            if (i >= 1 && known_log > 0) {           // the tiles of k_1 = 0 mod 2^known_log drop out of the grid
+                q.known_k1_shift = (pl.log_n - q.log_mprev) - pl.lr[0];
+                q.tiles_per_poly -= q.tiles_per_poly >> known_log;
+            }
             if (i == 0) {
                 q.in = (const u128 *)in; q.in_poly_stride = in_poly_stride;
                 q.in_valid_elems = in_valid_elems;

@@ -110,6 +110,26 @@ def test_zero_padded_coset_input(libs, maxlogr, log_in, log_out):
         assert got[b] == oracle(F, log_out, a, shift=F.g)
 
 
+@pytest.mark.parametrize("maxlogr,log_in,log_out", [(8, 7, 10), (8, 6, 10), (8, 9, 12), (4, 6, 10), (4, 6, 9), (4, 8, 12),
+                                                     (3, 6, 9), (3, 3, 9), (8, 5, 7), (8, 3, 6), (4, 9, 13)])
+def test_lde_with_known_outputs(libs, maxlogr, log_in, log_out):
+    """lde_device as the runtime drives it (iNTT, then the zero-padded forward transform that takes the outputs at
+    multiples of the blow-up from the input evaluations) against polynomial_dfs::resize; 2/3/4-pass plans, blow-ups
+    4..64 (below 8 the known-output path is off), with the work buffer poisoned."""
+    F = fields.NTT_FIELDS[(log_in + log_out) % 4]
+    lib = libs[maxlogr]
+    batch = 3
+    polys = [fields.random_elements(F, 1 << log_in, 50 + b) for b in range(batch)]
+    a = fields.ints_to_u32_array([v for p in polys for v in p], 8)
+    out = np.zeros((batch << log_out, 8), dtype=np.uint32)
+    rc = lib.zkb_host_lde(F.fid, log_in, log_out, batch, a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    vals = fields.u32_array_to_ints(out)
+    n = 1 << log_out
+    for b in range(batch):
+        assert vals[b * n:(b + 1) * n] == ntt.dfs_resize(polys[b], F, n)
+
+
 def test_ragged_batch(libs):
     F = fields.BN254_FR
     polys = [fields.random_elements(F, 16, b) for b in range(11)]   # 11 = 8 + 3 columns
