@@ -33,6 +33,13 @@ def main():
     elif mode == "lpc":
         x = rand((16, 1 << 20, 8), 1)
         fn = lambda: ctx.lpc_commit("pallas_fq", int(sys.argv[2]) if len(sys.argv) > 2 else 0, x, 20, 23, 1)
+    elif mode == "evalpm":     # query-phase openings: 31 polynomials of 2^20 coefficients at 40 (z, -z) pairs
+        x = rand((31, 1 << 20, 8), 5)
+        pts = [pow(7, 3 * i + 1, (1 << 61) - 1) for i in range(40)]
+        fn = lambda: ctx.poly_evaluate_pm("pallas_fp", x, 1 << 20, pts)
+    elif mode == "grind":
+        st = bytes(range(32))
+        fn = lambda: ctx.pow_grind(0, st, (1 << 24) - 1)
     elif mode == "msm":
         log_m = int(sys.argv[2]) if len(sys.argv) > 2 else 20
         C = CURVE_BY_NAME["bls12_381_g1"]
