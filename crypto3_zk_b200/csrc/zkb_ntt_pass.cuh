@@ -111,8 +111,11 @@ ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
         t.ncols = left < C ? (uint32_t)left : C;
         return t;
     }
-    uint64_t poly = tile / p.tiles_per_poly;
-    uint64_t tt = tile % p.tiles_per_poly;
+    // polynomial-minor order: the CTAs in flight at any time work on the same tile position of different polynomials, so
+    // the slice of the N-entry inter-pass (or coset) table they share is read from DRAM once and then served by the L2
+    // (polynomial-major order re-read the 268 MB table of a 2^23 transform for every polynomial)
+    uint64_t poly = tile % p.batch;
+    uint64_t tt = tile / p.batch;
     t.ncols = C;
     t.poly = poly;
     if (p.mode == NTT_MODE_STRIDED) {
