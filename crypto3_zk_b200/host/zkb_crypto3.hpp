@@ -608,6 +608,207 @@ public:
         for (std::size_t i = 0; i < depth; i++) p[i].assign(raw.begin() + i * db, raw.begin() + (i + 1) * db);
         return p;
     }
+    // the lambda paths of a FRI query phase (basic_fri.hpp:846-862) with one device gather
+    std::vector<std::vector<std::vector<std::uint8_t>>> paths(const std::vector<std::uint64_t> &idx) const {
+        std::size_t depth = 0, db = (std::size_t)zkb_merkle_digest_bytes(HashId);
+        for (std::size_t n = leaves(); n > 1; n >>= 1) depth++;
+        std::vector<std::uint8_t> raw(idx.size() * depth * db + 1);
+        zkb_ctx *ctx = zkb_detail::context();
+        zkb_detail::check(zkb_merkle_paths(ctx, h, (std::uint32_t)idx.size(), idx.data(), raw.data(), nullptr), ctx, "zkb_merkle_paths");
+        std::vector<std::vector<std::vector<std::uint8_t>>> out(idx.size(), std::vector<std::vector<std::uint8_t>>(depth));
+        for (std::size_t q = 0; q < idx.size(); q++)
+            for (std::size_t i = 0; i < depth; i++)
+                out[q][i].assign(raw.begin() + (q * depth + i) * db, raw.begin() + (q * depth + i + 1) * db);
+        return out;
+    }
+};
+}  // namespace commitments
+
+}  // namespace zk
+
+// ========================================================================================== hashes (host side of the transcript)
+// The transcript stays on the host, as in the reference: a few hundred bytes per proof.  Tag types carry the ABI hash id so
+// that the same tag selects the device Merkle hash (zkb_lpc_commit) and the device grinding kernel (zkb_pow_grind).
+namespace hashes {
+namespace zkb_detail_hash {
+inline std::uint64_t rol(std::uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+inline void keccak_f(std::uint64_t a[25]) {
+    static const std::uint64_t RC[24] = {
+        0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808Aull, 0x8000000080008000ull, 0x000000000000808Bull,
+        0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008Aull, 0x0000000000000088ull,
+        0x0000000080008009ull, 0x000000008000000Aull, 0x000000008000808Bull, 0x800000000000008Bull, 0x8000000000008089ull,
+        0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800Aull, 0x800000008000000Aull,
+        0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+    static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    for (int r = 0; r < 24; r++) {
+        std::uint64_t c[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; x++) {
+            std::uint64_t d = c[(x + 4) % 5] ^ rol(c[(x + 1) % 5], 1);
+            for (int y = 0; y < 5; y++) a[x + 5 * y] ^= d;
+        }
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol(a[x + 5 * y], ROT[x + 5 * y]);
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        a[0] ^= RC[r];
+    }
+}
+// original Keccak padding (0x01 .. 0x80), as crypto3-hash keccak_1600
+inline std::vector<std::uint8_t> keccak(const std::uint8_t *data, std::size_t n, std::size_t digest_bytes) {
+    const std::size_t rate = 200 - 2 * digest_bytes;
+    std::uint64_t a[25] = {0};
+    std::vector<std::uint8_t> m(data, data + n);
+    m.push_back(0x01);
+    while (m.size() % rate) m.push_back(0);
+    m.back() |= 0x80;
+    for (std::size_t off = 0; off < m.size(); off += rate) {
+        for (std::size_t i = 0; i < rate; i++) a[i / 8] ^= (std::uint64_t)m[off + i] << (8 * (i % 8));
+        keccak_f(a);
+    }
+    std::vector<std::uint8_t> out(digest_bytes);
+    for (std::size_t i = 0; i < digest_bytes; i++) out[i] = (std::uint8_t)(a[i / 8] >> (8 * (i % 8)));
+    return out;
+}
+inline std::uint32_t ror(std::uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+inline std::vector<std::uint8_t> sha256(const std::uint8_t *data, std::size_t n) {
+    static const std::uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+        0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+        0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+        0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+        0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+        0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    std::uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    std::vector<std::uint8_t> m(data, data + n);
+    m.push_back(0x80);
+    while (m.size() % 64 != 56) m.push_back(0);
+    for (int i = 7; i >= 0; i--) m.push_back((std::uint8_t)(((std::uint64_t)n * 8) >> (8 * i)));
+    for (std::size_t off = 0; off < m.size(); off += 64) {
+        std::uint32_t w[64];
+        for (int i = 0; i < 16; i++)
+            w[i] = ((std::uint32_t)m[off + 4 * i] << 24) | ((std::uint32_t)m[off + 4 * i + 1] << 16) | ((std::uint32_t)m[off + 4 * i + 2] << 8) | m[off + 4 * i + 3];
+        for (int i = 16; i < 64; i++)
+            w[i] = w[i - 16] + (ror(w[i - 15], 7) ^ ror(w[i - 15], 18) ^ (w[i - 15] >> 3)) + w[i - 7] + (ror(w[i - 2], 17) ^ ror(w[i - 2], 19) ^ (w[i - 2] >> 10));
+        std::uint32_t v[8];
+        for (int i = 0; i < 8; i++) v[i] = h[i];
+        for (int i = 0; i < 64; i++) {
+            std::uint32_t t1 = v[7] + (ror(v[4], 6) ^ ror(v[4], 11) ^ ror(v[4], 25)) + ((v[4] & v[5]) ^ (~v[4] & v[6])) + K[i] + w[i];
+            std::uint32_t t2 = (ror(v[0], 2) ^ ror(v[0], 13) ^ ror(v[0], 22)) + ((v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]));
+            for (int k = 7; k > 0; k--) v[k] = v[k - 1];
+            v[4] += t1;
+            v[0] = t1 + t2;
+        }
+        for (int i = 0; i < 8; i++) h[i] += v[i];
+    }
+    std::vector<std::uint8_t> out(32);
+    for (int i = 0; i < 8; i++)
+        for (int b = 0; b < 4; b++) out[4 * i + b] = (std::uint8_t)(h[i] >> (24 - 8 * b));
+    return out;
+}
+}  // namespace zkb_detail_hash
+
+template <std::size_t Bits> struct keccak_1600;
+template <> struct keccak_1600<256> {
+    static constexpr int hash_id = ZKB_HASH_KECCAK_256;
+    static constexpr std::size_t digest_bytes = 32;
+    static std::vector<std::uint8_t> hash(const std::uint8_t *d, std::size_t n) { return zkb_detail_hash::keccak(d, n, 32); }
+};
+template <> struct keccak_1600<512> {
+    static constexpr int hash_id = ZKB_HASH_KECCAK_512;
+    static constexpr std::size_t digest_bytes = 64;
+    static std::vector<std::uint8_t> hash(const std::uint8_t *d, std::size_t n) { return zkb_detail_hash::keccak(d, n, 64); }
+};
+template <std::size_t Bits> struct sha2;
+template <> struct sha2<256> {
+    static constexpr int hash_id = ZKB_HASH_SHA2_256;
+    static constexpr std::size_t digest_bytes = 32;
+    static std::vector<std::uint8_t> hash(const std::uint8_t *d, std::size_t n) { return zkb_detail_hash::sha256(d, n); }
+};
+}  // namespace hashes
+
+namespace zk {
+namespace transcript {
+// fiat_shamir_heuristic_sequential<Hash> (zk/transcript/fiat_shamir.hpp:131-199): state = H(init); absorbing is
+// state = H(state || data); challenge<Field>() is state = H(state) read as a big-endian integer into the field;
+// int_challenge<Integral>() the low bits of the same.  Known answers: test/transcript/transcript.cpp:50-64.
+template <class Hash>
+class fiat_shamir_heuristic_sequential {
+    std::vector<std::uint8_t> _state;
+
+public:
+    typedef Hash hash_type;
+    fiat_shamir_heuristic_sequential() {
+        const std::uint8_t zero = 0;
+        _state = Hash::hash(&zero, 1);
+    }
+    template <class Range>
+    explicit fiat_shamir_heuristic_sequential(const Range &r) {
+        std::vector<std::uint8_t> d(r.begin(), r.end());
+        _state = Hash::hash(d.data(), d.size());
+    }
+    const std::vector<std::uint8_t> &state() const { return _state; }
+    template <class Range>
+    void operator()(const Range &r) {
+        std::vector<std::uint8_t> d(_state);
+        d.insert(d.end(), r.begin(), r.end());
+        _state = Hash::hash(d.data(), d.size());
+    }
+    template <class FieldType>
+    typename FieldType::value_type challenge() {
+        typedef typename FieldType::backend B;
+        _state = Hash::hash(_state.data(), _state.size());
+        // big-endian digest = sum_k chunk_k 2^(256 k), chunk_0 the last 32 bytes; Montgomery products accept any 256-bit input
+        typename FieldType::value_type acc, radix = FieldType::value_type::one(), scale = FieldType::value_type::one();
+        const typename FieldType::value_type two32(std::uint64_t(1) << 32);
+        for (int i = 0; i < 8; i++) radix *= two32;   // 2^256 mod p
+        for (std::size_t off = _state.size(); off > 0; off -= 32) {
+            std::uint32_t l[FieldType::limbs32] = {0};
+            for (int i = 0; i < 32; i++) l[i / 4] |= (std::uint32_t)_state[off - 1 - i] << (8 * (i % 4));
+            typename FieldType::value_type chunk;
+            chunk.data = B::from_limbs32(l).to_mont();
+            acc += chunk * scale;
+            scale *= radix;
+        }
+        return acc;
+    }
+    template <class Integral>
+    Integral int_challenge() {
+        _state = Hash::hash(_state.data(), _state.size());
+        Integral v = 0;
+        for (std::size_t i = _state.size() - sizeof(Integral); i < _state.size(); i++) v = (Integral)((v << 8) | _state[i]);
+        return v;
+    }
+};
+}  // namespace transcript
+
+namespace commitments {
+// proof_of_work<TranscriptHashType, std::uint32_t> (zk/commitments/detail/polynomial/proof_of_work.hpp:40-82): the search
+// runs on the device (zkb_pow_grind, one nonce per thread) from nonce 0 instead of std::rand(); verify is the reference's.
+template <class TranscriptHashType, class OutType = std::uint32_t>
+class proof_of_work {
+public:
+    typedef TranscriptHashType transcript_hash_type;
+    typedef transcript::fiat_shamir_heuristic_sequential<transcript_hash_type> transcript_type;
+    typedef OutType output_type;
+    static std::vector<std::uint8_t> be32(output_type v) {
+        return {std::uint8_t(v >> 24), std::uint8_t(v >> 16), std::uint8_t(v >> 8), std::uint8_t(v)};
+    }
+    static output_type generate(transcript_type &transcript, OutType mask = 0xFFFF) {
+        zkb_ctx *ctx = zkb_detail::context();
+        std::uint32_t nonce = 0;
+        zkb_detail::check(zkb_pow_grind(ctx, TranscriptHashType::hash_id, transcript.state().data(), 0, (std::uint32_t)mask, &nonce, nullptr),
+                          ctx, "zkb_pow_grind");
+        transcript(be32(nonce));
+        (void)transcript.template int_challenge<output_type>();
+        return (output_type)nonce;
+    }
+    static bool verify(transcript_type &transcript, output_type proof_of_work, OutType mask = 0xFFFF) {
+        transcript(be32(proof_of_work));
+        output_type result = transcript.template int_challenge<output_type>();
+        return (result & mask) == 0;
+    }
 };
 }  // namespace commitments
 

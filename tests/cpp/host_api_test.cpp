@@ -186,10 +186,57 @@ static void precommit_root() {
     CHECK(tree.path(3).size() == 4);
 }
 
+// fiat_shamir_heuristic_sequential known answers (test/transcript/transcript.cpp:50-64: keccak-256 over bytes 0..9, BN254 Fr)
+// and proof_of_work generate / verify (proof_of_work.hpp:47-81) with the device search.
+static void transcript_and_grinding_test(bool with_gpu) {
+    typedef algebra::fields::alt_bn128_fr<254> field_type;
+    typedef hashes::keccak_1600<256> hash_type;
+    std::vector<std::uint8_t> init = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9};
+    zk::transcript::fiat_shamir_heuristic_sequential<hash_type> tr(init);
+    static const char *want[3] = {"00e858ba005424eabd6d97de7e930779def59a85c1a9ff7e8a5d001cdb07f6e4",
+                                  "0f61f38f58a55b3bbee0480fc5ec3cf8df81603579f4f7134f764bfd3ca5938b",
+                                  "04f6b97a9bc99d6996fab5e03d1cd0b418a9b3c97ed64cca070e15777e7cc99a"};
+    for (int k = 0; k < 3; k++) {
+        auto c = tr.challenge<field_type>();
+        std::uint32_t l[8];
+        c.to_canonical_limbs(l);
+        char hex[65];
+        for (int i = 0; i < 8; i++) std::snprintf(hex + 8 * i, 9, "%08x", l[7 - i]);
+        CHECK(std::string(hex) == want[k]);
+    }
+    // sha-256 and keccak-512 states have the right sizes and differ
+    zk::transcript::fiat_shamir_heuristic_sequential<hashes::sha2<256>> ts(init);
+    zk::transcript::fiat_shamir_heuristic_sequential<hashes::keccak_1600<512>> tk(init);
+    CHECK(ts.state().size() == 32 && tk.state().size() == 64);
+    std::vector<std::uint8_t> abc = {'a', 'b', 'c'};
+    auto d = hashes::sha2<256>::hash(abc.data(), 3);
+    CHECK(d[0] == 0xba && d[1] == 0x78 && d[31] == 0xad);   // FIPS 180-2 "abc"
+    if (!with_gpu) return;
+    typedef zk::commitments::proof_of_work<hash_type> pow_type;
+    auto prover = tr, verifier = tr;
+    std::uint32_t nonce = pow_type::generate(prover, 0xFFF);
+    CHECK(pow_type::verify(verifier, nonce, 0xFFF));
+    CHECK(prover.state() == verifier.state());
+    // minimality: no smaller nonce passes (host walk, <= 4096 expected trials)
+    for (std::uint32_t cand = 0; cand < nonce; cand++) {
+        auto t = tr;
+        if (pow_type::verify(t, cand, 0xFFF)) { CHECK(false); break; }
+    }
+    typedef zk::commitments::proof_of_work<hashes::sha2<256>> pow_sha;
+    auto ps = ts, vs = ts;
+    std::uint32_t n2 = pow_sha::generate(ps, 0xFF);
+    CHECK(pow_sha::verify(vs, n2, 0xFF));
+    typedef zk::commitments::proof_of_work<hashes::keccak_1600<512>> pow_k512;
+    auto pk = tk, vk = tk;
+    std::uint32_t n3 = pow_k512::generate(pk, 0xFF);
+    CHECK(pow_k512::verify(vk, n3, 0xFF));
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !std::strcmp(argv[1], "compile-only")) {
-        std::printf("compiled\n");
-        return 0;
+        transcript_and_grinding_test(false);   // host-only part: transcript known answers
+        std::printf(failures ? "FAILED %d checks\n" : "compiled\n", failures);
+        return failures ? 1 : 0;
     }
     try {
         kzg_basic_test<algebra::curves::bls12<381>>();
@@ -203,6 +250,7 @@ int main(int argc, char **argv) {
         domain_and_fold_test<algebra::fields::alt_bn128_fr<254>>();
         domain_and_fold_test<algebra::fields::pallas_base_field>();
         domain_and_fold_test<algebra::fields::pallas_scalar_field>();
+        transcript_and_grinding_test(true);
         precommit_root();
     } catch (const std::exception &e) {
         std::printf("EXCEPTION %s\n", e.what());
