@@ -164,13 +164,17 @@ def pow_verify(transcript, pow_, mask=0xFFFF):
 
 # ------------------------------------------------------------------------------------------------ prover
 def _domain_index(D, x):
-    """the reference's linear search for x in D (basic_fri.hpp:780-786)"""
-    w, acc = D.omega, 1
-    for i in range(D.m):
-        if acc == x:
-            return i
-        acc = acc * w % D.field.p
-    raise ValueError("x is not in the domain")
+    """index of x in D.  The reference searches linearly (basic_fri.hpp:780-786); same result bit by bit for the
+    2^k-th roots of unity: bit i of the exponent is set iff (x w^-e)^(2^(k-1-i)) != 1 for the bits e found so far."""
+    p, k = D.field.p, D.log_m
+    w_inv = D.omega_inv
+    e = 0
+    for i in range(k):
+        if pow(x * pow(w_inv, e, p) % p, 1 << (k - 1 - i), p) != 1:
+            e |= 1 << i
+    if pow(D.omega, e, p) != x % p:
+        raise ValueError("x is not in the domain")
+    return e
 
 
 def fri_proof_eval(g, combined_Q, precommitments, params, transcript, h):

@@ -328,6 +328,68 @@ def test_lpc_full_proof_vs_oracle(ctx, F, hid, steps, degree_log, expand, grind,
     assert not fri_query.lpc_verify_eval(bad, points, commitments, params, tr.copy(), h, (0,), etha, fixed_values)
 
 
+def test_lpc_full_size_proof_verifies(ctx):
+    """BASELINE configs[4] size: 2^20-row Pallas columns, blow-up 8, 19 FRI rounds of step 1 (fri_params(1, 20, lambda, 3),
+    test/systems/plonk/placeholder/placeholder.cpp:231), keccak-256.  The complete lpc proof of the device path is
+    accepted by the oracle verifier (basic_fri.hpp:932-1150 / lpc.hpp:202-263), which never sees the polynomials, and
+    rejected after one opened value changes.  lambda and the column counts are kept small only because the verifier's
+    Keccak is pure Python."""
+    import torch
+    from crypto3_zk_b200.lpc import FriParams, LpcCommitmentScheme
+    from crypto3_zk_b200.transcript import FiatShamirSequential
+    from oracle import fri_query
+    F, h, hid, lam, degree_log, expand = fields.PALLAS_FP, hashes.keccak256, 0, 6, 20, 3
+    n, p = 1 << degree_log, fields.PALLAS_FP.p
+    counts = {0: 5, 1: 4, 2: 1, 3: 2}
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cols = {}
+    for k, cnt in counts.items():
+        x = torch.randint(-2**31, 2**31 - 1, (cnt, n, 8), dtype=torch.int32, device="cuda", generator=g)
+        x[..., 7] &= 0x0FFFFFFF
+        cols[k] = x
+    fri = FriParams.with_max_step_one(degree_log, lam, expand, use_grinding=True, grinding_parameter=0xFFFF)
+    scheme = LpcCommitmentScheme(ctx, F.name, hid, fri)
+    tr = FiatShamirSequential(hid, b"full-size")
+    for k in counts:
+        scheme.append_to_batch(k, cols[k])
+    scheme.mark_batch_as_fixed(0)
+    scheme.commit(0)
+    scheme.setup(tr, None)
+    commitments = {0: scheme._trees[0].root()}
+    for k in (1, 2, 3):
+        commitments[k] = scheme.commit(k)
+    y = 0x1234567890abcdef1234567890abcdef % p
+    yw = y * F.omega(degree_log) % p
+    for k in counts:
+        scheme.append_eval_point(k, y)
+    for k in (1, 2):
+        scheme.append_eval_point(k, yw)
+    co = ctx.ntt(F.name, cols[0].clone(), degree_log, inverse=True)
+    scheme._fixed_values = {0: [v[0] for v in ctx.poly_evaluate(F.name, co, n, [scheme._etha])]}
+    etha, fixed_values = scheme._etha, scheme._fixed_values
+    t_prover = FiatShamirSequential(hid, b"full-size")
+    t_prover.state = tr.state
+    res = scheme.proof_eval(t_prover, query=True)
+    proof = res["proof"]
+    assert all(r == 0 for r in res["remainders"])
+    assert len(proof["fri_proof"]["query_proofs"]) == lam and len(proof["fri_proof"]["fri_roots"]) == degree_log - 1
+    points = {k: [list(pts) for pts in scheme._points[k]] for k in counts}
+    params = fri_query.FriParams(F, fri.step_list, degree_log, lam, expand, True, 0xFFFF)
+
+    def verifier_transcript():
+        t = hashes.FiatShamirSequential(h, b"full-size")
+        t.state = tr.state
+        return t
+
+    tv = verifier_transcript()
+    assert fri_query.lpc_verify_eval(proof, points, commitments, params, tv, h, (0,), etha, fixed_values)
+    assert tv.state == t_prover.state
+    q0 = proof["fri_proof"]["query_proofs"][0]
+    v = q0["initial_proof"][1]["values"][2][0]
+    v[1] = (v[1] + 1) % p
+    assert not fri_query.lpc_verify_eval(proof, points, commitments, params, verifier_transcript(), h, (0,), etha, fixed_values)
+
+
 # ------------------------------------------------------------------------------------------ Groth16 (config #4)
 @pytest.mark.parametrize("F", [fields.BN254_FR, fields.BLS12_381_FR], ids=lambda f: f.name)
 def test_sparse_matvec_vs_oracle(ctx, F):
