@@ -115,7 +115,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times) * args.batch / sample_polys, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit prime field, exact)", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference cannot be compiled here (Boost + un-vendored crypto3 libs): timed code is oracle/c, a C port of its CPU algorithm; ms_per_step extrapolated from the sample to the full batch",
@@ -662,6 +662,30 @@ def main():
                         "traffic": traffic, "peak_source": peak_src, "kernel": "ntt_pass_kernel<PallasFq>",
                         "algorithmic_bytes_per_launch": per_launch, "launches_per_step": launches / args.steps,
                         "avg_launch_ms": ms_per_step / max(launches / args.steps, 1)}
+    # the co-limiter SURVEY 8(d) asks for next to the HBM figure: modular products per step against the measured peak of
+    # this field's multiplier.  Products per polynomial: inverse transform = butterflies log_in/2 per
+    # element + one inter-pass twiddle per pass boundary; forward transform = the same on 2^log_out elements minus the
+    # zero levels of pass 1 (half a product per element and level) and minus the known outputs in the middle passes.
+    try:
+        from crypto3_zk_b200.csrc_plan import ntt_radices
+        lr_in, lr_out = ntt_radices(args.log_in), ntt_radices(args.log_out)
+        z = args.log_out - args.log_in
+        known = z >= 3 and len(lr_out) >= 2 and z <= lr_out[0]
+        prod = n_in * (args.log_in / 2.0 + len(lr_in) - 1)
+        fwd = 0.0
+        for i, r in enumerate(lr_out):
+            per = r / 2.0 + (1 if i + 1 < len(lr_out) else 0)
+            if i == 0:
+                per -= min(z, r) / 2.0
+            frac = (1 - 2.0 ** -z) if (known and 0 < i < len(lr_out) - 1) else 1.0
+            fwd += per * frac
+        prod += n_out * fwd
+        peak_mul = ctx.bench_field_mul("pallas_fq", 148 * 8, 256, 2048)
+        line["roofline"]["int_pipe"] = {"field_mul_per_step": prod * args.batch, "field_mul_per_s": prod * args.batch / (ms_per_step * 1e-3),
+                                        "peak_field_mul_per_s": peak_mul, "frac": prod * args.batch / (ms_per_step * 1e-3) / peak_mul,
+                                        "note": "Pallas Fq Montgomery products (88 IMAD.WIDE each); peak = zkb_bench_field_mul on this GPU"}
+    except Exception as e:
+        line["roofline"]["int_pipe"] = {"error": repr(e)}
 
     if rank == 0 and world == 1:
         if not args.no_cpu:
