@@ -291,3 +291,76 @@ extern "C" int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uin
     cudaSetDevice(ctx->device);
     ZKB_DISPATCH_ANY_FIELD(field, bench_field_mul, ctx, blocks, threads, iters, muls_per_s)
 }
+
+// ------------------------------------------------------------------------------------ device buffers for host templates
+// The reference's commitment scheme keeps its polynomials as members between commit / eval_polys / proof_eval
+// (zk/commitments/polynomial/lpc.hpp:66-200, batched_commitment.hpp:60-250); a host template over this ABI keeps them in
+// device buffers instead.  Plain cudaMalloc / cudaMemcpyAsync / cudaMemsetAsync behind status codes, plus a gather of
+// 32-byte elements (the FRI query phase reads 2 lambda values of every retained f_i, basic_fri.hpp:880-887).
+__global__ void __launch_bounds__(256) gather_elems_kernel(const uint4 *__restrict__ src, uint32_t count,
+                                                           const uint64_t *__restrict__ idx, uint4 *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * count) return;
+    out[i] = src[2 * idx[i >> 1] + (i & 1)];
+}
+
+extern "C" {
+
+int zkb_buf_alloc(zkb_ctx *ctx, uint64_t bytes, void **out) {
+    if (!ctx || !out) return ZKB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return zkb::ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, std::string("zkb_buf_alloc: ") + cudaGetErrorString(e));
+    }
+    return ZKB_OK;
+}
+
+void zkb_buf_free(zkb_ctx *ctx, void *p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+
+int zkb_buf_copy(zkb_ctx *ctx, void *dst, int dst_mem, const void *src, int src_mem, uint64_t bytes, void *stream) {
+    if (!ctx || (bytes && (!dst || !src))) return ZKB_ERR_INVALID_ARGUMENT;
+    if (bytes == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemcpyKind kind = dst_mem == ZKB_MEM_DEVICE ? (src_mem == ZKB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                                    : (src_mem == ZKB_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, bytes, kind, st));
+    if (kind != cudaMemcpyDeviceToDevice) ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));   // host buffers are the caller's again
+    return ZKB_OK;
+}
+
+int zkb_buf_zero(zkb_ctx *ctx, void *dev, uint64_t bytes, void *stream) {
+    if (!ctx || (bytes && !dev)) return ZKB_ERR_INVALID_ARGUMENT;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    ZKB_CUDA_OK(ctx, cudaMemsetAsync(dev, 0, bytes, (cudaStream_t)stream));
+    return ZKB_OK;
+}
+
+int zkb_gather(zkb_ctx *ctx, const void *src_device, uint32_t count, const uint64_t *indices, uint32_t *out, void *stream) {
+    if (!ctx || (count && (!src_device || !indices || !out))) return ZKB_ERR_INVALID_ARGUMENT;
+    if (count == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    void *p;
+    const size_t idx_pad = ((size_t)count * 8 + 15) & ~(size_t)15;
+    ZKB_TRY(zkb::ctx_scratch(ctx, "gather", idx_pad + (size_t)count * 32, &p));
+    uint64_t *d_idx = (uint64_t *)p;
+    uint4 *d_out = (uint4 *)((char *)p + idx_pad);
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d_idx, indices, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+    gather_elems_kernel<<<(2 * count + 255) / 256, 256, 0, st>>>((const uint4 *)src_device, count, d_idx, d_out);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    ZKB_CUDA_OK(ctx, cudaMemcpyAsync(out, d_out, (size_t)count * 32, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return ZKB_OK;
+}
+
+}  // extern "C"

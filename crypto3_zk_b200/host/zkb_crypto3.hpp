@@ -23,6 +23,9 @@
 #include <cstdint>
 #include <cstring>
 #include <iterator>
+#include <map>
+#include <array>
+#include <algorithm>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -107,7 +110,36 @@ struct zkb_field {
             }
             return r;
         }
+        // this^e, e given as little-endian 32-bit limbs
+        value_type pow_limbs(const std::uint32_t *e, int n) const {
+            value_type r = one();
+            for (int i = n - 1; i >= 0; i--)
+                for (int b = 31; b >= 0; b--) {
+                    r *= r;
+                    if ((e[i] >> b) & 1) r *= *this;
+                }
+            return r;
+        }
+        bool operator<(const value_type &o) const {   // canonical integer order (std::map / std::find keys)
+            std::uint32_t a[limbs32], b[limbs32];
+            to_canonical_limbs(a);
+            o.to_canonical_limbs(b);
+            for (int i = limbs32 - 1; i >= 0; i--)
+                if (a[i] != b[i]) return a[i] < b[i];
+            return false;
+        }
     };
+    // (p - 1) >> k as limbs
+    static void modulus_minus_one_shifted(int k, std::uint32_t *out) {
+        std::uint32_t m[limbs32];
+        for (int i = 0; i < limbs32; i++) m[i] = Params::mod(i);
+        m[0] -= 1;   // p is odd
+        for (int i = 0; i < limbs32; i++) {
+            int src = i + k / 32, sh = k % 32;
+            std::uint64_t lo = src < limbs32 ? m[src] : 0, hi = src + 1 < limbs32 ? m[src + 1] : 0;
+            out[i] = (std::uint32_t)(sh ? ((lo >> sh) | (hi << (32 - sh))) : lo);
+        }
+    }
 };
 
 template <std::size_t> struct bls12_fr;
@@ -808,6 +840,453 @@ public:
         transcript(be32(proof_of_work));
         output_type result = transcript.template int_challenge<output_type>();
         return (result & mask) == 0;
+    }
+};
+}  // namespace commitments
+
+// ------------------------------------------------------------------------------------------ lpc_commitment_scheme
+namespace zkb_detail_lpc {
+// RAII device buffer over zkb_buf_alloc / zkb_buf_free
+struct device_buffer {
+    void *p = nullptr;
+    std::size_t bytes = 0;
+    device_buffer() = default;
+    explicit device_buffer(std::size_t n) : bytes(n) {
+        zkb_ctx *ctx = zkb_detail::context();
+        zkb_detail::check(zkb_buf_alloc(ctx, n, &p), ctx, "zkb_buf_alloc");
+    }
+    device_buffer(const device_buffer &) = delete;
+    device_buffer &operator=(const device_buffer &) = delete;
+    device_buffer(device_buffer &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; }
+    device_buffer &operator=(device_buffer &&o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; }
+        return *this;
+    }
+    void release() { if (p) zkb_buf_free(zkb_detail::context(), p); p = nullptr; }
+    ~device_buffer() { release(); }
+};
+}  // namespace zkb_detail_lpc
+
+namespace commitments {
+// basic_batched_fri::params_type (basic_fri.hpp:151-229): the fields the prover reads
+struct fri_params_type {
+    std::vector<std::size_t> step_list;
+    std::size_t degree_log = 0, lambda = 40, expand_factor = 2;
+    bool use_grinding = false;
+    std::uint32_t grinding_parameter = 0xFFFF;
+    std::size_t log_d0() const { return degree_log + expand_factor; }
+    std::size_t r() const { std::size_t s = 0; for (auto v : step_list) s += v; return s; }
+    // params_type(max_step = 1, degree_log, lambda, expand_factor) (basic_fri.hpp:150-166): degree_log - 1 steps of 1
+    static fri_params_type with_max_step_one(std::size_t degree_log, std::size_t lambda, std::size_t expand_factor,
+                                             bool use_grinding = false, std::uint32_t grinding_parameter = 0xFFFF) {
+        fri_params_type q;
+        q.step_list.assign(degree_log - 1, 1);
+        q.degree_log = degree_log; q.lambda = lambda; q.expand_factor = expand_factor;
+        q.use_grinding = use_grinding; q.grinding_parameter = grinding_parameter;
+        return q;
+    }
+};
+
+// lpc_commitment_scheme (zk/commitments/polynomial/lpc.hpp:66-200) over its base polys_evaluator
+// (zk/commitments/batched_commitment.hpp:60-250), with zk::algorithms::proof_eval<FRI> (basic_fri.hpp:670-923) behind
+// proof_eval(): commit phase, grinding and query phase.  Polynomials are polynomial_dfs values; after commit() a batch
+// lives in a device buffer, every per-element operation is one ABI call, the transcript and the proof stay on the host.
+// The same sequence as crypto3_zk_b200/lpc.py (which tests/test_gpu_flows.py checks bit for bit against the oracle).
+template <class FieldType, class MerkleHash, class TranscriptHash>
+class lpc_commitment_scheme {
+public:
+    typedef FieldType field_type;
+    typedef typename FieldType::value_type value_type;
+    typedef math::polynomial_dfs<value_type> poly_type;
+    typedef transcript::fiat_shamir_heuristic_sequential<TranscriptHash> transcript_type;
+    typedef std::vector<std::uint8_t> commitment_type;
+    typedef device_merkle_tree<MerkleHash::hash_id> precommitment_type;
+    struct merkle_proof_type {
+        std::size_t index = 0;
+        std::vector<commitment_type> path;
+        commitment_type root;
+    };
+    typedef std::vector<std::array<value_type, 2>> polynomial_values_type;
+    struct initial_proof_type { std::vector<polynomial_values_type> values; merkle_proof_type p; };
+    struct round_proof_type { polynomial_values_type y; merkle_proof_type p; };
+    struct query_proof_type { std::map<std::size_t, initial_proof_type> initial_proof; std::vector<round_proof_type> round_proofs; };
+    struct fri_proof_type {
+        std::vector<commitment_type> fri_roots;
+        std::vector<value_type> final_polynomial;
+        std::vector<query_proof_type> query_proofs;
+        std::uint32_t proof_of_work = 0;
+    };
+    struct proof_type { std::map<std::size_t, std::vector<std::vector<value_type>>> z; fri_proof_type fri_proof; };
+
+private:
+    typedef zkb_detail_lpc::device_buffer dbuf;
+    static constexpr int fid = FieldType::field_id;
+    fri_params_type _fri;
+    std::map<std::size_t, std::vector<poly_type>> _polys;
+    std::map<std::size_t, std::vector<std::vector<value_type>>> _points;
+    std::map<std::size_t, precommitment_type> _trees;
+    std::map<std::size_t, bool> _fixed, _locked;
+    std::map<std::size_t, dbuf> _dev, _coef;           // evaluations / coefficients of a batch on the device
+    std::map<std::size_t, std::size_t> _n;
+    value_type _etha;
+    std::map<std::size_t, std::vector<value_type>> _fixed_values;
+    std::map<std::size_t, std::vector<std::vector<value_type>>> _z;
+
+    static zkb_ctx *ctx() { return zkb_detail::context(); }
+    static void ck(int st, const char *what) { zkb_detail::check(st, ctx(), what); }
+    static void limbs(const value_type &v, std::uint32_t *l) { v.to_canonical_limbs(l); }
+    static value_type omega(std::size_t log_n) {
+        std::uint32_t l[8];
+        ck(zkb_field_unity_root(fid, (int)log_n, l), "zkb_field_unity_root");
+        return value_type::from_canonical_limbs(l);
+    }
+    // batch k as canonical limbs on the device (leaves hash canonical integers; the transforms are linear anyway)
+    void upload(std::size_t k) {
+        if (_dev.count(k)) return;
+        const auto &ps = _polys.at(k);
+        const std::size_t n = ps[0].size();
+        std::vector<std::uint32_t> buf(ps.size() * n * 8);
+        for (std::size_t i = 0; i < ps.size(); i++) {
+            if (ps[i].size() != n) throw std::invalid_argument("lpc: polynomials of one batch must have the same size");
+            for (std::size_t j = 0; j < n; j++) ps[i][j].to_canonical_limbs(&buf[(i * n + j) * 8]);
+        }
+        dbuf d(buf.size() * 4);
+        ck(zkb_buf_copy(ctx(), d.p, ZKB_MEM_DEVICE, buf.data(), ZKB_MEM_HOST, buf.size() * 4, nullptr), "zkb_buf_copy");
+        _dev[k] = std::move(d);
+        _n[k] = n;
+    }
+    std::vector<value_type> unique_points() const {
+        std::vector<value_type> out;
+        for (const auto &kv : _points)
+            for (const auto &pts : kv.second)
+                for (const auto &x : pts)
+                    if (std::find(out.begin(), out.end(), x) == out.end()) out.push_back(x);
+        return out;
+    }
+    struct cb_state { transcript_type *tr; };
+    static int on_root(void *user, std::uint32_t, const std::uint8_t *root, std::uint32_t root_bytes, std::uint32_t count,
+                       std::uint32_t *alphas_out) {
+        try {
+            cb_state *s = static_cast<cb_state *>(user);
+            (*s->tr)(std::vector<std::uint8_t>(root, root + root_bytes));
+            for (std::uint32_t k = 0; k < count; k++) limbs(s->tr->template challenge<FieldType>(), alphas_out + 8 * k);
+            return 0;
+        } catch (...) {
+            return 1;
+        }
+    }
+    static std::vector<std::pair<std::size_t, std::size_t>> s_indices(std::size_t x_index, std::size_t domain_size, std::size_t fri_step) {
+        // index pairs of calculate_s (basic_fri.hpp:583-617), each ordered (min, max)
+        const std::size_t half = domain_size / 2;
+        std::vector<std::size_t> idx = {x_index};
+        std::size_t base = domain_size / 4, prev = 1;
+        while (idx.size() < (std::size_t(1) << fri_step) / 2) {
+            for (std::size_t j = 0; j < prev; j++) idx.push_back((base + idx[j]) % domain_size);
+            base /= 2;
+            prev <<= 1;
+        }
+        std::vector<std::pair<std::size_t, std::size_t>> out;
+        for (auto a : idx) {
+            std::size_t b = (a + half) % domain_size;
+            out.emplace_back(std::min(a, b), std::max(a, b));
+        }
+        return out;
+    }
+    static std::size_t folded_index(std::size_t x_index, std::size_t domain_size, std::size_t fri_step) {
+        for (std::size_t i = 0; i < fri_step; i++) { domain_size /= 2; x_index %= domain_size; }
+        return x_index;
+    }
+    // index of x in the 2^log_n subgroup (the reference searches linearly, basic_fri.hpp:780-786)
+    static std::size_t domain_index(const value_type &x, std::size_t log_n) {
+        const value_type w_inv = omega(log_n).inversed();
+        std::size_t e = 0;
+        for (std::size_t i = 0; i < log_n; i++) {
+            value_type t = x * w_inv.pow(e);
+            for (std::size_t k = 0; k + 1 + i < log_n; k++) t *= t;
+            if (!t.is_one()) e |= std::size_t(1) << i;
+        }
+        return e;
+    }
+    static value_type horner(const std::vector<value_type> &c, const value_type &x) {
+        value_type r = value_type::zero();
+        for (std::size_t i = c.size(); i-- > 0;) r = r * x + c[i];
+        return r;
+    }
+    static merkle_proof_type make_proof(std::size_t index, std::vector<commitment_type> path, const commitment_type &root) {
+        merkle_proof_type p;
+        p.index = index; p.path = std::move(path); p.root = root;
+        return p;
+    }
+
+public:
+    explicit lpc_commitment_scheme(const fri_params_type &fri_params) : _fri(fri_params) {
+        if (_fri.r() > _fri.log_d0()) throw std::invalid_argument("lpc: sum(step_list) exceeds log2 |D[0]|");
+    }
+    const fri_params_type &get_commitment_params() const { return _fri; }
+
+    // ---- polys_evaluator interface (batched_commitment.hpp:196-250)
+    void append_to_batch(std::size_t index, const poly_type &poly) {
+        if (_locked[index]) throw std::logic_error("lpc: batch is already committed");
+        _polys[index].push_back(poly);
+        _points[index].emplace_back();
+    }
+    template <class Container>
+    void append_to_batch(std::size_t index, const Container &polys) { for (const auto &q : polys) append_to_batch(index, q); }
+    void append_eval_point(std::size_t batch, const value_type &point) { for (auto &pts : _points.at(batch)) pts.push_back(point); }
+    void append_eval_point(std::size_t batch, std::size_t poly, const value_type &point) { _points.at(batch).at(poly).push_back(point); }
+    const std::map<std::size_t, std::vector<std::vector<value_type>>> &get_z() const { return _z; }
+
+    // ---- lpc.hpp:101-111
+    commitment_type commit(std::size_t index) {
+        _locked[index] = true;
+        upload(index);
+        const std::size_t n = _n.at(index);
+        std::vector<std::uint8_t> root(MerkleHash::digest_bytes);
+        zkb_merkle_tree *t = nullptr;
+        ck(zkb_lpc_commit(ctx(), fid, MerkleHash::hash_id, zkb_detail::log2_exact(n), (int)_fri.log_d0(), (int)_fri.step_list.front(),
+                          (std::uint32_t)_polys.at(index).size(), _dev.at(index).p, ZKB_MEM_DEVICE, root.data(), &t, nullptr),
+           "zkb_lpc_commit");
+        _trees.erase(index);
+        _trees.emplace(index, precommitment_type(t, root));
+        return root;
+    }
+    void mark_batch_as_fixed(std::size_t index) { _fixed[index] = true; }
+    // etha from the transcript; the values of the fixed batches at etha are computed here with the same device evaluation
+    void setup(transcript_type &transcript) {
+        _etha = transcript.template challenge<FieldType>();
+        for (const auto &kv : _fixed) {
+            if (!kv.second) continue;
+            const std::size_t k = kv.first;
+            upload(k);
+            const std::size_t n = _n.at(k), cnt = _polys.at(k).size();
+            std::uint32_t pt[8];
+            limbs(_etha, pt);
+            std::vector<std::uint32_t> out(cnt * 8);
+            ck(zkb_poly_evaluate(ctx(), fid, ZKB_POLY_DFS, n, (std::uint32_t)cnt, _dev.at(k).p, ZKB_MEM_DEVICE, 1, pt, out.data(), nullptr),
+               "zkb_poly_evaluate");
+            std::vector<value_type> v(cnt);
+            for (std::size_t i = 0; i < cnt; i++) v[i] = value_type::from_canonical_limbs(&out[8 * i]);
+            _fixed_values[k] = v;
+        }
+    }
+    const value_type &etha() const { return _etha; }
+    const std::map<std::size_t, std::vector<value_type>> &fixed_values() const { return _fixed_values; }
+
+    // ---- eval_polys (batched_commitment.hpp:176-190): one inverse transform per batch, all points of the batch at once
+    void eval_polys() {
+        _z.clear();
+        for (const auto &kv : _polys) {
+            const std::size_t k = kv.first, cnt = kv.second.size();
+            upload(k);
+            const std::size_t n = _n.at(k);
+            dbuf co(cnt * n * 32);
+            ck(zkb_ntt(ctx(), fid, zkb_detail::log2_exact(n), (std::uint32_t)cnt, _dev.at(k).p, co.p, 1, nullptr, ZKB_MEM_DEVICE, nullptr), "zkb_ntt");
+            std::vector<value_type> uni;
+            for (const auto &pts : _points.at(k))
+                for (const auto &x : pts)
+                    if (std::find(uni.begin(), uni.end(), x) == uni.end()) uni.push_back(x);
+            _z[k].assign(cnt, {});
+            if (!uni.empty()) {
+                std::vector<std::uint32_t> pl(uni.size() * 8), out(cnt * uni.size() * 8);
+                for (std::size_t j = 0; j < uni.size(); j++) limbs(uni[j], &pl[8 * j]);
+                ck(zkb_poly_evaluate(ctx(), fid, ZKB_POLY_COEFFICIENTS, n, (std::uint32_t)cnt, co.p, ZKB_MEM_DEVICE, (std::uint32_t)uni.size(),
+                                     pl.data(), out.data(), nullptr), "zkb_poly_evaluate");
+                for (std::size_t i = 0; i < cnt; i++)
+                    for (const auto &x : _points.at(k)[i]) {
+                        std::size_t j = std::find(uni.begin(), uni.end(), x) - uni.begin();
+                        _z[k][i].push_back(value_type::from_canonical_limbs(&out[(i * uni.size() + j) * 8]));
+                    }
+            }
+            _coef[k] = std::move(co);
+        }
+    }
+
+    // ---- proof_eval (lpc.hpp:113-200 -> basic_fri.hpp:670-923)
+    proof_type proof_eval(transcript_type &transcript) {
+        eval_polys();
+        for (const auto &kv : _trees) transcript(kv.second.root());
+        const value_type theta = transcript.template challenge<FieldType>();
+        value_type theta_acc = value_type::one();
+        std::size_t n_max = 0;
+        for (const auto &kv : _n) n_max = std::max(n_max, kv.second);
+        dbuf combined(n_max * 32), numer(n_max * 32), quot(n_max * 32);
+        ck(zkb_buf_zero(ctx(), combined.p, n_max * 32, nullptr), "zkb_buf_zero");
+        struct term { std::size_t k; std::vector<std::uint32_t> scalars; value_type constant; };
+        auto add_quotient = [&](const value_type &point, const std::vector<term> &terms) {
+            ck(zkb_buf_zero(ctx(), numer.p, n_max * 32, nullptr), "zkb_buf_zero");
+            for (const auto &t : terms) {
+                std::uint32_t c[8];
+                limbs(t.constant, c);
+                ck(zkb_poly_lincomb(ctx(), fid, _n.at(t.k), (std::uint32_t)_polys.at(t.k).size(), _coef.at(t.k).p, t.scalars.data(), c,
+                                    numer.p, 1, nullptr), "zkb_poly_lincomb");
+            }
+            std::uint32_t pt[8], rem[8];
+            limbs(point, pt);
+            ck(zkb_poly_div_linear(ctx(), fid, n_max, numer.p, pt, quot.p, rem, nullptr), "zkb_poly_div_linear");
+            ck(zkb_vec(ctx(), fid, ZKB_VEC_ADD, n_max, combined.p, quot.p, nullptr, nullptr, combined.p, ZKB_MEM_DEVICE, nullptr), "zkb_vec");
+        };
+        for (const auto &point : unique_points()) {
+            std::vector<term> terms;
+            for (const auto &kv : _polys) {
+                const std::size_t k = kv.first;
+                term t;
+                t.k = k;
+                t.scalars.assign(kv.second.size() * 8, 0);
+                t.constant = value_type::zero();
+                bool used = false;
+                for (std::size_t i = 0; i < kv.second.size(); i++) {
+                    const auto &pts = _points.at(k)[i];
+                    auto it = std::find(pts.begin(), pts.end(), point);
+                    if (it == pts.end()) continue;
+                    limbs(theta_acc, &t.scalars[8 * i]);
+                    t.constant += _z.at(k)[i][it - pts.begin()] * theta_acc;
+                    theta_acc *= theta;
+                    used = true;
+                }
+                if (used) terms.push_back(std::move(t));
+            }
+            add_quotient(point, terms);
+        }
+        for (const auto &kv : _polys) {
+            const std::size_t k = kv.first;
+            if (!_fixed.count(k) || !_fixed.at(k)) continue;
+            term t;
+            t.k = k;
+            t.scalars.assign(kv.second.size() * 8, 0);
+            t.constant = value_type::zero();
+            for (std::size_t i = 0; i < kv.second.size(); i++) {
+                limbs(theta_acc, &t.scalars[8 * i]);
+                t.constant += _fixed_values.at(k)[i] * theta_acc;
+                theta_acc *= theta;
+            }
+            add_quotient(_etha, {t});
+        }
+        // combined_Q.from_coefficients + precommit's resize to D[0]: one forward transform of the zero-padded coefficients
+        const std::size_t log_d0 = _fri.log_d0(), d0 = std::size_t(1) << log_d0;
+        dbuf q_d0(d0 * 32);
+        ck(zkb_buf_zero(ctx(), q_d0.p, d0 * 32, nullptr), "zkb_buf_zero");
+        ck(zkb_buf_copy(ctx(), q_d0.p, ZKB_MEM_DEVICE, combined.p, ZKB_MEM_DEVICE, n_max * 32, nullptr), "zkb_buf_copy");
+        ck(zkb_ntt(ctx(), fid, (int)log_d0, 1, q_d0.p, q_d0.p, 0, nullptr, ZKB_MEM_DEVICE, nullptr), "zkb_ntt");
+        // ---- commit phase (basic_fri.hpp:706-742)
+        const auto &steps = _fri.step_list;
+        const std::size_t rounds = steps.size(), total = _fri.r(), db = MerkleHash::digest_bytes;
+        std::vector<std::uint32_t> step32(steps.begin(), steps.end()), alphas(total * 8), final_l((std::size_t(1) << (log_d0 - total)) * 8);
+        std::vector<std::uint8_t> roots(rounds * db);
+        std::vector<zkb_merkle_tree *> trees(rounds, nullptr);
+        std::vector<std::pair<std::size_t, std::size_t>> fs_off;   // (offset, log size) of fs[i+1]
+        std::size_t acc = log_d0, off = 0;
+        for (auto s_ : steps) { acc -= s_; fs_off.emplace_back(off, acc); off += std::size_t(1) << acc; }
+        dbuf fs(off * 32);
+        cb_state cbs{&transcript};
+        ck(zkb_fri_commit_phase(ctx(), fid, MerkleHash::hash_id, (int)log_d0, q_d0.p, ZKB_MEM_DEVICE, step32.data(), (std::uint32_t)rounds,
+                                &on_root, &cbs, roots.data(), trees.data(), fs.p, alphas.data(), final_l.data(), nullptr),
+           "zkb_fri_commit_phase");
+        std::vector<device_merkle_tree<MerkleHash::hash_id>> fri_trees;
+        proof_type proof;
+        for (std::size_t i = 0; i < rounds; i++) {
+            commitment_type r(roots.begin() + i * db, roots.begin() + (i + 1) * db);
+            fri_trees.emplace_back(trees[i], r);
+            proof.fri_proof.fri_roots.push_back(r);
+        }
+        for (std::size_t i = 0; i < final_l.size() / 8; i++) proof.fri_proof.final_polynomial.push_back(value_type::from_canonical_limbs(&final_l[8 * i]));
+        proof.z = _z;
+        // ---- grinding (basic_fri.hpp:744-747)
+        if (_fri.use_grinding)
+            proof.fri_proof.proof_of_work = proof_of_work<TranscriptHash>::generate(transcript, _fri.grinding_parameter);
+        // ---- query phase (basic_fri.hpp:749-915): the challenges depend on nothing that is opened, so draw them all first
+        if (steps.back() != 1) throw std::invalid_argument("lpc: step_list must end with 1 (check_step_list)");
+        const std::size_t lam = _fri.lambda;
+        std::vector<std::size_t> x_idx0(lam);
+        std::uint32_t expo[8];
+        FieldType::modulus_minus_one_shifted((int)log_d0, expo);
+        for (std::size_t q = 0; q < lam; q++)
+            x_idx0[q] = domain_index(transcript.template challenge<FieldType>().pow_limbs(expo, 8), log_d0);
+        const value_type w0 = omega(log_d0);
+        std::vector<std::vector<std::pair<std::size_t, std::size_t>>> init_pairs(lam);
+        std::vector<std::size_t> flat, leaf0(lam);
+        for (std::size_t q = 0; q < lam; q++) {
+            init_pairs[q] = s_indices(x_idx0[q], d0, steps[0]);
+            for (const auto &pr : init_pairs[q]) flat.push_back(pr.first);
+            leaf0[q] = folded_index(x_idx0[q], d0, steps[0]);
+        }
+        std::sort(flat.begin(), flat.end());
+        flat.erase(std::unique(flat.begin(), flat.end()), flat.end());
+        std::vector<std::uint32_t> pts(flat.size() * 8);
+        for (std::size_t j = 0; j < flat.size(); j++) limbs(w0.pow(flat[j]), &pts[8 * j]);
+        proof.fri_proof.query_proofs.assign(lam, query_proof_type());
+        for (const auto &kv : _polys) {
+            const std::size_t k = kv.first, cnt = kv.second.size(), n = _n.at(k);
+            std::vector<std::uint32_t> vals(cnt * flat.size() * 16);   // [poly][point][z, -z]
+            if (n == d0) {   // already on D[0]: the values themselves (basic_fri.hpp:812-818)
+                std::vector<std::uint64_t> idx;
+                for (std::size_t i = 0; i < cnt; i++)
+                    for (auto a : flat) { idx.push_back(i * n + a); idx.push_back(i * n + a + d0 / 2); }
+                ck(zkb_gather(ctx(), _dev.at(k).p, (std::uint32_t)idx.size(), idx.data(), vals.data(), nullptr), "zkb_gather");
+            } else {         // coefficient form at the 2 lambda points (:819-834), z and -z from one pass
+                ck(zkb_poly_evaluate_pm(ctx(), fid, n, (std::uint32_t)cnt, _coef.at(k).p, (std::uint32_t)flat.size(), pts.data(), vals.data(), nullptr),
+                   "zkb_poly_evaluate_pm");
+            }
+            std::vector<std::uint64_t> l64(leaf0.begin(), leaf0.end());
+            auto paths = _trees.at(k).paths(l64);
+            for (std::size_t q = 0; q < lam; q++) {
+                initial_proof_type ip;
+                ip.values.assign(cnt, {});
+                for (std::size_t i = 0; i < cnt; i++)
+                    for (const auto &pr : init_pairs[q]) {
+                        std::size_t j = std::lower_bound(flat.begin(), flat.end(), pr.first) - flat.begin();
+                        const std::uint32_t *v = &vals[(i * flat.size() + j) * 16];
+                        ip.values[i].push_back({value_type::from_canonical_limbs(v), value_type::from_canonical_limbs(v + 8)});
+                    }
+                ip.p = make_proof(leaf0[q], paths[q], _trees.at(k).root());
+                proof.fri_proof.query_proofs[q].initial_proof.emplace(k, std::move(ip));
+            }
+        }
+        // round proofs: paths of every fri tree, y from the retained fs (one gather), last round from final_polynomial
+        struct slot { std::size_t q, round, j, side; };
+        std::vector<std::uint64_t> gidx;
+        std::vector<slot> gslot;
+        std::vector<std::size_t> xs(x_idx0);
+        std::size_t t = 0;
+        for (std::size_t q = 0; q < lam; q++) proof.fri_proof.query_proofs[q].round_proofs.assign(rounds, round_proof_type());
+        for (std::size_t i = 0; i < rounds; i++) {
+            const std::size_t size_t_ = std::size_t(1) << (log_d0 - t);
+            std::vector<std::uint64_t> leaves(lam);
+            for (std::size_t q = 0; q < lam; q++) { xs[q] %= size_t_; leaves[q] = folded_index(xs[q], size_t_, steps[i]); }
+            auto paths = fri_trees[i].paths(leaves);
+            t += steps[i];
+            const std::size_t size_n = std::size_t(1) << (log_d0 - t);
+            for (std::size_t q = 0; q < lam; q++) {
+                round_proof_type &rp = proof.fri_proof.query_proofs[q].round_proofs[i];
+                rp.p = make_proof((std::size_t)leaves[q], paths[q], proof.fri_proof.fri_roots[i]);
+                if (i + 1 < rounds) {
+                    auto pairs = s_indices(xs[q] % size_n, size_n, steps[i + 1]);
+                    rp.y.assign(pairs.size(), {value_type::zero(), value_type::zero()});
+                    for (std::size_t j = 0; j < pairs.size(); j++) {
+                        gidx.push_back(fs_off[i].first + pairs[j].first);  gslot.push_back({q, i, j, 0});
+                        gidx.push_back(fs_off[i].first + pairs[j].second); gslot.push_back({q, i, j, 1});
+                    }
+                } else {
+                    const std::size_t size_p = std::size_t(1) << (log_d0 - t + 1);   // D[t-1]
+                    const std::size_t xq = xs[q] % size_p;
+                    value_type x = omega(log_d0 - t + 1).pow(xq);
+                    x = x * x;
+                    const std::size_t ind = (xq % (size_p / 2) < size_p / 4) ? 0 : 1;
+                    rp.y.assign(1, {value_type::zero(), value_type::zero()});
+                    rp.y[0][ind] = horner(proof.fri_proof.final_polynomial, x);
+                    rp.y[0][1 - ind] = horner(proof.fri_proof.final_polynomial, -x);
+                }
+            }
+            if (i + 1 < rounds)
+                for (std::size_t q = 0; q < lam; q++) xs[q] %= size_n;
+        }
+        if (!gidx.empty()) {
+            std::vector<std::uint32_t> g(gidx.size() * 8);
+            ck(zkb_gather(ctx(), fs.p, (std::uint32_t)gidx.size(), gidx.data(), g.data(), nullptr), "zkb_gather");
+            for (std::size_t n_ = 0; n_ < gslot.size(); n_++)
+                proof.fri_proof.query_proofs[gslot[n_].q].round_proofs[gslot[n_].round].y[gslot[n_].j][gslot[n_].side] =
+                    value_type::from_canonical_limbs(&g[8 * n_]);
+        }
+        return proof;
     }
 };
 }  // namespace commitments

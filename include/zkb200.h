@@ -264,6 +264,18 @@ int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const vo
 /* runs `iters` dependent Montgomery multiplications per thread on `threads` threads; returns field-mul/s */
 int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threads, uint32_t iters, double *muls_per_s);
 
+/* ---- device buffers for host templates ------------------------------------------------------------ */
+/* lpc_commitment_scheme keeps its polynomials as members between commit / eval_polys / proof_eval
+ * (zk/commitments/polynomial/lpc.hpp:66-200, batched_commitment.hpp:60-250: `_polys`, `_z`); a host template over this ABI
+ * keeps them in device buffers.  zkb_buf_copy synchronises the stream whenever a host buffer is involved;
+ * zkb_gather reads `count` 32-byte field elements src[indices[i]] into host memory with one kernel and one copy (the FRI
+ * query phase takes 2 lambda values from every retained f_i, basic_fri.hpp:880-887). */
+int zkb_buf_alloc(zkb_ctx *ctx, uint64_t bytes, void **device_out);
+void zkb_buf_free(zkb_ctx *ctx, void *device_ptr);
+int zkb_buf_copy(zkb_ctx *ctx, void *dst, int dst_mem, const void *src, int src_mem, uint64_t bytes, void *stream);
+int zkb_buf_zero(zkb_ctx *ctx, void *device_ptr, uint64_t bytes, void *stream);
+int zkb_gather(zkb_ctx *ctx, const void *src_device, uint32_t count, const uint64_t *indices, uint32_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -232,6 +232,82 @@ static void transcript_and_grinding_test(bool with_gpu) {
     CHECK(pow_k512::verify(vk, n3, 0xFF));
 }
 
+// lpc_commitment_scheme (lpc.hpp:66-200) end to end on the host templates: commit three batches (one fixed, one of a
+// smaller size), proof_eval with grinding and the query phase.  Prints "PROOF <keccak-256 of a canonical dump>"; the
+// Python wrapper builds the same proof with the oracle prover (oracle/fri_query.py) and compares the digest.
+template <class V>
+static void dump_value(std::vector<std::uint8_t> &out, const V &v) {
+    std::uint32_t l[8];
+    v.to_canonical_limbs(l);
+    for (int i = 7; i >= 0; i--)
+        for (int b = 3; b >= 0; b--) out.push_back((std::uint8_t)(l[i] >> (8 * b)));
+}
+template <class MP>
+static void dump_merkle_proof(std::vector<std::uint8_t> &out, const MP &p) {
+    for (int b = 7; b >= 0; b--) out.push_back((std::uint8_t)((std::uint64_t)p.index >> (8 * b)));
+    for (const auto &d : p.path) out.insert(out.end(), d.begin(), d.end());
+    out.insert(out.end(), p.root.begin(), p.root.end());
+}
+static void lpc_scheme_test() {
+    typedef algebra::fields::pallas_base_field field_type;
+    typedef field_type::value_type V;
+    typedef hashes::keccak_1600<256> hash_type;
+    typedef zk::commitments::lpc_commitment_scheme<field_type, hash_type, hash_type> scheme_type;
+    zk::commitments::fri_params_type fp;
+    fp.step_list = {2, 1, 1};
+    fp.degree_log = 5; fp.lambda = 5; fp.expand_factor = 2; fp.use_grinding = true; fp.grinding_parameter = 0x3FF;
+    scheme_type scheme(fp);
+    auto poly = [](std::size_t n, std::uint64_t seed) {
+        std::vector<V> v(n);
+        for (std::size_t i = 0; i < n; i++) v[i] = V(seed * 1000003ull + i * i * 7 + i + 1);
+        return math::polynomial_dfs<V>(n - 1, v);
+    };
+    for (std::uint64_t i = 0; i < 2; i++) scheme.append_to_batch(0, poly(32, 1 + i));
+    for (std::uint64_t i = 0; i < 3; i++) scheme.append_to_batch(1, poly(32, 10 + i));
+    scheme.append_to_batch(4, poly(16, 20));
+    std::vector<std::uint8_t> init = {7};
+    scheme_type::transcript_type tr(init);
+    scheme.mark_batch_as_fixed(0);
+    scheme.setup(tr);
+    for (std::size_t k : {0, 1, 4}) scheme.commit(k);
+    V y(123456789), yw = y * math::basic_radix2_domain<field_type>(32).get_domain_element(1);
+    scheme.append_eval_point(0, y);
+    scheme.append_eval_point(1, 0, y);
+    scheme.append_eval_point(1, 1, y);
+    scheme.append_eval_point(1, 1, yw);
+    scheme.append_eval_point(1, 2, yw);
+    scheme.append_eval_point(4, y);
+    auto proof = scheme.proof_eval(tr);
+    CHECK(proof.fri_proof.query_proofs.size() == 5 && proof.fri_proof.fri_roots.size() == 3);
+    CHECK(proof.fri_proof.final_polynomial.size() == 8);
+    std::vector<std::uint8_t> d;
+    for (const auto &kv : proof.z)
+        for (const auto &pz : kv.second)
+            for (const auto &v : pz) dump_value(d, v);
+    for (const auto &r : proof.fri_proof.fri_roots) d.insert(d.end(), r.begin(), r.end());
+    for (const auto &v : proof.fri_proof.final_polynomial) dump_value(d, v);
+    for (int b = 3; b >= 0; b--) d.push_back((std::uint8_t)(proof.fri_proof.proof_of_work >> (8 * b)));
+    for (const auto &q : proof.fri_proof.query_proofs) {
+        for (const auto &kv : q.initial_proof) {
+            for (const auto &pv : kv.second.values)
+                for (const auto &pr : pv) { dump_value(d, pr[0]); dump_value(d, pr[1]); }
+            dump_merkle_proof(d, kv.second.p);
+        }
+        for (const auto &rp : q.round_proofs) {
+            for (const auto &pr : rp.y) { dump_value(d, pr[0]); dump_value(d, pr[1]); }
+            dump_merkle_proof(d, rp.p);
+        }
+    }
+    auto h = hash_type::hash(d.data(), d.size());
+    std::printf("PROOF ");
+    for (auto b : h) std::printf("%02x", b);
+    std::printf(" %zu\n", d.size());
+    auto ts = tr.state();
+    std::printf("TRANSCRIPT ");
+    for (auto b : ts) std::printf("%02x", b);
+    std::printf("\n");
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !std::strcmp(argv[1], "compile-only")) {
         transcript_and_grinding_test(false);   // host-only part: transcript known answers
@@ -251,6 +327,7 @@ int main(int argc, char **argv) {
         domain_and_fold_test<algebra::fields::pallas_base_field>();
         domain_and_fold_test<algebra::fields::pallas_scalar_field>();
         transcript_and_grinding_test(true);
+        lpc_scheme_test();
         precommit_root();
     } catch (const std::exception &e) {
         std::printf("EXCEPTION %s\n", e.what());

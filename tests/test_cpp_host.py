@@ -5,7 +5,7 @@ import subprocess
 
 import pytest
 
-from oracle import fields, fri, hashes
+from oracle import fields, fri, fri_query, hashes, lpc, ntt
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "host_api_test")
@@ -38,3 +38,63 @@ def test_host_templates_on_gpu():
     polys = [[(p + 1) * 1000 + i for i in range(16)] for p in range(3)]
     levels, _ = fri.precommit(polys, F, 64, 2, hashes.keccak256)
     assert root == levels[-1][0].hex()
+    # lpc_commitment_scheme of the host templates: same proof as the oracle prover for the same inputs
+    got = [l.split() for l in r.stdout.splitlines() if l.startswith("PROOF ")][0]
+    want_digest, want_len, want_state = _oracle_lpc_proof_digest()
+    assert (got[1], int(got[2])) == (want_digest, want_len)
+    assert [l.split()[1] for l in r.stdout.splitlines() if l.startswith("TRANSCRIPT ")][0] == want_state
+
+
+def _oracle_lpc_proof_digest():
+    """tests/cpp/host_api_test.cpp:lpc_scheme_test restated with the oracle prover; same canonical dump"""
+    F, h = fields.PALLAS_FP, hashes.keccak256
+    p = F.p
+
+    def poly(n, seed):
+        return [(seed * 1000003 + i * i * 7 + i + 1) % p for i in range(n)]
+
+    polys = {0: [poly(32, 1 + i) for i in range(2)], 1: [poly(32, 10 + i) for i in range(3)], 4: [poly(16, 20)]}
+    params = fri_query.FriParams(F, [2, 1, 1], 5, 5, 2, True, 0x3FF)
+    tr = hashes.FiatShamirSequential(h, bytes([7]))
+    etha = tr.challenge(F)
+    fixed_values = {0: [lpc.poly_eval(ntt.dfs_coefficients(q, F), etha, p) for q in polys[0]]}
+    trees = {k: fri.precommit(polys[k], F, 128, 2, h)[0] for k in polys}
+    y = 123456789
+    yw = y * F.omega(5) % p
+    points = {0: [[y], [y]], 1: [[y], [y, yw], [yw]], 4: [[y]]}
+    proof = fri_query.lpc_proof_eval(polys, points, trees, params, tr, h, (0,), etha, fixed_values)
+    d = bytearray()
+
+    def val(v):
+        d.extend(int(v).to_bytes(32, "big"))
+
+    def mp(q):
+        d.extend(int(q["index"]).to_bytes(8, "big"))
+        for s in q["path"]:
+            d.extend(s)
+        d.extend(q["root"])
+
+    for k in sorted(proof["z"]):
+        for pz in proof["z"][k]:
+            for v in pz:
+                val(v)
+    f = proof["fri_proof"]
+    for r_ in f["fri_roots"]:
+        d.extend(r_)
+    for v in f["final_polynomial"]:
+        val(v)
+    d.extend(int(f["proof_of_work"]).to_bytes(4, "big"))
+    for q in f["query_proofs"]:
+        for k in sorted(q["initial_proof"]):
+            ip = q["initial_proof"][k]
+            for pv in ip["values"]:
+                for pr in pv:
+                    val(pr[0])
+                    val(pr[1])
+            mp(ip["p"])
+        for rp in q["round_proofs"]:
+            for pr in rp["y"]:
+                val(pr[0])
+                val(pr[1])
+            mp(rp["p"])
+    return hashes.keccak256(bytes(d)).hex(), len(d), tr.state.hex()
