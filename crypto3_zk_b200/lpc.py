@@ -47,8 +47,14 @@ class FriParams:
 
 
 class LpcCommitmentScheme:
-    def __init__(self, ctx, field, hash_id, fri_params):
+    def __init__(self, ctx, field, hash_id, fri_params, retain_lde=False):
+        """retain_lde: keep the extended evaluations of every committed batch on the device (|D0| elements per polynomial).
+        The reference drops them and re-evaluates the polynomials at the 2 lambda query points instead, "it takes waaay too
+        much RAM" (basic_fri.hpp:689-691, 750-775); with 180 GB of HBM the 2^20-row Placeholder circuit's 101 columns at
+        blow-up 8 are 27 GB, and the query phase becomes a gather."""
         self.ctx, self.hash_id, self.fri = ctx, hash_id, fri_params
+        self.retain_lde = bool(retain_lde)
+        self._ext = {}
         self.F = FIELD_BY_NAME[field] if isinstance(field, str) else field
         self._polys = {}       # batch index -> list of [n, 8] device tensors (same n within a batch)
         self._points = {}      # batch index -> list (per polynomial) of point lists
@@ -92,8 +98,13 @@ class LpcCommitmentScheme:
         self._points.setdefault(index, [[] for _ in self._polys[index]])
         batch, n = self._batch_tensor(index)
         log_n = n.bit_length() - 1
-        tree = self.ctx.lpc_commit(self.F.name, self.hash_id, batch, log_n, self.fri.log_d0, self.fri.step_list[0],
-                                   keep_tree=True)
+        if self.retain_lde:
+            ext = batch if log_n == self.fri.log_d0 else self.ctx.lde(self.F.name, batch, log_n, self.fri.log_d0)
+            tree = self.ctx.merkle_commit(self.F.name, self.hash_id, ext, self.fri.log_d0, self.fri.step_list[0], keep_tree=True)
+            self._ext[index] = ext
+        else:
+            tree = self.ctx.lpc_commit(self.F.name, self.hash_id, batch, log_n, self.fri.log_d0, self.fri.step_list[0],
+                                       keep_tree=True)
         self._trees[index] = tree
         return tree.root()
 
@@ -266,8 +277,8 @@ class LpcCommitmentScheme:
         leaf0 = [self._folded_index(xi, d0, steps[0]) for xi in x_idx0]
         for k in sorted(self._polys):
             co, n = self._coeffs[k]
-            if n == d0:    # already on D[0]: the values themselves (basic_fri.hpp:812-818)
-                batch, _ = self._batch_tensor(k)
+            if n == d0 or k in self._ext:    # on D[0] already (basic_fri.hpp:812-818) or retained: the values themselves
+                batch = self._ext[k] if k in self._ext else self._batch_tensor(k)[0]
                 idx = [i for a in flat for i in (a, a + half0)]
                 sel = batch[:, torch.tensor(idx, device=batch.device)].cpu().numpy().view(np.uint32)
                 vals = [[(int.from_bytes(sel[i, 2 * j].tobytes(), "little"), int.from_bytes(sel[i, 2 * j + 1].tobytes(), "little"))

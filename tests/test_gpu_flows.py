@@ -302,7 +302,9 @@ def test_lpc_full_proof_vs_oracle(ctx, F, hid, steps, degree_log, expand, grind,
     tp = tr.copy()
     want = fri_query.lpc_proof_eval(polys, points, trees, params, tp, h, (0,), etha, fixed_values)
     # ---- device
-    scheme = LpcCommitmentScheme(ctx, F.name, hid, FriParams(steps, degree_log, lam, expand, grind, 0x3FF))
+    # every other case keeps the extended evaluations on the device (query phase = gather): same proof either way
+    scheme = LpcCommitmentScheme(ctx, F.name, hid, FriParams(steps, degree_log, lam, expand, grind, 0x3FF),
+                                 retain_lde=bool(len(steps) % 2))
     t2 = OracleTranscript(h, F, b"\x07")
     for k in polys:
         nk = len(polys[k][0])
