@@ -243,8 +243,9 @@ class Context:
                                       _stream_ptr(data, stream)), self._h)
         return out
 
-    def lde(self, field, data, log_n_in, log_n_out, out=None, stream=None):
-        """polynomial_dfs::resize(2^log_n_out) for data[batch, 2^log_n_in, 8] -> [batch, 2^log_n_out, 8]."""
+    def lde(self, field, data, log_n_in, log_n_out, out=None, stream=None, coefficients_out=None):
+        """polynomial_dfs::resize(2^log_n_out) for data[batch, 2^log_n_in, 8] -> [batch, 2^log_n_out, 8].
+        coefficients_out (device tensor like data): also receives the coefficient form (zkb_lde_with_coefficients)."""
         fid = _field_id(field)
         b = _Buf(data)
         batch = b.nbytes // ((1 << log_n_in) * 32)
@@ -255,6 +256,13 @@ class Context:
         o = _Buf(out, writable=True)
         if o.mem != b.mem or o.nbytes != batch * (1 << log_n_out) * 32:
             raise ValueError("out must be [batch, 2^log_n_out, 8] in the same memory space as data")
+        if coefficients_out is not None:
+            c = _Buf(coefficients_out, writable=True)
+            if b.mem != capi.MEM_DEVICE or c.mem != capi.MEM_DEVICE or c.nbytes != b.nbytes:
+                raise ValueError("coefficients_out must be a device tensor of the shape of data")
+            capi.check(capi.lib().zkb_lde_with_coefficients(self._h, fid, log_n_in, log_n_out, batch, b.ptr, o.ptr, c.ptr,
+                                                            _stream_ptr(data, stream)), self._h)
+            return out
         capi.check(capi.lib().zkb_lde(self._h, fid, log_n_in, log_n_out, batch, b.ptr, o.ptr, b.mem,
                                       _stream_ptr(data, stream)), self._h)
         return out

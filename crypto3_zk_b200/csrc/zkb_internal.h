@@ -59,8 +59,9 @@ int ctx_table(zkb_ctx *ctx, const std::string &key, size_t bytes, void **out, bo
 int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
                const uint32_t *coset_shift, uint64_t in_poly_stride, uint64_t in_valid_elems, cudaStream_t st,
                const void *known_src = nullptr, int known_log = 0, uint64_t known_poly_stride = 0);
+// d_coef_out (optional, [batch][2^log_n_in]): receives the coefficient form the resize passes through
 int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
-               cudaStream_t st);
+               cudaStream_t st, void *d_coef_out = nullptr);
 // one FRI fold on device buffers (alpha: host, canonical limbs)
 int fold_device(zkb_ctx *ctx, int field, int log_n, const void *d_f, const uint32_t *alpha, void *d_out, cudaStream_t st);
 // leaf packing + Merkle tree over extended evaluations [batch][2^log_d] on the device (zkb_hash.cu)

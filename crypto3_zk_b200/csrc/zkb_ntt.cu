@@ -167,11 +167,12 @@ int ntt_device(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *d
 }
 
 int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *d_in, void *d_out,
-               cudaStream_t st) {
+               cudaStream_t st, void *d_coef_out) {
     if (batch == 0) return ZKB_OK;
     const uint64_t Nin = 1ull << log_n_in, Nout = 1ull << log_n_out;
     if (log_n_in == log_n_out) {
         if (d_in != d_out) ZKB_CUDA_OK(ctx, cudaMemcpyAsync(d_out, d_in, (size_t)batch * Nin * 32, cudaMemcpyDeviceToDevice, st));
+        if (d_coef_out) ZKB_TRY(ntt_device(ctx, field, log_n_in, batch, d_in, d_coef_out, 1, nullptr, Nin, Nin, st));
         return ZKB_OK;
     }
     // coefficients of a chunk of polynomials, then the zero-padded forward transform
@@ -180,12 +181,13 @@ int lde_device(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t ba
     uint64_t fit = ctx->scratch_limit / per_poly;
     if (fit < 1) fit = 1;
     if (fit < chunk) chunk = (uint32_t)fit;
-    void *coef;
-    ZKB_TRY(ctx_scratch(ctx, "lde_coef", (size_t)chunk * Nin * 32, &coef));
+    void *coef_scratch = nullptr;
+    if (!d_coef_out) ZKB_TRY(ctx_scratch(ctx, "lde_coef", (size_t)chunk * Nin * 32, &coef_scratch));
     for (uint32_t b0 = 0; b0 < batch; b0 += chunk) {
         uint32_t nb = batch - b0 < chunk ? batch - b0 : chunk;
         const char *cin = (const char *)d_in + (size_t)b0 * Nin * 32;
         char *cout = (char *)d_out + (size_t)b0 * Nout * 32;
+        void *coef = d_coef_out ? (void *)((char *)d_coef_out + (size_t)b0 * Nin * 32) : coef_scratch;
         ZKB_TRY(ntt_device(ctx, field, log_n_in, nb, cin, coef, 1, nullptr, Nin, Nin, st));
         // out[8 i] (blow-up 8) are the input evaluations: the forward transform neither computes nor stores them
         ZKB_TRY(ntt_device(ctx, field, log_n_out, nb, coef, cout, 0, nullptr, Nin, Nin, st, cin, log_n_out - log_n_in, Nin));
@@ -401,6 +403,17 @@ int zkb_lde(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch
                                  return lde_device(ctx, field, log_n_in, log_n_out, nb, di, dout, st);
                              });
     return lde_device(ctx, field, log_n_in, log_n_out, batch, in, out, st);
+}
+
+int zkb_lde_with_coefficients(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *in_device,
+                              void *out_device, void *coefficients_out_device, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!is_ntt_field(field) || log_n_in < 1 || log_n_out < log_n_in || (batch && (!in_device || !out_device || !coefficients_out_device)))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_lde_with_coefficients: need 1 <= log_n_in <= log_n_out and device buffers");
+    if (log_n_out > zkb_field_two_adicity(field)) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n_out exceeds the two-adicity");
+    if (batch == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return lde_device(ctx, field, log_n_in, log_n_out, batch, in_device, out_device, (cudaStream_t)stream, coefficients_out_device);
 }
 
 int zkb_vec(zkb_ctx *ctx, int field, int op, uint64_t n, const void *a, const void *b, const void *c,

@@ -55,6 +55,7 @@ class LpcCommitmentScheme:
         self.ctx, self.hash_id, self.fri = ctx, hash_id, fri_params
         self.retain_lde = bool(retain_lde)
         self._ext = {}
+        self._commit_coeffs = {}
         self.F = FIELD_BY_NAME[field] if isinstance(field, str) else field
         self._polys = {}       # batch index -> list of [n, 8] device tensors (same n within a batch)
         self._points = {}      # batch index -> list (per polynomial) of point lists
@@ -99,7 +100,10 @@ class LpcCommitmentScheme:
         batch, n = self._batch_tensor(index)
         log_n = n.bit_length() - 1
         if self.retain_lde:
-            ext = batch if log_n == self.fri.log_d0 else self.ctx.lde(self.F.name, batch, log_n, self.fri.log_d0)
+            import torch
+            co = torch.empty_like(batch)      # the coefficient form is a by-product of the resize: eval_polys reuses it
+            ext = self.ctx.lde(self.F.name, batch, log_n, self.fri.log_d0, coefficients_out=co)
+            self._commit_coeffs[index] = (co, n)
             tree = self.ctx.merkle_commit(self.F.name, self.hash_id, ext, self.fri.log_d0, self.fri.step_list[0], keep_tree=True)
             self._ext[index] = ext
         else:
@@ -120,10 +124,13 @@ class LpcCommitmentScheme:
         self._coeffs = {}
         self.z = {}
         for k in sorted(self._polys):
-            batch, n = self._batch_tensor(k)
-            import torch
-            co = torch.empty_like(batch)
-            self.ctx.ntt(self.F.name, batch, n.bit_length() - 1, inverse=True, out=co)
+            if k in self._commit_coeffs:
+                co, n = self._commit_coeffs[k]
+            else:
+                batch, n = self._batch_tensor(k)
+                import torch
+                co = torch.empty_like(batch)
+                self.ctx.ntt(self.F.name, batch, n.bit_length() - 1, inverse=True, out=co)
             self._coeffs[k] = (co, n)
             union = []
             for pts in self._points[k]:

@@ -113,6 +113,11 @@ int zkb_ntt(zkb_ctx *ctx, int field, int log_n, uint32_t batch, const void *in, 
  * out: [batch][2^log_n_out]; log_n_out >= log_n_in >= 1. */
 int zkb_lde(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *in, void *out,
             int mem, void *stream);
+/* the same resize on DEVICE buffers, also returning the coefficient form it passes through ([batch][2^log_n_in]):
+ * lpc's eval_polys / proof_eval call `.coefficients()` on every committed polynomial again (batched_commitment.hpp:185,
+ * lpc.hpp:142) - a scheme that keeps this by-product of commit() skips those inverse transforms */
+int zkb_lde_with_coefficients(zkb_ctx *ctx, int field, int log_n_in, int log_n_out, uint32_t batch, const void *in_device,
+                              void *out_device, void *coefficients_out_device, void *stream);
 
 /* ---- pointwise helpers of the QAP witness map (r1cs_to_qap.hpp:256-262,280-285,301-321) -------- */
 typedef enum {

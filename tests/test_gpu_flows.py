@@ -256,6 +256,21 @@ def test_pow_grind_vs_oracle(ctx, hid, mask):
             assert not fri_query.pow_verify(t.copy(), cand, mask)
 
 
+@pytest.mark.parametrize("log_in,log_out", [(4, 4), (5, 8), (10, 13), (16, 19)])
+def test_lde_with_coefficients(ctx, log_in, log_out):
+    """zkb_lde_with_coefficients: the resize and the coefficient form it passes through (= inverse_fft of the input)"""
+    import torch
+    F = fields.BLS12_381_FR
+    x = dev(to_arr(fields.random_elements(F, 3 << log_in, 17)).reshape(3, 1 << log_in, 8))
+    co = torch.empty_like(x)
+    ext = ctx.lde(F.name, x, log_in, log_out, coefficients_out=co)
+    assert torch.equal(ext, ctx.lde(F.name, x, log_in, log_out))
+    assert torch.equal(co, ctx.ntt(F.name, x.clone(), log_in, inverse=True))
+    if log_in <= 10:
+        want = [v for b in range(3) for v in ntt.dfs_coefficients(from_arr(host(x[b])), F)]
+        assert from_arr(host(co)) == want
+
+
 def test_merkle_paths_vs_single_path(ctx):
     F, h = fields.PALLAS_FQ, hashes.keccak256
     polys = [fields.random_elements(F, 256, 3 + i) for i in range(2)]
