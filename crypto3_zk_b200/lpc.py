@@ -56,6 +56,7 @@ class LpcCommitmentScheme:
         self.retain_lde = bool(retain_lde)
         self._ext = {}
         self._commit_coeffs = {}
+        self._cache = {}
         self.F = FIELD_BY_NAME[field] if isinstance(field, str) else field
         self._polys = {}       # batch index -> list of [n, 8] device tensors (same n within a batch)
         self._points = {}      # batch index -> list (per polynomial) of point lists
@@ -228,13 +229,21 @@ class LpcCommitmentScheme:
     # ---- grinding + query phase of zk::algorithms::proof_eval<FRI> (basic_fri.hpp:743-915)
     def _domain_index(self, x, log_n):
         """index of x in the 2^log_n subgroup (the reference searches linearly, basic_fri.hpp:780-786): bit by bit,
-        bit i of the exponent is set iff (x w^-e)^(2^(log_n-1-i)) != 1"""
+        bit i of the exponent is set iff (x w^-e)^(2^(log_n-1-i)) != 1 for the bits e found so far"""
         p = self.F.p
-        w_inv = pow(omega(self.F, log_n), p - 2, p)
-        e = 0
+        key = ("winv", log_n)
+        if key not in self._cache:
+            w_inv, tab = pow(omega(self.F, log_n), p - 2, p), []
+            for _ in range(log_n):
+                tab.append(w_inv)              # w^-(2^i)
+                w_inv = w_inv * w_inv % p
+            self._cache[key] = tab
+        tab = self._cache[key]
+        e, cur = 0, x % p
         for i in range(log_n):
-            if pow(x * pow(w_inv, e, p) % p, 1 << (log_n - 1 - i), p) != 1:
+            if pow(cur, 1 << (log_n - 1 - i), p) != 1:
                 e |= 1 << i
+                cur = cur * tab[i] % p
         return e
 
     @staticmethod
