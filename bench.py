@@ -523,38 +523,39 @@ def placeholder_extra(args, torch, ctx, dev):
         if name == "expand_factor_3_keccak256":
             # the same proof with the extended evaluations retained on the device (27 GB): the query phase is a gather
             try:
-                tr = FiatShamirSequential(0, b"placeholder")
-                scheme = LpcCommitmentScheme(ctx, F.name, hid, fri, retain_lde=True)
-                for k in sizes:
-                    scheme.append_to_batch(k, cols[k])
-                scheme.mark_batch_as_fixed(0)
-                scheme.commit(0)
-                scheme.setup(tr, {0: [0] * sizes[0]})
-                t_c = 0.0
-                for k in (1, 2, 3):
+                for rit in range(2):   # the first pass lets the torch allocator obtain the 27 GB once
+                    tr = FiatShamirSequential(0, b"placeholder")
+                    scheme = LpcCommitmentScheme(ctx, F.name, hid, fri, retain_lde=True)
+                    for k in sizes:
+                        scheme.append_to_batch(k, cols[k])
+                    scheme.mark_batch_as_fixed(0)
+                    scheme.commit(0)
+                    scheme.setup(tr, {0: [0] * sizes[0]})
+                    t_c = 0.0
+                    for k in (1, 2, 3):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        tr(scheme.commit(k))
+                        torch.cuda.synchronize()
+                        t_c += (time.perf_counter() - t0) * 1e3
+                    y = tr.challenge(F.p)
+                    for k in sizes:
+                        scheme.append_eval_point(k, y)
+                    for k in (1, 2):
+                        scheme.append_eval_point(k, y * omega(F, rows_log) % F.p)
+                    co = scheme.ctx.ntt(F.name, cols[0].clone(), rows_log, inverse=True)
+                    scheme._fixed_values = {0: [v[0] for v in ctx.poly_evaluate(F.name, co, n, [scheme._etha])]}
+                    del co
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    tr(scheme.commit(k))
+                    scheme.proof_eval(tr, query=True)
                     torch.cuda.synchronize()
-                    t_c += (time.perf_counter() - t0) * 1e3
-                y = tr.challenge(F.p)
-                for k in sizes:
-                    scheme.append_eval_point(k, y)
-                for k in (1, 2):
-                    scheme.append_eval_point(k, y * omega(F, rows_log) % F.p)
-                co = scheme.ctx.ntt(F.name, cols[0].clone(), rows_log, inverse=True)
-                scheme._fixed_values = {0: [v[0] for v in ctx.poly_evaluate(F.name, co, n, [scheme._etha])]}
-                del co
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                scheme.proof_eval(tr, query=True)
-                torch.cuda.synchronize()
-                t_all = (time.perf_counter() - t0) * 1e3
-                res["retain_lde"] = {"commit_ms_three_batches": t_c, "proof_eval_ms": t_all,
-                                     "proof_eval_query_phase_ms": scheme.timings["query_phase_ms"],
-                                     "ms_per_proof_with_query_phase": t_c + t_all,
-                                     "retained_bytes": sum(int(t.numel()) * 4 for t in scheme._ext.values())}
-                del scheme
+                    t_all = (time.perf_counter() - t0) * 1e3
+                    res["retain_lde"] = {"commit_ms_three_batches": t_c, "proof_eval_ms": t_all,
+                                         "proof_eval_query_phase_ms": scheme.timings["query_phase_ms"],
+                                         "ms_per_proof_with_query_phase": t_c + t_all,
+                                         "retained_bytes": sum(int(t.numel()) * 4 for t in scheme._ext.values())}
+                    del scheme
             except Exception as e:
                 res["retain_lde"] = {"error": repr(e)[:200]}
         out[name] = res
