@@ -710,7 +710,7 @@ def main():
     # zero levels of pass 1 (half a product per element and level) and minus the known outputs in the middle passes.
     try:
         from crypto3_zk_b200.csrc_plan import ntt_radices
-        lr_in, lr_out = ntt_radices(args.log_in), ntt_radices(args.log_out)
+        lr_in, lr_out = ntt_radices(args.log_in), ntt_radices(args.log_out, small_first=True)
         z = args.log_out - args.log_in
         known = z >= 3 and len(lr_out) >= 2 and z <= lr_out[0]
         prod = n_in * (args.log_in / 2.0 + len(lr_in) - 1)

@@ -99,7 +99,8 @@ static int host_ntt(int log_n, int log_n_in, int inverse, const uint32_t *shift,
     typedef Fp<P> F;
     if (log_n > P::TWO_ADICITY || log_n < 1) return 2;
     const uint64_t N = 1ull << log_n, Nin = 1ull << log_n_in;
-    NttPlan pl = ntt_make_plan(log_n);
+    NttPlan pl = ntt_make_plan(log_n, Nin < N);   // as ntt_device_t chooses
+    if (pl.n_passes < 1) pl = ntt_make_plan(log_n);
     if (pl.n_passes < 1) return 3;
     F wN = ntt_omega<F, P>(log_n, inverse);
     F wT = ntt_omega<F, P>(ZKB_NTT_TW_LOG, inverse);

@@ -117,7 +117,8 @@ static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_i
     typedef Fp<P> F;
     if (log_n > P::TWO_ADICITY) return ctx_fail(ctx, ZKB_ERR_DOMAIN_TOO_LARGE, "2^log_n exceeds the two-adicity");
     const uint64_t N = 1ull << log_n;
-    NttPlan pl = ntt_make_plan(log_n);
+    NttPlan pl = ntt_make_plan(log_n, in_valid < N);
+    if (pl.n_passes < 1) pl = ntt_make_plan(log_n);
     if (pl.n_passes < 1) return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "no pass plan");
     NttTables tb;
     ZKB_TRY(ntt_tables<P>(ctx, pl, inverse, shift, &tb, st));

@@ -27,7 +27,10 @@ struct NttPlan {
     }
 };
 
-inline NttPlan ntt_make_plan(int log_n) {
+// small_first: the smaller radices go to the first passes.  For a zero-padded (LDE) input the first pass skips
+// z = log2(blow-up) levels, and 2^23 = 2^7 2^8 2^8 with z = 3 leaves 4 levels = two radix-4 phases there and no radix-2
+// phase anywhere, where 2^8 2^8 2^7 has one in the first and one in the last pass.
+inline NttPlan ntt_make_plan(int log_n, bool small_first = false) {
     NttPlan pl;
     pl.log_n = log_n;
     int p = (log_n + ZKB_NTT_MAX_LOG_R - 1) / ZKB_NTT_MAX_LOG_R;
@@ -35,10 +38,10 @@ inline NttPlan ntt_make_plan(int log_n) {
     pl.n_passes = p;
     int base = log_n / p, rem = log_n % p;
     for (int i = 0; i < ZKB_NTT_MAX_PASSES; i++) pl.lr[i] = 0;
-    for (int i = 0; i < p; i++) pl.lr[i] = base + (i < rem ? 1 : 0);
+    for (int i = 0; i < p; i++) pl.lr[i] = base + ((small_first ? i >= p - rem : i < rem) ? 1 : 0);
     // multi-pass tiles need R_1 >= C and M_i >= C (C = 8): true for every log_n with the default
     // ZKB_NTT_MAX_LOG_R = 8 (p >= 2 only when log_n >= 9 -> every lr >= 4).
-    if (p >= 2 && pl.lr[p - 1] < 3) pl.n_passes = -1;
+    if (p >= 2 && (pl.lr[p - 1] < 3 || pl.lr[0] < 3)) pl.n_passes = -1;
     return pl;
 }
 
