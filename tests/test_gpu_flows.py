@@ -271,6 +271,34 @@ def test_lde_with_coefficients(ctx, log_in, log_out):
         assert from_arr(host(co)) == want
 
 
+def test_query_phase_entry_points_edge_cases(ctx):
+    """argument checking and degenerate sizes of the 8(f)-2 entry points"""
+    import ctypes
+    from crypto3_zk_b200 import capi
+    F = fields.PALLAS_FQ
+    st = hashes.keccak256(b"x")
+    assert ctx.pow_grind(0, st, 0) == 0 and ctx.pow_grind(0, st, 0, start=77) == 77      # empty mask: the start itself
+    with pytest.raises(capi.ZkbInvalidArgument):
+        ctx.pow_grind(0, st[:31], 0xFF)
+    with pytest.raises(capi.ZkbInvalidArgument):
+        ctx.pow_grind(7, st, 0xFF)
+    nonce = ctypes.c_uint32(0)
+    buf = (ctypes.c_uint8 * 32).from_buffer_copy(st)
+    assert capi.lib().zkb_pow_grind(ctx._h, 0, None, 0, 1, ctypes.byref(nonce), None) == capi.ERR_INVALID_ARGUMENT
+    assert capi.lib().zkb_pow_grind(ctx._h, 0, buf, 0, 1, None, None) == capi.ERR_INVALID_ARGUMENT
+    # a single polynomial of two evaluations, fri_step 1: one leaf, depth 0
+    one = ctx.merkle_commit(F.name, 0, dev(to_arr([5, 9]).reshape(1, 2, 8)), 1, 1, keep_tree=True)
+    assert one.leaves == 1 and one.paths([0, 0]) == [[], []]
+    assert one.root() == hashes.keccak256((5).to_bytes(32, "big") + (9).to_bytes(32, "big"))
+    # constants and tiny polynomials through the paired evaluation
+    x = dev(to_arr([3, 4, 5]).reshape(3, 1, 8))
+    assert ctx.poly_evaluate_pm(F.name, x, 1, [0, 1, F.p - 1]) == [[(c, c)] * 3 for c in (3, 4, 5)]
+    y = dev(to_arr([2, 7]).reshape(1, 2, 8))
+    assert ctx.poly_evaluate_pm(F.name, y, 2, [10]) == [[(72, (2 - 70) % F.p)]]
+    with pytest.raises(ValueError):
+        ctx.poly_evaluate_pm(F.name, to_arr([1, 2]).reshape(1, 2, 8), 2, [1])           # host polynomials: device only
+
+
 def test_merkle_paths_vs_single_path(ctx):
     F, h = fields.PALLAS_FQ, hashes.keccak256
     polys = [fields.random_elements(F, 256, 3 + i) for i in range(2)]
