@@ -453,6 +453,15 @@ def groth16_extra(args, torch, ctx, dev):
         torch.cuda.synchronize()
         tables["ms_per_proof"] = (time.perf_counter() - t0) / 3 * 1e3
         tables["same_proof"] = proof_t == proof
+        # the five multiexps on five streams (groth16.prove(concurrent=True))
+        proof_c = dg.prove(ctx, pk, None, None, r, s, x_device=xd, concurrent=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dg.prove(ctx, pk, None, None, r, s, x_device=xd, concurrent=True)
+        torch.cuda.synchronize()
+        tables["ms_per_proof_concurrent_msms"] = (time.perf_counter() - t0) / 3 * 1e3
+        tables["same_proof_concurrent"] = proof_c == proof
         tables["parts_ms_random_scalars"] = {
             "msm_A_g1": time_cuda(torch, lambda: ctx.multiexp(pk.A, sc[:pk.A.n]), 3),
             "msm_B_g2": time_cuda(torch, lambda: ctx.multiexp(pk.B2, sc[:pk.B2.n]), 3)}

@@ -35,7 +35,8 @@ int msm_window_combine(int curve, int c, int W, const uint32_t *sums, uint32_t *
 }
 
 struct zkb_msm_bases {
-    zkb_ctx *ctx;
+    int device;      // bases are plain device memory: any context of the same device may use them (one context per
+                     // concurrent call - a context's scratch serves one call at a time)
     int curve;
     uint64_t n;
     void *d_points;  // Affine<F>, Montgomery form
@@ -771,7 +772,7 @@ int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points
         }
     }
     zkb_msm_bases *b = new zkb_msm_bases();
-    b->ctx = ctx;
+    b->device = ctx->device;
     b->curve = curve;
     b->n = n;
     b->d_points = d;
@@ -782,7 +783,7 @@ int zkb_msm_bases_create(zkb_ctx *ctx, int curve, uint64_t n, const void *points
 void zkb_msm_bases_free(zkb_msm_bases *b) {
     if (!b) return;
     if (b->d_points || b->d_table) {
-        cudaSetDevice(b->ctx->device);
+        cudaSetDevice(b->device);
         if (b->d_points) cudaFree(b->d_points);
         if (b->d_table) cudaFree(b->d_table);
     }
@@ -792,7 +793,7 @@ void zkb_msm_bases_free(zkb_msm_bases *b) {
 uint64_t zkb_msm_bases_size(const zkb_msm_bases *b) { return b ? b->n : 0; }
 
 int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *b, int window_bits, uint64_t max_bytes, void *stream) {
-    if (!ctx || !b || b->ctx != ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (!ctx || !b || b->device != ctx->device) return ZKB_ERR_INVALID_ARGUMENT;
     if (b->d_table || b->n == 0) return ZKB_OK;
     int c = window_bits;
     if (c == 0) {   // one bucket per ~2 points of a full-length MSM
@@ -811,7 +812,7 @@ int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *b, int window_bits, ui
 int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
                     uint32_t *partial_xyzz_host, void *stream) {
     if (!ctx || !bases || !partial_xyzz_host) return ZKB_ERR_INVALID_ARGUMENT;
-    if (bases->ctx != ctx || offset > bases->n || n > bases->n - offset || (n && !scalars))
+    if (bases->device != ctx->device || offset > bases->n || n > bases->n - offset || (n && !scalars))
         return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_msm: range outside the bases / null scalars");
     int cl = curve_coord_limbs(bases->curve);
     if (n == 0) {  // empty sum = infinity (XYZZ all zero)

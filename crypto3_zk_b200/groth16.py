@@ -121,10 +121,13 @@ def witness_map(ctx, pk, x):
     return h
 
 
-def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None):
+def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None, concurrent=False):
     """Returns (g1_A, g2_B, g1_C) in affine form.  r, s: the prover's zero-knowledge randomness (the reference draws
     them with algebra::random_element, prover.hpp:91-92).  x_device: optional device tensor with the full assignment
-    (1, primary, auxiliary) as [num_variables + 1, 8] limbs; otherwise it is uploaded from the Python integers."""
+    (1, primary, auxiliary) as [num_variables + 1, 8] limbs; otherwise it is uploaded from the Python integers.
+    concurrent: the five multiexps of prover.hpp:108-139 are independent; run each on its own stream (and context: a
+    context's scratch belongs to one call at a time) from its own host thread, so the latency-bound bucket-reduce tail of
+    one overlaps the bucket accumulation of the others.  Same proof."""
     import torch
     F = pk.F
     p = F.p
@@ -142,13 +145,40 @@ def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None):
     def head(*vals):
         return torch.from_numpy(_int_rows([v % p for v in vals]).view(np.int32)).to(dev)
 
-    g1_A = ctx.multiexp(pk.A, torch.cat([head(1, r), x]))
+    sa = torch.cat([head(1, r), x])
     xb = x.index_select(0, pk.B_index)
     sb = torch.cat([head(1, s), xb])
-    g2_B = ctx.multiexp(pk.B2, sb)
-    g1_B = ctx.multiexp(pk.B1, sb)
-    ev_H = ctx.multiexp(pk.H, h[:m - 1].contiguous(), n=m - 1)
-    ev_L = ctx.multiexp(pk.L, x[ni + 1:].contiguous())
+    sh, sl = h[:m - 1].contiguous(), x[ni + 1:].contiguous()
+    jobs = [(pk.B2, sb, None), (pk.A, sa, None), (pk.B1, sb, None), (pk.H, sh, m - 1), (pk.L, sl, None)]
+    if not concurrent:
+        g2_B, g1_A, g1_B, ev_H, ev_L = [ctx.multiexp(b, sc, n=n) for b, sc, n in jobs]
+    else:
+        import threading
+        from .api import Context
+        if not hasattr(pk, "_side"):
+            pk._side = [(Context(ctx.device), torch.cuda.Stream(device=dev)) for _ in jobs]
+        main = torch.cuda.current_stream(dev)
+        out, err = [None] * len(jobs), []
+
+        def run(i):
+            try:
+                c, st = pk._side[i]
+                torch.cuda.set_device(ctx.device)
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    b, sc, n = jobs[i]
+                    out[i] = c.multiexp(b, sc, n=n)
+            except Exception as e:   # surfaces in the calling thread
+                err.append(e)
+
+        th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        if err:
+            raise err[0]
+        g2_B, g1_A, g1_B, ev_H, ev_L = out
     tail = ctx.msm_bases(pk.g1.name, _points_array(pk.g1, [ev_H, ev_L, g1_A, g1_B, pk.delta_g1]))
     g1_C = ctx.multiexp(tail, _int_rows([1, 1, s % p, r % p, (-r * s) % p]))
     tail.free()

@@ -490,6 +490,7 @@ def test_groth16_prove_vs_oracle(ctx, curve, kind, nc, ni):
     assert from_arr(host(h)) == H[:m]
     got = dg.prove(ctx, dpk, primary, aux, r, s)
     assert got == want
+    assert dg.prove(ctx, dpk, primary, aux, r, s, concurrent=True) == want     # five multiexps on five streams
     a, b, c = groth16.proof_in_the_exponent(pk, primary, aux, r, s, F)
     assert got[0] == G1.mul(G1.gen, a) and got[1] == G2.mul(G2.gen, b) and got[2] == G1.mul(G1.gen, c)
     # zero randomness and a binary assignment exercise the 0/1 scalar paths of the MSM
