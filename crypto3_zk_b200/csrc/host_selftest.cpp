@@ -145,6 +145,15 @@ static int host_ntt(int log_n, int log_n_in, int inverse, const uint32_t *shift,
     memset(work.data(), 0xA5, work.size() * sizeof(F));
     auto passes = ntt_build_passes(pl, tb, in, out, work.data(), batch, Nin, N, Nin, known_src, known_log, Nin);
     for (auto &q : passes) replay_pass<P>(q);
+    if (passes.back().known_log > 0) {
+        const int kl = passes.back().known_log;
+        const uint64_t total = (uint64_t)batch << (log_n - kl);
+        for (uint64_t e = 0; e < total; e++) {
+            uint64_t s_, d_;
+            ntt_known_scatter_index(e, log_n, kl, Nin, N, &s_, &d_);
+            memcpy(out + 8 * d_, known_src + 8 * s_, 32);
+        }
+    }
     return 0;
 }
 

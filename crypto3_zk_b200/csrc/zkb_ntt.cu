@@ -110,6 +110,17 @@ static int ntt_launch(zkb_ctx *ctx, const NttPassParams &q, cudaStream_t st) {
     return ZKB_OK;
 }
 
+// the known outputs of an LDE (see NttPassParams::known_log): a strided copy of the input evaluations
+__global__ void __launch_bounds__(256) ntt_known_scatter_kernel(const u128 *__restrict__ src, u128 *__restrict__ dst, uint64_t total,
+                                                                int log_n, int known_log, uint64_t known_poly_stride,
+                                                                uint64_t out_poly_stride) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * total) return;
+    uint64_t s, d;
+    ntt_known_scatter_index(i >> 1, log_n, known_log, known_poly_stride, out_poly_stride, &s, &d);
+    dst[2 * d + (i & 1)] = src[2 * s + (i & 1)];
+}
+
 template <class P>
 static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_in, void *d_out, int inverse,
                         const uint32_t *shift, uint64_t in_poly_stride, uint64_t in_valid, cudaStream_t st,
@@ -139,6 +150,14 @@ static int ntt_device_t(zkb_ctx *ctx, int log_n, uint32_t batch, const void *d_i
         const char *ksrc = known_src ? (const char *)known_src + (size_t)b0 * known_poly_stride * sizeof(F) : nullptr;
         auto passes = ntt_build_passes(pl, tb, cin, cout, work, nb, in_poly_stride, N, in_valid, ksrc, known_log, known_poly_stride);
         for (auto &q : passes) ZKB_TRY(ntt_launch<P>(ctx, q, st));
+        if (passes.back().known_log > 0) {
+            const int kl = passes.back().known_log;
+            const uint64_t total = (uint64_t)nb << (log_n - kl);
+            ntt_known_scatter_kernel<<<(unsigned)((2 * total + 255) / 256), 256, 0, st>>>((const u128 *)ksrc, (u128 *)cout, total, log_n, kl,
+                                                                                       known_poly_stride, N);
+            ctx->launches++;
+            ZKB_CUDA_OK(ctx, cudaGetLastError());
+        }
     }
     return ZKB_OK;
 }

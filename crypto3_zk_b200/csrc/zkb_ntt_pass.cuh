@@ -58,7 +58,8 @@ struct NttPassParams {
     // LDE: the outputs at multiples of 2^known_log are the input evaluations themselves (the coset of index 0 of the
     // larger domain is the smaller domain), out[poly][j 2^known_log] = known_src[poly][j].  Such outputs have
     // k_1 = 0 mod 2^known_log, so they are never computed: pass 1 does not store those rows, the middle passes skip
-    // the tiles of those k_1, and the last pass leaves their column out and copies it from known_src.
+    // the tiles of those k_1, and the tiles of the last pass take their 8 columns from the kept k_1 only (one gap per
+    // tile at most); ntt_known_scatter writes them from known_src.
     int known_log;                // 0 = off; otherwise 3 <= known_log <= lr[0]
     int known_k1_shift;           // middle pass: k_1 = q >> known_k1_shift
     const u128 *known_src;
@@ -88,16 +89,15 @@ struct NttTile {
     uint64_t in_row_stride, in_col_stride, out_row_stride, out_col_stride;
     uint64_t in_tab_base, out_tab_base;         // offsets within the polynomial (for the tables)
     uint32_t ncols;                             // valid columns
-    uint32_t skip_col0;                         // 1: column 0 of this FINAL tile is known: loaded as zeros, stored from known_src
-                                                // (its butterflies still run: a 7-column task map breaks the conflict-free
-                                                // quarter-warp shared-memory pattern and measured slower)
+    uint32_t col_skip;                          // columns >= col_skip sit one k_1 further (the known k_1 between them is
+                                                // not part of any tile); 0xffffffff: the 8 columns are consecutive
     uint64_t poly;
 };
 
 ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
     NttTile t;
     const uint32_t C = ZKB_NTT_C;
-    t.skip_col0 = 0;
+    t.col_skip = 0xffffffffu;
     t.poly = 0;
     if (p.mode == NTT_MODE_SINGLE) {
         // columns = polynomials of the batch
@@ -137,21 +137,34 @@ ZKB_HD NttTile ntt_tile(const NttPassParams &p, uint64_t tile) {
         t.out_row_stride = 1ull << p.log_m; t.out_col_stride = 1;
     } else {  // FINAL: rows contiguous on input, columns (k_1) contiguous on output
         uint64_t kblocks = (1ull << p.lr[0]) / C;
-        uint64_t kb = tt % kblocks, q = tt / kblocks;  // q = (k_2 .. k_{p-1}) mixed radix, k_2 major
-        uint64_t in_off = ((kb * C) << p.log_m) + (q << p.log_r);
+        uint64_t k1_0;                                 // k_1 of column 0
+        if (p.known_log > 0) {
+            // columns = 8 consecutive KEPT k_1 (those that are not 0 mod 2^known_log): kept index kappa -> k_1 = kappa +
+            // kappa / per + 1 with per = 2^known_log - 1 kept values per period; 8 consecutive kappa cross one period
+            // boundary at most (per >= 7)
+            const uint64_t per = (1ull << p.known_log) - 1;
+            kblocks = (((1ull << p.lr[0]) >> p.known_log) * per) / C;
+            const uint64_t kappa0 = (tt % kblocks) * C;
+            k1_0 = kappa0 + kappa0 / per + 1;
+            const uint64_t c1 = per - kappa0 % per;
+            if (c1 < C) t.col_skip = (uint32_t)c1;
+        } else {
+            k1_0 = (tt % kblocks) * C;
+        }
+        uint64_t q = tt / kblocks;                     // q = (k_2 .. k_{p-1}) mixed radix, k_2 major
+        uint64_t in_off = (k1_0 << p.log_m) + (q << p.log_r);
         uint64_t rev = 0, qq = q;
         for (int i = p.n_passes - 2; i >= 1; i--) {
             uint64_t d = qq & ((1ull << p.lr[i]) - 1);
             qq >>= p.lr[i];
             rev = (rev << p.lr[i]) | d;
         }
-        uint64_t out_off = kb * C + (rev << p.lr[0]);
+        uint64_t out_off = k1_0 + (rev << p.lr[0]);
         t.in_tab_base = in_off; t.out_tab_base = out_off;
         t.in_base = poly * p.in_poly_stride + in_off;
         t.out_base = poly * p.out_poly_stride + out_off;
         t.in_row_stride = 1; t.in_col_stride = 1ull << p.log_m;
         t.out_row_stride = 1ull << (p.log_n - p.log_r); t.out_col_stride = 1;
-        if (p.known_log > 0 && ((kb * C) & ((1ull << p.known_log) - 1)) == 0) t.skip_col0 = 1;
     }
     return t;
 }
@@ -199,9 +212,10 @@ ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem,
             half = u & 1; r = (u >> 1) % L; c = u / (2 * L);
         }
         u128 v = zero;
-        uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
-        if (c < t.ncols && c >= t.skip_col0 && widx < p.in_valid_elems)
-            v = p.in[2 * (t.in_base + r * t.in_row_stride + c * t.in_col_stride) + half];
+        const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
+        uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : ce * t.in_col_stride);
+        if (c < t.ncols && widx < p.in_valid_elems)
+            v = p.in[2 * (t.in_base + r * t.in_row_stride + ce * t.in_col_stride) + half];
         for (uint32_t k = 0; k < copies; k++) smem[ntt_slot(p.log_r, half, r + k * L, c)] = v;
     }
 }
@@ -214,7 +228,8 @@ ZKB_HD void ntt_phase_premul(const NttPassParams &p, const NttTile &t, u128 *sme
     const uint32_t L = R >> p.zero_levels, copies = 1u << p.zero_levels;
     for (uint32_t e = tid; e < L * C; e += nthreads) {
         uint32_t c = e % C, r = e / C;
-        uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.in_col_stride);
+        const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
+        uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : ce * t.in_col_stride);
         F v = ntt_ld_elem<F>(smem, p.log_r, r, c);
         if (c < t.ncols && widx < p.in_valid_elems) {
             uint64_t idx = widx & p.load_mask;
@@ -303,14 +318,9 @@ ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128
                 half = u & 1; k = (u >> 1) % R; c = u / (2 * R);
             }
             if (c >= t.ncols) continue;
-            u128 v;
-            if (c < t.skip_col0) {   // known output: the input evaluation at (output index) >> known_log
-                uint64_t o = t.out_tab_base + k * t.out_row_stride;
-                v = p.known_src[2 * (t.poly * p.known_poly_stride + (o >> p.known_log)) + half];
-            } else {
-                v = smem[ntt_slot(p.log_r, half, brev(k, p.log_r), c)];
-            }
-            p.out[2 * (t.out_base + k * t.out_row_stride + c * t.out_col_stride) + half] = v;
+            const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
+            p.out[2 * (t.out_base + k * t.out_row_stride + ce * t.out_col_stride) + half] =
+                smem[ntt_slot(p.log_r, half, brev(k, p.log_r), c)];
         }
         return;
     }
@@ -321,11 +331,12 @@ ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128
         uint32_t k, c;
         if (t.out_col_stride == 1) { c = e % C; k = e / C; } else { k = e % R; c = e / R; }
         if (c >= t.ncols || (kskip && (k & kmask) == 0)) continue;
-        uint64_t off = k * t.out_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : c * t.out_col_stride);
+        const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
+        uint64_t off = k * t.out_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : ce * t.out_col_stride);
         F v = ntt_ld_elem<F>(smem, p.log_r, brev(k, p.log_r), c);
         v = v * ntt_ld_tab<F>(p.store_tab, (t.out_tab_base + off) & p.store_mask);
         u128 lo = {v.l[0], v.l[1], v.l[2], v.l[3]}, hi = {v.l[4], v.l[5], v.l[6], v.l[7]};
-        u128 *dst = p.out + 2 * (t.out_base + k * t.out_row_stride + c * t.out_col_stride);
+        u128 *dst = p.out + 2 * (t.out_base + k * t.out_row_stride + ce * t.out_col_stride);
         dst[0] = lo;
         dst[1] = hi;
     }

@@ -76,7 +76,8 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
     const int p = pl.n_passes;
     // known outputs (see NttPassParams::known_log): multi-pass plans whose first radix covers the period, a whole
     // number of periods per column block of the last pass, and no post-scale on the last pass
-    if (!(known_src && p >= 2 && known_log >= 3 && known_log <= pl.lr[0] && tb.store_tab == nullptr)) known_log = 0;
+    // (the kept k_1 values must fill whole column blocks of the last pass: R_1 / 2^known_log a multiple of 8)
+    if (!(known_src && p >= 2 && known_log >= 3 && known_log + 3 <= pl.lr[0] && tb.store_tab == nullptr)) known_log = 0;
     for (int i = 0; i < p; i++) {
         NttPassParams q;
         q.batch = batch;
@@ -125,6 +126,7 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
             q.mode = NTT_MODE_FINAL;
             q.log_m = pl.log_m(1);
             q.tiles_per_poly = N >> (q.log_r + 3);
+            if (known_log > 0) q.tiles_per_poly -= q.tiles_per_poly >> known_log;   // no tile holds a known k_1
             q.in = (const u128 *)work; q.in_poly_stride = N;
             q.out = (u128 *)out; q.out_poly_stride = out_poly_stride;
             q.store_tab = tb.store_tab; q.store_mask = tb.store_mask;
@@ -132,6 +134,16 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
         v.push_back(q);
     }
     return v;
+}
+
+// out[poly][j 2^known_log] = known_src[poly][j]: element e of the flat range [0, batch * (N >> known_log)) (the device
+// kernel in zkb_ntt.cu and the CPU replay both use this mapping)
+ZKB_HD void ntt_known_scatter_index(uint64_t e, int log_n, int known_log, uint64_t known_poly_stride, uint64_t out_poly_stride,
+                                    uint64_t *src, uint64_t *dst) {
+    const uint64_t per_poly = 1ull << (log_n - known_log);
+    const uint64_t poly = e / per_poly, j = e % per_poly;
+    *src = poly * known_poly_stride + j;
+    *dst = poly * out_poly_stride + (j << known_log);
 }
 
 inline uint64_t ntt_pass_tiles(const NttPassParams &q) {

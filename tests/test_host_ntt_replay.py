@@ -111,14 +111,16 @@ def test_zero_padded_coset_input(libs, maxlogr, log_in, log_out):
 
 
 @pytest.mark.parametrize("maxlogr,log_in,log_out", [(8, 7, 10), (8, 6, 10), (8, 9, 12), (4, 6, 10), (4, 6, 9), (4, 8, 12),
-                                                     (3, 6, 9), (3, 3, 9), (8, 5, 7), (8, 3, 6), (4, 9, 13)])
+                                                     (3, 6, 9), (3, 3, 9), (8, 5, 7), (8, 3, 6), (4, 9, 13),
+                                                     (8, 10, 13), (8, 11, 14), (8, 12, 16), (8, 15, 18)])
 def test_lde_with_known_outputs(libs, maxlogr, log_in, log_out):
     """lde_device as the runtime drives it (iNTT, then the zero-padded forward transform that takes the outputs at
     multiples of the blow-up from the input evaluations) against polynomial_dfs::resize; 2/3/4-pass plans, blow-ups
     4..64 (below 8 the known-output path is off), with the work buffer poisoned."""
     F = fields.NTT_FIELDS[(log_in + log_out) % 4]
     lib = libs[maxlogr]
-    batch = 3
+    batch = 3 if log_out <= 14 else 2      # (the last cases are the ones where the known-output path is on: 2- and 3-pass
+                                           # plans, periods of 7 and 15 kept k_1, first radix 64 / 128 / 256)
     polys = [fields.random_elements(F, 1 << log_in, 50 + b) for b in range(batch)]
     a = fields.ints_to_u32_array([v for p in polys for v in p], 8)
     out = np.zeros((batch << log_out, 8), dtype=np.uint32)
