@@ -738,19 +738,19 @@ def main():
     # the co-limiter SURVEY 8(d) asks for next to the HBM figure: modular products per step against the measured peak of
     # this field's multiplier.  Products per polynomial: inverse transform = butterflies log_in/2 per
     # element + one inter-pass twiddle per pass boundary; forward transform = the same on 2^log_out elements minus the
-    # zero levels of pass 1 (half a product per element and level) and minus the known outputs in the middle passes.
+    # zero levels of pass 1 (half a product per element and level) and minus the known outputs in every later pass.
     try:
         from crypto3_zk_b200.csrc_plan import ntt_radices
         lr_in, lr_out = ntt_radices(args.log_in), ntt_radices(args.log_out, small_first=True)
         z = args.log_out - args.log_in
-        known = z >= 3 and len(lr_out) >= 2 and z <= lr_out[0]
+        known = z >= 3 and len(lr_out) >= 2 and z + 3 <= lr_out[0]
         prod = n_in * (args.log_in / 2.0 + len(lr_in) - 1)
         fwd = 0.0
         for i, r in enumerate(lr_out):
             per = r / 2.0 + (1 if i + 1 < len(lr_out) else 0)
             if i == 0:
                 per -= min(z, r) / 2.0
-            frac = (1 - 2.0 ** -z) if (known and 0 < i < len(lr_out) - 1) else 1.0
+            frac = (1 - 2.0 ** -z) if (known and i > 0) else 1.0
             fwd += per * frac
         prod += n_out * fwd
         peak_mul = ctx.bench_field_mul("pallas_fq", 148 * 8, 256, 2048)
