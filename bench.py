@@ -492,6 +492,17 @@ def placeholder_extra(args, torch, ctx, dev):
     out = {"rows": n, "field": "pallas_fp", "batches": sizes,
            "note": "fri_params(1, rows_log, lambda 40, expand_factor) as test/systems/plonk/placeholder/placeholder.cpp:231; "
                    "every column opened at y, variable and permutation columns also at y*omega"}
+    # the grand product V_P of the permutation argument (permutation_argument.hpp:104-133) over the 31 permuted columns:
+    # the reference inverts once per row on the CPU; here one inversion per column through two product scans
+    try:
+        sid, ssg = rand_elems(torch, (sizes[1], n, 8), 401, dev), rand_elems(torch, (sizes[1], n, 8), 402, dev)
+        vp = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        out["permutation_grand_product"] = {
+            "columns": sizes[1], "rows": n,
+            "ms": time_cuda(torch, lambda: ctx.permutation_grand_product(F.name, cols[1], sid, ssg, 0x1234567, 0x7654321, out=vp), 5, warmup=2)}
+        del sid, ssg, vp
+    except Exception as e:
+        out["permutation_grand_product"] = {"error": repr(e)[:200]}
     for name, expand, hid in (("expand_factor_4_keccak512", 4, 2), ("expand_factor_3_keccak256", 3, 0)):
         torch.cuda.empty_cache()
         fri = FriParams.with_max_step_one(rows_log, 40, expand)

@@ -470,6 +470,47 @@ class Context:
                                                   _stream_ptr(poly, stream)), self._h)
         return out, _ints(rem)[0]
 
+    # ------------------------------------------------------------------ Placeholder permutation argument (8(f)-3)
+    def permutation_grand_product(self, field, columns, s_id, s_sigma, beta, gamma, out=None, stream=None):
+        """V_P of permutation_argument.hpp:104-133 for device tensors [ncols, n, 8] (columns in global_indices order):
+        V_P[0] = 1, V_P[j] = V_P[j-1] prod_i (c_i + beta id_i + gamma)[j-1] / prod_i (c_i + beta sigma_i + gamma)[j-1]."""
+        fid = _field_id(field)
+        c, a, b = _Buf(columns), _Buf(s_id), _Buf(s_sigma)
+        if not (c.mem == a.mem == b.mem == capi.MEM_DEVICE) or not (c.nbytes == a.nbytes == b.nbytes):
+            raise ValueError("columns, s_id and s_sigma must be device tensors of the same shape [ncols, n, 8]")
+        ncols, n = int(columns.shape[0]), int(columns.shape[1])
+        if out is None:
+            out = _empty_like(columns, (n, 8))
+        o = _Buf(out, writable=True)
+        capi.check(capi.lib().zkb_permutation_grand_product(self._h, fid, n, ncols, c.ptr, a.ptr, b.ptr, _limbs(beta, 8),
+                                                            _limbs(gamma, 8), o.ptr, _stream_ptr(columns, stream)), self._h)
+        return out
+
+    def prefix_product(self, field, x, exclusive=True, out=None, stream=None):
+        """out[i] = prod_{j<i} x[j] (exclusive, out[0] = 1) or prod_{j<=i} x[j] for a device tensor [n, 8]."""
+        fid = _field_id(field)
+        b = _Buf(x)
+        if out is None:
+            out = _empty_like(x, tuple(x.shape))
+        o = _Buf(out, writable=True)
+        if b.mem != capi.MEM_DEVICE or o.mem != capi.MEM_DEVICE:
+            raise ValueError("prefix_product works on device tensors")
+        capi.check(capi.lib().zkb_prefix_product(self._h, fid, b.nbytes // 32, b.ptr, o.ptr, 1 if exclusive else 0,
+                                                 _stream_ptr(x, stream)), self._h)
+        return out
+
+    def batch_inverse(self, field, x, out=None, stream=None):
+        """out[i] = x[i]^-1 for a device tensor [n, 8]; raises ZkbInvalidArgument if an element is zero."""
+        fid = _field_id(field)
+        b = _Buf(x)
+        if out is None:
+            out = _empty_like(x, tuple(x.shape))
+        o = _Buf(out, writable=True)
+        if b.mem != capi.MEM_DEVICE or o.mem != capi.MEM_DEVICE:
+            raise ValueError("batch_inverse works on device tensors")
+        capi.check(capi.lib().zkb_batch_inverse(self._h, fid, b.nbytes // 32, b.ptr, o.ptr, _stream_ptr(x, stream)), self._h)
+        return out
+
     # ------------------------------------------------------------------ R1CS rows (r1cs_to_qap.hpp:245-248,289-291)
     def sparse_matrix(self, field, rows, cols, row_ptr, col_idx, values, stream=None):
         return SparseMatrix(self, field, rows, cols, row_ptr, col_idx, values, stream)

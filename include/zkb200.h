@@ -269,6 +269,23 @@ int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const vo
 /* runs `iters` dependent Montgomery multiplications per thread on `threads` threads; returns field-mul/s */
 int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threads, uint32_t iters, double *muls_per_s);
 
+/* ---- multiplicative scans: the grand product of the Placeholder permutation argument ---------- */
+/* zk/snark/systems/plonk/placeholder/permutation_argument.hpp:104-133:
+ *   g_v[i] = column_i + beta S_id[i] + gamma,  h_v[i] = column_i + beta S_sigma[i] + gamma   (i < ncols, all of n rows)
+ *   V_P[0] = 1,  V_P[j] = V_P[j-1] * prod_i g_v[i][j-1] * (prod_i h_v[i][j-1]).inversed()
+ * columns / s_id / s_sigma: DEVICE, [ncols][n] canonical elements (the columns selected by global_indices, in that
+ * order); beta, gamma: host; v_out: DEVICE, n elements.  The reference inverts once per row; here one inversion serves
+ * the whole column (prefix and suffix product scans).  ZKB_ERR_INVALID_ARGUMENT if a denominator is zero (the
+ * reference's inversed() of zero is undefined). */
+int zkb_permutation_grand_product(zkb_ctx *ctx, int field, uint64_t n, uint32_t ncols, const void *columns_device,
+                                  const void *s_id_device, const void *s_sigma_device, const uint32_t *beta, const uint32_t *gamma,
+                                  void *v_out_device, void *stream);
+/* its two building blocks on DEVICE vectors of n canonical elements: out[i] = prod_{j < i} in[j] (exclusive != 0, out[0] = 1)
+ * or prod_{j <= i} in[j]; out[i] = in[i]^-1 (ZKB_ERR_INVALID_ARGUMENT if some in[i] is zero).  The lookup argument's
+ * V_L (lookup_argument.hpp) is the same pair of operations. */
+int zkb_prefix_product(zkb_ctx *ctx, int field, uint64_t n, const void *in_device, void *out_device, int exclusive, void *stream);
+int zkb_batch_inverse(zkb_ctx *ctx, int field, uint64_t n, const void *in_device, void *out_device, void *stream);
+
 /* ---- device buffers for host templates ------------------------------------------------------------ */
 /* lpc_commitment_scheme keeps its polynomials as members between commit / eval_polys / proof_eval
  * (zk/commitments/polynomial/lpc.hpp:66-200, batched_commitment.hpp:60-250: `_polys`, `_z`); a host template over this ABI

@@ -435,6 +435,72 @@ def test_lpc_full_size_proof_verifies(ctx):
     assert not fri_query.lpc_verify_eval(proof, points, commitments, params, verifier_transcript(), h, (0,), etha, fixed_values)
 
 
+# ------------------------------------------------------------------------------------------ permutation argument (8(f)-3)
+@pytest.mark.parametrize("F", [fields.PALLAS_FP, fields.BLS12_381_FR], ids=lambda f: f.name)
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 2047, 2048, 2049, 5000, 1 << 16])
+def test_prefix_product_and_batch_inverse_vs_oracle(ctx, F, n):
+    from crypto3_zk_b200 import capi
+    from oracle import placeholder
+    x = fields.random_elements(F, n, 3 + n)
+    d = dev(to_arr(x))
+    assert from_arr(host(ctx.prefix_product(F.name, d))) == placeholder.prefix_product(x, F.p)
+    assert from_arr(host(ctx.prefix_product(F.name, d, exclusive=False))) == placeholder.prefix_product(x, F.p, exclusive=False)
+    inv = from_arr(host(ctx.batch_inverse(F.name, d)))
+    if n <= 5000:
+        assert inv == placeholder.batch_inverse(x, F.p)
+    else:
+        assert all(a * b % F.p == 1 for a, b in zip(x[::97], inv[::97]))
+    if n >= 2:
+        x[n // 2] = 0
+        with pytest.raises(capi.ZkbInvalidArgument):
+            ctx.batch_inverse(F.name, dev(to_arr(x)))
+        got = from_arr(host(ctx.prefix_product(F.name, dev(to_arr(x)), exclusive=False)))      # zeros are fine for products
+        assert got[n // 2:] == [0] * (n - n // 2)
+
+
+@pytest.mark.parametrize("n,ncols", [(1, 1), (8, 2), (2048, 3), (3000, 1), (1 << 14, 4)])
+def test_permutation_grand_product_vs_oracle(ctx, n, ncols):
+    """permutation_argument.hpp:104-133 bit for bit; the last case also checks that the product closes for columns
+    that satisfy the copy constraints of a permutation of their cells (the relation the argument proves)"""
+    import random
+    from oracle import placeholder
+    F = fields.PALLAS_FP
+    p = F.p
+    cols = [fields.random_elements(F, n, 11 + i) for i in range(ncols)]
+    sid = [fields.random_elements(F, n, 21 + i) for i in range(ncols)]
+    ssg = [fields.random_elements(F, n, 31 + i) for i in range(ncols)]
+    beta, gamma = fields.random_elements(F, 2, 5)
+    if n == 1 << 14:
+        rnd = random.Random(9)
+        cells = [(i, j) for i in range(ncols) for j in range(n)]
+        perm = cells[:]
+        rnd.shuffle(perm)
+        sigma = dict(zip(cells, perm))
+        val, seen = {}, set()
+        for c in cells:
+            if c in seen:
+                continue
+            v, x = rnd.randrange(p), c
+            while x not in seen:
+                seen.add(x)
+                val[x] = v
+                x = sigma[x]
+        cols = [[val[(i, j)] for j in range(n)] for i in range(ncols)]
+        ssg = [[sid[sigma[(i, j)][0]][sigma[(i, j)][1]] for j in range(n)] for i in range(ncols)]
+
+    def t(v):
+        return dev(to_arr([x for c in v for x in c]).reshape(ncols, n, 8))
+
+    got = from_arr(host(ctx.permutation_grand_product(F.name, t(cols), t(sid), t(ssg), beta, gamma)))
+    assert got == placeholder.permutation_grand_product(cols, sid, ssg, beta, gamma, F)
+    if n == 1 << 14:
+        nom = denom = 1
+        for i in range(ncols):
+            nom = nom * (cols[i][n - 1] + beta * sid[i][n - 1] + gamma) % p
+            denom = denom * (cols[i][n - 1] + beta * ssg[i][n - 1] + gamma) % p
+        assert got[n - 1] * nom % p * pow(denom, p - 2, p) % p == 1
+
+
 # ------------------------------------------------------------------------------------------ Groth16 (config #4)
 @pytest.mark.parametrize("F", [fields.BN254_FR, fields.BLS12_381_FR], ids=lambda f: f.name)
 def test_sparse_matvec_vs_oracle(ctx, F):
