@@ -559,7 +559,8 @@ def placeholder_extra(args, torch, ctx, dev):
         if name == "expand_factor_3_keccak256":
             # the same proof with the extended evaluations retained on the device (27 GB): the query phase is a gather
             try:
-                for rit in range(2):   # the first pass lets the torch allocator obtain the 27 GB once
+                rbest = None
+                for rit in range(3):   # the first pass lets the torch allocator obtain the 27 GB once; the faster of the other two counts
                     tr = FiatShamirSequential(0, b"placeholder")
                     scheme = LpcCommitmentScheme(ctx, F.name, hid, fri, retain_lde=True)
                     for k in sizes:
@@ -587,11 +588,14 @@ def placeholder_extra(args, torch, ctx, dev):
                     scheme.proof_eval(tr, query=True)
                     torch.cuda.synchronize()
                     t_all = (time.perf_counter() - t0) * 1e3
-                    res["retain_lde"] = {"commit_ms_three_batches": t_c, "proof_eval_ms": t_all,
-                                         "proof_eval_query_phase_ms": scheme.timings["query_phase_ms"],
-                                         "ms_per_proof_with_query_phase": t_c + t_all,
-                                         "retained_bytes": sum(int(t.numel()) * 4 for t in scheme._ext.values())}
+                    cur = {"commit_ms_three_batches": t_c, "proof_eval_ms": t_all,
+                           "proof_eval_query_phase_ms": scheme.timings["query_phase_ms"],
+                           "ms_per_proof_with_query_phase": t_c + t_all,
+                           "retained_bytes": sum(int(t.numel()) * 4 for t in scheme._ext.values())}
+                    if rit >= 1 and (rbest is None or cur["ms_per_proof_with_query_phase"] < rbest["ms_per_proof_with_query_phase"]):
+                        rbest = cur
                     del scheme
+                res["retain_lde"] = rbest
             except Exception as e:
                 res["retain_lde"] = {"error": repr(e)[:200]}
         out[name] = res
