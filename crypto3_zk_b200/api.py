@@ -486,6 +486,23 @@ class Context:
                                                             _limbs(gamma, 8), o.ptr, _stream_ptr(columns, stream)), self._h)
         return out
 
+    def lookup_grand_product(self, field, inputs, values, sorted_, beta, gamma, usable_rows, out=None, stream=None):
+        """compute_V_L (lookup_argument.hpp:375-409) for device tensors reduced_input / reduced_value / sorted of shape
+        [count, n, 8]."""
+        fid = _field_id(field)
+        bufs = [_Buf(t) for t in (inputs, values, sorted_)]
+        if any(b.mem != capi.MEM_DEVICE for b in bufs):
+            raise ValueError("lookup_grand_product works on device tensors")
+        n = int(sorted_.shape[1])
+        if out is None:
+            out = _empty_like(sorted_, (n, 8))
+        o = _Buf(out, writable=True)
+        capi.check(capi.lib().zkb_lookup_grand_product(self._h, fid, n, int(usable_rows), int(inputs.shape[0]), bufs[0].ptr,
+                                                       int(values.shape[0]), bufs[1].ptr, int(sorted_.shape[0]), bufs[2].ptr,
+                                                       _limbs(beta, 8), _limbs(gamma, 8), o.ptr, _stream_ptr(sorted_, stream)),
+                   self._h)
+        return out
+
     def prefix_product(self, field, x, exclusive=True, out=None, stream=None):
         """out[i] = prod_{j<i} x[j] (exclusive, out[0] = 1) or prod_{j<=i} x[j] for a device tensor [n, 8]."""
         fid = _field_id(field)

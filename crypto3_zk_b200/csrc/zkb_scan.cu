@@ -152,6 +152,32 @@ __global__ void __launch_bounds__(256) perm_rows_kernel(uint64_t n, uint32_t nco
     den[j] = b;
 }
 
+// lookup argument, compute_V_L (lookup_argument.hpp:375-409): for row j < usable
+//   nom[j] = (1+beta)^n_in prod_i (gamma + input_i[j]) prod_i (part1 + value_i[j] + beta value_i[j+1])
+//   den[j] = prod_i (part1 + sorted_i[j] + beta sorted_i[j+1]),   part1 = (1+beta) gamma;   rows >= usable: 1
+template <class P>
+__global__ void __launch_bounds__(256) lookup_rows_kernel(uint64_t n, uint64_t usable, uint32_t n_in, const Fp<P> *__restrict__ inputs,
+                                                          uint32_t n_val, const Fp<P> *__restrict__ values, uint32_t n_sorted,
+                                                          const Fp<P> *__restrict__ sorted, Fp<P> beta_mont, Fp<P> gamma, Fp<P> part1,
+                                                          Fp<P> one_beta_pow_mont, Fp<P> *__restrict__ nom, Fp<P> *__restrict__ den) {
+    typedef Fp<P> F;
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j >= usable) {
+        nom[j] = F::one();
+        den[j] = F::one();
+        return;
+    }
+    F a = one_beta_pow_mont, b = F::one();
+    for (uint32_t i = 0; i < n_in; i++) a = a * (gamma + inputs[(uint64_t)i * n + j]).to_mont();
+    for (uint32_t i = 0; i < n_val; i++)
+        a = a * (part1 + values[(uint64_t)i * n + j] + values[(uint64_t)i * n + j + 1] * beta_mont).to_mont();
+    for (uint32_t i = 0; i < n_sorted; i++)
+        b = b * (part1 + sorted[(uint64_t)i * n + j] + sorted[(uint64_t)i * n + j + 1] * beta_mont).to_mont();
+    nom[j] = a;
+    den[j] = b;
+}
+
 template <class P>
 static int scan_run(zkb_ctx *ctx, const Fp<P> *in, uint64_t n, int reverse, int exclusive, int from_mont, Fp<P> *out, Fp<P> *total_out,
                     Fp<P> *total_inv_out, cudaStream_t st) {
@@ -250,6 +276,43 @@ static int perm_grand_product_t(zkb_ctx *ctx, uint64_t n, uint32_t ncols, const 
     return scan_run<P>(ctx, ratio, n, 0, 1, 1, (F *)v_out, nullptr, nullptr, st);
 }
 
+template <class P>
+static bool scan_canonical(const Fp<P> &x) {
+    for (int i = Fp<P>::N - 1; i >= 0; i--) {
+        if (x.l[i] < P::mod(i)) return true;
+        if (x.l[i] > P::mod(i)) return false;
+    }
+    return false;
+}
+
+template <class P>
+static int lookup_grand_product_t(zkb_ctx *ctx, uint64_t n, uint64_t usable, uint32_t n_in, const void *inputs, uint32_t n_val,
+                                  const void *values, uint32_t n_sorted, const void *sorted, const uint32_t *beta,
+                                  const uint32_t *gamma, void *v_out, cudaStream_t st) {
+    typedef Fp<P> F;
+    F b, g;
+    memcpy(b.l, beta, sizeof(b.l));
+    memcpy(g.l, gamma, sizeof(g.l));
+    if (!scan_canonical<P>(b) || !scan_canonical<P>(g)) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "beta / gamma >= modulus");
+    const F bm = b.to_mont(), one_beta = F::one() + bm;               // Montgomery
+    const F part1 = (one_beta * g.to_mont()).from_mont();             // canonical (1 + beta) gamma
+    const F pw = one_beta.pow_u64(n_in);                              // Montgomery (1 + beta)^n_in
+    void *p;
+    ZKB_TRY(ctx_scratch(ctx, "perm_rows", (size_t)3 * n * sizeof(F), &p));
+    F *nom = (F *)p, *den = nom + n, *ratio = den + n;
+    lookup_rows_kernel<P><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, usable, n_in, (const F *)inputs, n_val, (const F *)values, n_sorted,
+                                                                      (const F *)sorted, bm, g, part1, pw, nom, den);
+    ctx->launches++;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    bool zero = false;
+    ZKB_TRY(batch_inverse_mont<P>(ctx, den, nom, n, 0, ratio, &zero, st));
+    if (zero) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "lookup grand product: a denominator is zero");
+    ZKB_TRY(scan_run<P>(ctx, ratio, n, 0, 1, 1, (F *)v_out, nullptr, nullptr, st));
+    // V_L[k] stays zero beyond the usable rows (the polynomial is created zero-filled, :382-383)
+    if (usable + 1 < n) ZKB_CUDA_OK(ctx, cudaMemsetAsync((F *)v_out + usable + 1, 0, (size_t)(n - usable - 1) * sizeof(F), st));
+    return ZKB_OK;
+}
+
 #define ZKB_DISPATCH_SCAN_FIELD(field, FN, ...)                                  \
     switch (field) {                                                             \
         case ZKB_FIELD_BLS12_381_FR: return FN<params::Bls12381Fr>(__VA_ARGS__); \
@@ -270,7 +333,25 @@ static int perm_dispatch(zkb_ctx *ctx, int field, uint64_t n, uint32_t ncols, co
     ZKB_DISPATCH_SCAN_FIELD(field, perm_grand_product_t, ctx, n, ncols, cols, sid, ssigma, beta, gamma, v_out, st)
 }
 
+static int lookup_dispatch(zkb_ctx *ctx, int field, uint64_t n, uint64_t usable, uint32_t n_in, const void *inputs, uint32_t n_val,
+                           const void *values, uint32_t n_sorted, const void *sorted, const uint32_t *beta, const uint32_t *gamma,
+                           void *v_out, cudaStream_t st) {
+    ZKB_DISPATCH_SCAN_FIELD(field, lookup_grand_product_t, ctx, n, usable, n_in, inputs, n_val, values, n_sorted, sorted, beta, gamma, v_out, st)
+}
+
 extern "C" {
+
+int zkb_lookup_grand_product(zkb_ctx *ctx, int field, uint64_t n, uint64_t usable_rows, uint32_t n_inputs, const void *inputs_device,
+                             uint32_t n_values, const void *values_device, uint32_t n_sorted, const void *sorted_device,
+                             const uint32_t *beta, const uint32_t *gamma, void *v_out_device, void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    if (field < ZKB_FIELD_BLS12_381_FR || field > ZKB_FIELD_PALLAS_FQ || n == 0 || usable_rows >= n || !beta || !gamma || !v_out_device ||
+        (n_inputs && !inputs_device) || (n_values && !values_device) || (n_sorted && !sorted_device))
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_lookup_grand_product: bad arguments (usable_rows must be < n)");
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return lookup_dispatch(ctx, field, n, usable_rows, n_inputs, inputs_device, n_values, values_device, n_sorted, sorted_device, beta, gamma,
+                           v_out_device, (cudaStream_t)stream);
+}
 
 int zkb_prefix_product(zkb_ctx *ctx, int field, uint64_t n, const void *in_device, void *out_device, int exclusive, void *stream) {
     if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;

@@ -280,6 +280,15 @@ int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threa
 int zkb_permutation_grand_product(zkb_ctx *ctx, int field, uint64_t n, uint32_t ncols, const void *columns_device,
                                   const void *s_id_device, const void *s_sigma_device, const uint32_t *beta, const uint32_t *gamma,
                                   void *v_out_device, void *stream);
+/* compute_V_L of the lookup argument (zk/snark/systems/plonk/placeholder/lookup_argument.hpp:375-409): V_L[0] = 1 and for
+ * k = 1 .. usable_rows (< n)
+ *   V_L[k] = V_L[k-1] (1+beta)^n_inputs prod_i (gamma + input_i[k-1]) prod_i (part1 + value_i[k-1] + beta value_i[k])
+ *                     / prod_i (part1 + sorted_i[k-1] + beta sorted_i[k]),        part1 = (1 + beta) gamma,
+ * V_L[k] = 0 for k > usable_rows.  inputs / values / sorted: DEVICE, [count][n] canonical elements (reduced_input,
+ * reduced_value, sorted); v_out: DEVICE, n elements. */
+int zkb_lookup_grand_product(zkb_ctx *ctx, int field, uint64_t n, uint64_t usable_rows, uint32_t n_inputs, const void *inputs_device,
+                             uint32_t n_values, const void *values_device, uint32_t n_sorted, const void *sorted_device,
+                             const uint32_t *beta, const uint32_t *gamma, void *v_out_device, void *stream);
 /* its two building blocks on DEVICE vectors of n canonical elements: out[i] = prod_{j < i} in[j] (exclusive != 0, out[0] = 1)
  * or prod_{j <= i} in[j]; out[i] = in[i]^-1 (ZKB_ERR_INVALID_ARGUMENT if some in[i] is zero).  The lookup argument's
  * V_L (lookup_argument.hpp) is the same pair of operations. */

@@ -36,3 +36,23 @@ def prefix_product(x, p, exclusive=True):
 
 def batch_inverse(x, p):
     return [pow(v, p - 2, p) for v in x]
+
+
+def lookup_grand_product(reduced_input, reduced_value, sorted_, beta, gamma, usable_rows, field):
+    """compute_V_L, lookup_argument.hpp:375-409 (lists of n-value lists)"""
+    p = field.p
+    n = len(sorted_[0])
+    V = [0] * n
+    V[0] = 1
+    part1 = (1 + beta) * gamma % p
+    for k in range(1, usable_rows + 1):
+        g_tmp = pow(1 + beta, len(reduced_input), p)
+        for col in reduced_input:
+            g_tmp = g_tmp * (gamma + col[k - 1]) % p
+        for col in reduced_value:
+            g_tmp = g_tmp * (part1 + col[k - 1] + beta * col[k]) % p
+        h_tmp = 1
+        for col in sorted_:
+            h_tmp = h_tmp * (part1 + col[k - 1] + beta * col[k]) % p
+        V[k] = V[k - 1] * g_tmp % p * pow(h_tmp, p - 2, p) % p
+    return V

@@ -501,6 +501,25 @@ def test_permutation_grand_product_vs_oracle(ctx, n, ncols):
         assert got[n - 1] * nom % p * pow(denom, p - 2, p) % p == 1
 
 
+@pytest.mark.parametrize("n,usable,counts", [(8, 5, (1, 1, 2)), (64, 63, (2, 1, 3)), (4096, 4000, (3, 2, 5)), (1 << 14, (1 << 14) - 3, (1, 1, 2))])
+def test_lookup_grand_product_vs_oracle(ctx, n, usable, counts):
+    """compute_V_L (lookup_argument.hpp:375-409) bit for bit, including the zero tail beyond the usable rows"""
+    from oracle import placeholder
+    F = fields.BLS12_381_FR
+    ni, nv, ns = counts
+    inp = [fields.random_elements(F, n, 41 + i) for i in range(ni)]
+    val = [fields.random_elements(F, n, 51 + i) for i in range(nv)]
+    srt = [fields.random_elements(F, n, 61 + i) for i in range(ns)]
+    beta, gamma = fields.random_elements(F, 2, 8)
+
+    def t(v):
+        return dev(to_arr([x for c in v for x in c]).reshape(len(v), n, 8))
+
+    got = from_arr(host(ctx.lookup_grand_product(F.name, t(inp), t(val), t(srt), beta, gamma, usable)))
+    want = placeholder.lookup_grand_product(inp, val, srt, beta, gamma, usable, F)
+    assert got == want and got[usable + 1:] == [0] * (n - usable - 1)
+
+
 # ------------------------------------------------------------------------------------------ Groth16 (config #4)
 @pytest.mark.parametrize("F", [fields.BN254_FR, fields.BLS12_381_FR], ids=lambda f: f.name)
 def test_sparse_matvec_vs_oracle(ctx, F):
