@@ -557,6 +557,26 @@ class Context:
                                               _stream_ptr(scalars, stream)), self._h)
         return res
 
+    def batch_exp(self, curve, base, scalars, stream=None):
+        """algebra::batch_exp (generator.hpp:187-225): scalars[i] * base for one affine base (Python ints, (c0, c1) pairs
+        on the G2 groups) and a [n, 8] scalar array / device tensor.  Returns affine points [n, 2, coord_limbs] in the
+        memory space of `scalars` (zero scalar -> all-zero point)."""
+        c = _curve(curve)
+        cl = coord_limbs(c)
+        parts = []
+        for k in range(2):
+            comp = base[k] if c.deg == 2 else (base[k],)
+            h = cl // len(comp)
+            for v in comp:
+                parts += [(int(v) >> (32 * l)) & 0xFFFFFFFF for l in range(h)]
+        b = (ctypes.c_uint32 * (2 * cl))(*parts)
+        sb = _Buf(scalars)
+        n = sb.nbytes // 32
+        out = _empty_like(scalars, (n, 2, cl))
+        o = _Buf(out, writable=True)
+        capi.check(capi.lib().zkb_batch_exp(self._h, c.cid, n, b, sb.ptr, o.ptr, sb.mem, _stream_ptr(scalars, stream)), self._h)
+        return out
+
     def grid_points(self, curve, n, table_a, table_b, stream=None):
         """Synthetic bases on the device: out[i] = table_a[i % m] + table_b[i // m] (torch int32 [n,2,cl])."""
         import torch

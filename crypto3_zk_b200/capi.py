@@ -23,7 +23,7 @@ SYMBOLS = [
     "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul",
     "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
     "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec", "zkb_pow_grind", "zkb_merkle_paths", "zkb_poly_evaluate_pm",
-    "zkb_lde_with_coefficients", "zkb_permutation_grand_product", "zkb_lookup_grand_product", "zkb_prefix_product", "zkb_batch_inverse", "zkb_buf_alloc", "zkb_buf_free", "zkb_buf_copy", "zkb_buf_zero", "zkb_gather",
+    "zkb_lde_with_coefficients", "zkb_batch_exp", "zkb_permutation_grand_product", "zkb_lookup_grand_product", "zkb_prefix_product", "zkb_batch_inverse", "zkb_buf_alloc", "zkb_buf_free", "zkb_buf_copy", "zkb_buf_zero", "zkb_gather",
 ]
 POLY_COEFFICIENTS, POLY_DFS = 0, 1
 # int (*zkb_fri_challenge_fn)(void *user, uint32_t round, const uint8_t *root, uint32_t root_bytes, uint32_t count, uint32_t *alphas_out)
@@ -110,6 +110,7 @@ def lib():
     L.zkb_sparse_matvec.argtypes = [vp, vp, vp, i, vp, vp]
     L.zkb_merkle_paths.argtypes = [vp, vp, u32, ctypes.POINTER(u64), u8p, vp]
     L.zkb_lde_with_coefficients.argtypes = [vp, i, i, i, u32, vp, vp, vp, vp]
+    L.zkb_batch_exp.argtypes = [vp, i, u64, u32p, vp, vp, i, vp]
     L.zkb_permutation_grand_product.argtypes = [vp, i, u64, u32, vp, vp, vp, u32p, u32p, vp, vp]
     L.zkb_lookup_grand_product.argtypes = [vp, i, u64, u64, u32, vp, u32, vp, u32, vp, u32p, u32p, vp, vp]
     L.zkb_prefix_product.argtypes = [vp, i, u64, vp, vp, i, vp]

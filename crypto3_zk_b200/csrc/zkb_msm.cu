@@ -669,6 +669,51 @@ static int grid_points_t(zkb_ctx *ctx, uint64_t n, uint32_t m, const void *dA, c
     return ZKB_OK;
 }
 
+// ------------------------------------------------------------------------------------ fixed-base batch exponentiation
+// algebra::batch_exp<G, Fr>(scalar_size, window, table, v) / windowed_exp as the Groth16 generator calls them
+// (r1cs_gg_ppzksnark/generator.hpp:167-225, knowledge_commitment_multiexp.hpp:110-205): out[i] = v_i * base for one
+// base and many scalars.  Table: d * 2^(8 w) * base for the 32 byte windows of a 256-bit scalar, d = 1 .. 255 (one thread
+// per entry: doublings to its window, double-and-add over the byte, one inversion - the table is affine so the main pass
+// uses mixed additions).  Main pass: one thread per scalar, at most 32 mixed additions and one inversion to hand back
+// affine points (the form every consumer here takes).  Setup-time operation: no bucket machinery.
+#define BEXP_WINDOWS 32
+template <class F>
+__global__ void __launch_bounds__(128) batch_exp_table_kernel(Affine<F> base_mont, Affine<F> *__restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BEXP_WINDOWS * 255) return;
+    const uint32_t w = i / 255, d = i % 255 + 1;
+    XYZZ<F> b = XYZZ<F>::from_affine(base_mont);
+    for (uint32_t k = 0; k < 8 * w; k++) b = b.dbl();
+    table[i] = b.mul_small(d).to_affine();
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) batch_exp_kernel(uint64_t n, const uint32_t *__restrict__ scalars,
+                                                        const Affine<F> *__restrict__ table, Affine<F> *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (int w = 0; w < BEXP_WINDOWS; w++) {
+        const uint32_t d = (scalars[i * 8 + w / 4] >> (8 * (w % 4))) & 0xffu;
+        if (d) acc.add_mixed(table[w * 255 + d - 1]);
+    }
+    out[i] = acc.to_affine().from_mont();      // infinity -> the all-zero encoding
+}
+
+template <class F>
+static int batch_exp_t(zkb_ctx *ctx, uint64_t n, const uint32_t *base_affine, const void *d_scalars, void *d_out, cudaStream_t st) {
+    typedef Affine<F> A;
+    A base;
+    memcpy(&base, base_affine, sizeof(A));
+    void *tab;
+    ZKB_TRY(ctx_scratch(ctx, "bexp_table", (size_t)BEXP_WINDOWS * 255 * sizeof(A), &tab));
+    batch_exp_table_kernel<F><<<(BEXP_WINDOWS * 255 + 127) / 128, 128, 0, st>>>(base.to_mont(), (A *)tab);
+    batch_exp_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, (const uint32_t *)d_scalars, (const A *)tab, (A *)d_out);
+    ctx->launches += 2;
+    ZKB_CUDA_OK(ctx, cudaGetLastError());
+    return ZKB_OK;
+}
+
 // ------------------------------------------------------------------------------------ window table
 // table[w * n + i] = 2^(c w) P_i for w = 1 .. W-1 (affine, Montgomery form; row 0 is a copy of the bases).
 // A commitment key / proving-key query vector is long-lived, so this is paid once: afterwards every digit
@@ -717,6 +762,35 @@ static int msm_table_t(zkb_ctx *ctx, zkb_msm_bases *b, int c, uint64_t max_bytes
 
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" {
+
+int zkb_batch_exp(zkb_ctx *ctx, int curve, uint64_t n, const uint32_t *base_affine, const void *scalars, void *out_affine, int mem,
+                  void *stream) {
+    if (!ctx) return ZKB_ERR_INVALID_ARGUMENT;
+    int cl = curve_coord_limbs(curve);
+    if (!cl || !base_affine || (n && (!scalars || !out_affine))) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_batch_exp: bad arguments");
+    if (n == 0) return ZKB_OK;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pb = (size_t)2 * cl * 4;
+    const void *d_sc = scalars;
+    void *d_out = out_affine;
+    if (mem != ZKB_MEM_DEVICE) {
+        void *p, *q;
+        ZKB_TRY(ctx_scratch(ctx, "io_in", n * 32, &p));
+        ZKB_TRY(ctx_scratch(ctx, "io_out", n * pb, &q));
+        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+        d_sc = p;
+        d_out = q;
+    }
+    int s = ZKB_ERR_INVALID_ARGUMENT;
+    ZKB_DISPATCH_CURVE(curve, s = batch_exp_t<CF>(ctx, n, base_affine, d_sc, d_out, st))
+    ZKB_TRY(s);
+    if (mem != ZKB_MEM_DEVICE) {
+        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(out_affine, d_out, n * pb, cudaMemcpyDeviceToHost, st));
+        ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    }
+    return ZKB_OK;
+}
 
 int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const void *table_a, const void *table_b,
                        void *out_device, void *stream) {

@@ -269,6 +269,15 @@ int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const vo
 /* runs `iters` dependent Montgomery multiplications per thread on `threads` threads; returns field-mul/s */
 int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threads, uint32_t iters, double *muls_per_s);
 
+/* ---- fixed-base batch exponentiation: the Groth16 generator ----------------------------------- */
+/* algebra::batch_exp<G, Fr>(scalar_size, window, table, v) and the windowed_exp calls of kc_batch_exp
+ * (zk/snark/systems/ppzksnark/r1cs_gg_ppzksnark/generator.hpp:167-225,
+ *  zk/commitments/polynomial/knowledge_commitment_multiexp.hpp:110-205): out[i] = scalars[i] * base, affine; a zero scalar
+ * gives the point at infinity (all-zero encoding - kc_batch_exp skips those entries, :129).  base_affine: host, (x || y)
+ * canonical limbs; scalars / out: host or device by `mem`, n x 8 limbs / n points.  G1 and G2 curves. */
+int zkb_batch_exp(zkb_ctx *ctx, int curve, uint64_t n, const uint32_t *base_affine, const void *scalars, void *out_affine, int mem,
+                  void *stream);
+
 /* ---- multiplicative scans: the grand product of the Placeholder permutation argument ---------- */
 /* zk/snark/systems/plonk/placeholder/permutation_argument.hpp:104-133:
  *   g_v[i] = column_i + beta S_id[i] + gamma,  h_v[i] = column_i + beta S_sigma[i] + gamma   (i < ncols, all of n rows)

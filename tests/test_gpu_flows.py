@@ -520,6 +520,27 @@ def test_lookup_grand_product_vs_oracle(ctx, n, usable, counts):
     assert got == want and got[usable + 1:] == [0] * (n - usable - 1)
 
 
+@pytest.mark.parametrize("cname", ["bls12_381_g1", "bn254_g1", "pallas", "bn254_g2", "bls12_381_g2"])
+def test_batch_exp_vs_oracle(ctx, cname):
+    """algebra::batch_exp / windowed_exp of the Groth16 generator (generator.hpp:167-225): scalar * base for many scalars,
+    affine, bit for bit; zero, one, p-1 and single-byte scalars included; host and device buffers"""
+    from oracle import curves
+    C = {"bls12_381_g1": curves.BLS12_381_G1, "bn254_g1": curves.BN254_G1, "pallas": curves.PALLAS,
+         "bn254_g2": curves.BN254_G2, "bls12_381_g2": curves.BLS12_381_G2}[cname]
+    r = C.scalar_field.p
+    sc = [0, 1, 2, r - 1, 255, 256, 1 << 248, (1 << 64) - 1] + fields.random_elements(C.scalar_field, 40, 3)
+    base = C.mul(C.gen, 5)
+    want = [C.mul(base, k) for k in sc]
+    cl = C.coord_limbs32
+    for arr in (to_arr(sc), dev(to_arr(sc))):
+        got = ctx.batch_exp(cname, base, arr)
+        g = host(got) if not isinstance(got, np.ndarray) else got
+        from crypto3_zk_b200.api import _affine_from_limbs
+        deg = 2 if cname.endswith("g2") else 1
+        pts = [_affine_from_limbs(g[i].reshape(-1), cl, deg) for i in range(len(sc))]
+        assert pts == want
+
+
 # ------------------------------------------------------------------------------------------ Groth16 (config #4)
 @pytest.mark.parametrize("F", [fields.BN254_FR, fields.BLS12_381_FR], ids=lambda f: f.name)
 def test_sparse_matvec_vs_oracle(ctx, F):
