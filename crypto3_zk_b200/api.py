@@ -215,6 +215,21 @@ class Context:
         except Exception:
             pass
 
+    def workspace(self, name, shape):
+        """A cached int32 device tensor of this shape, owned by the context and reused by later calls under the same name:
+        a prover that builds one proof after another should not go back to the allocator for its multi-GB temporaries
+        (a cudaMalloc inside a commit costs tens of milliseconds now and then).  Contents are undefined."""
+        import torch
+        if not hasattr(self, "_ws"):
+            self._ws = {}
+        shape = tuple(int(v) for v in shape)
+        t = self._ws.get(name)
+        if t is None or tuple(t.shape) != shape:
+            self._ws[name] = None
+            t = torch.empty(shape, dtype=torch.int32, device="cuda:%d" % self.device)
+            self._ws[name] = t
+        return t
+
     def kernel_launches(self):
         return int(capi.lib().zkb_ctx_kernel_launches(self._h))
 

@@ -57,6 +57,7 @@ class LpcCommitmentScheme:
         self._ext = {}
         self._commit_coeffs = {}
         self._cache = {}
+        self._whole = {}
         self.F = FIELD_BY_NAME[field] if isinstance(field, str) else field
         self._polys = {}       # batch index -> list of [n, 8] device tensors (same n within a batch)
         self._points = {}      # batch index -> list (per polynomial) of point lists
@@ -73,6 +74,8 @@ class LpcCommitmentScheme:
         if self._locked.get(index):
             raise RuntimeError("batch %d is already committed" % index)
         t = poly if poly.dim() == 3 else poly.unsqueeze(0)
+        # a batch handed over as one [count, n, 8] tensor is used as it is (no re-stacking copy per commit / eval_polys)
+        self._whole[index] = t.contiguous() if index not in self._polys else None
         for i in range(t.shape[0]):
             self._polys.setdefault(index, []).append(t[i])
 
@@ -92,7 +95,9 @@ class LpcCommitmentScheme:
         n = polys[0].shape[0]
         if any(p.shape[0] != n for p in polys):
             raise ValueError("polynomials of one batch must have the same size")
-        return torch.stack(polys).contiguous(), n
+        if self._whole.get(index) is None:
+            self._whole[index] = torch.stack(polys).contiguous()
+        return self._whole[index], n
 
     # ---- lpc_commitment_scheme (lpc.hpp:95-111)
     def commit(self, index):
@@ -129,8 +134,7 @@ class LpcCommitmentScheme:
                 co, n = self._commit_coeffs[k]
             else:
                 batch, n = self._batch_tensor(k)
-                import torch
-                co = torch.empty_like(batch)
+                co = self.ctx.workspace("lpc_coeffs_%d" % k, batch.shape)     # valid until the next proof on this context
                 self.ctx.ntt(self.F.name, batch, n.bit_length() - 1, inverse=True, out=co)
             self._coeffs[k] = (co, n)
             union = []
@@ -167,9 +171,9 @@ class LpcCommitmentScheme:
         theta_acc = 1
         n_max = max(n for _, n in self._coeffs.values())
         dev = next(iter(self._coeffs.values()))[0].device
-        combined = torch.zeros((n_max, 8), dtype=torch.int32, device=dev)
-        numer = torch.empty((n_max, 8), dtype=torch.int32, device=dev)
-        quot = torch.empty((n_max, 8), dtype=torch.int32, device=dev)
+        combined = self.ctx.workspace("lpc_combined", (n_max, 8)).zero_()
+        numer = self.ctx.workspace("lpc_numer", (n_max, 8))
+        quot = self.ctx.workspace("lpc_quot", (n_max, 8))
         remainders = []
 
         def add_quotient(point, terms):
@@ -210,7 +214,7 @@ class LpcCommitmentScheme:
         # combined_Q.from_coefficients(combined_Q_normal) and precommit's resize to D[0]: the same polynomial
         # evaluated on D[0] - one forward NTT of the zero-padded coefficients
         nd = 1 << self.fri.log_d0
-        q_d0 = torch.zeros((1, nd, 8), dtype=torch.int32, device=dev)
+        q_d0 = self.ctx.workspace("lpc_q_d0", (1, nd, 8)).zero_()
         q_d0[0, :n_max] = combined
         self.ctx.ntt(self.F.name, q_d0, self.fri.log_d0)
         fri = self.ctx.fri_commit_phase(
