@@ -141,12 +141,13 @@ __global__ void __launch_bounds__(256) perm_rows_kernel(uint64_t n, uint32_t nco
     if (j >= n) return;
     F a = F::one(), b = F::one();
     for (uint32_t i = 0; i < ncols; i++) {
-        // canonical x times Montgomery beta is the canonical product; one to_mont per factor afterwards
+        // canonical x times Montgomery beta is the canonical product.  The canonical factors go into the Montgomery products
+        // as they are: that scales nom and den by the same R^-ncols, which cancels in nom / den - no to_mont per factor.
         F c = cols[(uint64_t)i * n + j];
         F g = c + sid[(uint64_t)i * n + j] * beta + gamma;
         F h = c + ssigma[(uint64_t)i * n + j] * beta + gamma;
-        a = a * g.to_mont();
-        b = b * h.to_mont();
+        a = a * g;
+        b = b * h;
     }
     nom[j] = a;
     den[j] = b;
