@@ -346,6 +346,49 @@ typename std::iterator_traits<BaseIt>::value_type multiexp_with_mixed_addition(B
                                                                                ScalarIt s1, std::size_t chunks) {
     return multiexp<Method>(b0, b1, s0, s1, chunks);
 }
+
+// Fixed-base batch exponentiation of the Groth16 generator (r1cs_gg_ppzksnark/generator.hpp:167-225): upstream builds a
+// window table on the host (get_window_table) and calls batch_exp(scalar_size, window, table, v); here the table lives on
+// the device inside zkb_batch_exp (32 byte windows), so window_table only carries the base point.
+template <class GroupType>
+struct window_table {
+    typename GroupType::value_type base;
+};
+template <class GroupType>
+std::size_t get_exp_window_size(std::size_t) { return 8; }
+template <class GroupType>
+window_table<GroupType> get_window_table(std::size_t /*scalar_size*/, std::size_t /*window*/, const typename GroupType::value_type &g) {
+    window_table<GroupType> t;
+    t.base = g;
+    return t;
+}
+// v[i] * table.base for every i (zero scalars give the group's zero)
+template <class GroupType, class FieldType>
+std::vector<typename GroupType::value_type> batch_exp(std::size_t /*scalar_size*/, std::size_t /*window*/,
+                                                      const window_table<GroupType> &table,
+                                                      const std::vector<typename FieldType::value_type> &v) {
+    typedef typename GroupType::base_field_type BF;
+    constexpr int CL = BF::limbs32;
+    std::vector<typename GroupType::value_type> out(v.size(), GroupType::value_type::zero());
+    if (v.empty() || table.base.is_zero()) return out;
+    std::uint32_t base[2 * 24] = {0};
+    auto a = table.base.to_affine();
+    a.X.to_canonical_limbs(base);
+    a.Y.to_canonical_limbs(base + CL);
+    std::vector<std::uint32_t> sc(v.size() * 8), res(v.size() * 2 * CL);
+    for (std::size_t i = 0; i < v.size(); i++) v[i].to_canonical_limbs(&sc[8 * i]);
+    zkb_ctx *ctx = zkb_detail::context();
+    zkb_detail::check(zkb_batch_exp(ctx, GroupType::curve_id, v.size(), base, sc.data(), res.data(), ZKB_MEM_HOST, nullptr), ctx,
+                      "zkb_batch_exp");
+    for (std::size_t i = 0; i < v.size(); i++) {
+        bool inf = true;
+        for (int k = 0; k < 2 * CL; k++) inf = inf && res[i * 2 * CL + k] == 0;
+        if (!inf)
+            out[i] = GroupType::value_type::from_affine(BF::value_type::from_canonical_limbs(&res[i * 2 * CL]),
+                                                        BF::value_type::from_canonical_limbs(&res[i * 2 * CL + CL]));
+    }
+    return out;
+}
 }  // namespace algebra
 
 // ========================================================================================== math

@@ -308,6 +308,29 @@ static void lpc_scheme_test() {
     std::printf("\n");
 }
 
+// algebra::batch_exp as the Groth16 generator uses it (generator.hpp:167-225): v_i * G for a vector of scalars must agree
+// with the multiexp over the single base G (and with 0 * G = zero, 1 * G = G)
+template <class Curve>
+static void batch_exp_test() {
+    typedef typename Curve::template g1_type<> g1_type;
+    typedef typename Curve::scalar_field_type field_type;
+    typedef typename field_type::value_type fr;
+    auto G = g1_type::value_type::one();
+    std::size_t window = algebra::get_exp_window_size<g1_type>(5);
+    auto table = algebra::get_window_table<g1_type>(field_type::modulus_bits, window, G);
+    std::vector<fr> v = {fr(0), fr(1), fr(2), fr(123456789), -fr(1), fr(0xFFFFFFFFFFFFFFFFull) * fr(0xFFFFFFFFFFFFFFFFull)};
+    auto out = algebra::batch_exp<g1_type, field_type>(field_type::modulus_bits, window, table, v);
+    CHECK(out.size() == v.size());
+    CHECK(out[0].is_zero());
+    CHECK(out[1] == G);
+    std::vector<typename g1_type::value_type> gen = {G};
+    algebra::multiexp_bases<g1_type> B(gen.begin(), gen.end());
+    for (std::size_t i = 0; i < v.size(); i++) {
+        std::vector<fr> s = {v[i]};
+        CHECK(out[i] == B.multiexp(0, s.begin(), s.end()));
+    }
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !std::strcmp(argv[1], "compile-only")) {
         transcript_and_grinding_test(false);   // host-only part: transcript known answers
@@ -327,6 +350,8 @@ int main(int argc, char **argv) {
         domain_and_fold_test<algebra::fields::pallas_base_field>();
         domain_and_fold_test<algebra::fields::pallas_scalar_field>();
         transcript_and_grinding_test(true);
+        batch_exp_test<algebra::curves::bls12<381>>();
+        batch_exp_test<algebra::curves::alt_bn128<254>>();
         lpc_scheme_test();
         precommit_root();
     } catch (const std::exception &e) {
