@@ -81,7 +81,9 @@ class LpcCommitmentScheme:
 
     def append_eval_point(self, batch, point, poly=None):
         """(batch, point): every polynomial of the batch; (batch, poly, point): one polynomial."""
-        pts = self._points.setdefault(batch, [[] for _ in self._polys[batch]])
+        if batch not in self._points:      # a prover-side batch; a verifier calls set_batch_size first
+            self._points[batch] = [[] for _ in self._polys[batch]]
+        pts = self._points[batch]
         targets = range(len(pts)) if poly is None else [poly]
         for i in targets:
             pts[i].append(int(point) % self.F.p)
@@ -229,6 +231,14 @@ class LpcCommitmentScheme:
             out["proof"] = {"z": self.z, "fri_proof": self._query_phase(transcript, fri)}
             self.timings["query_phase_ms"] = (time.perf_counter() - t0) * 1e3
         return out
+
+    # ---- verify_eval (lpc.hpp:202-263): host code, like the reference's; a verifier-side scheme only needs
+    # set_batch_size / append_eval_point (and setup for fixed batches) before this call
+    def verify_eval(self, proof, commitments, transcript):
+        from . import lpc_verify
+        fixed = tuple(k for k, v in self._fixed.items() if v)
+        return lpc_verify.lpc_verify_eval(self.F, self.hash_id, self.fri, proof, self._points, commitments, transcript,
+                                          fixed, self._etha, self._fixed_values)
 
     # ---- grinding + query phase of zk::algorithms::proof_eval<FRI> (basic_fri.hpp:743-915)
     def _domain_index(self, x, log_n):

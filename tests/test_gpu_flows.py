@@ -429,6 +429,10 @@ def test_lpc_full_size_proof_verifies(ctx):
     tv = verifier_transcript()
     assert fri_query.lpc_verify_eval(proof, points, commitments, params, tv, h, (0,), etha, fixed_values)
     assert tv.state == t_prover.state
+    # and by the product's own host verifier (lpc.hpp:202-263), through the scheme object
+    t_own = FiatShamirSequential(hid, b"full-size")
+    t_own.state = tr.state
+    assert scheme.verify_eval(proof, commitments, t_own) and t_own.state == t_prover.state
     q0 = proof["fri_proof"]["query_proofs"][0]
     v = q0["initial_proof"][1]["values"][2][0]
     v[1] = (v[1] + 1) % p
