@@ -1,0 +1,306 @@
+"""Groth16 proof / verification-key wire format for BLS12-381 (host side only - no device work).
+
+Mirrors `verifier_input_serializer_tvm` / `verifier_input_deserializer_tvm<r1cs_gg_ppzksnark<bls12<381>>>`
+(zk/snark/systems/ppzksnark/r1cs_gg_ppzksnark/marshalling.hpp:100-890 reader, :897-1258 writer):
+
+  std::size_t      4 bytes big-endian                           (:465-491, :975-985)
+  Fr / Fp element  fixed width ceil(modulus_bits / 8) = 32 / 48 bytes, LEAST significant byte first
+                   (export_bits(..., 8, false), :921-935)
+  Fp2/Fp6/Fp12     the coefficients data[0], data[1], ... in order, recursively (:937-949)
+  G1 / G2 point    48 / 96 bytes, `curve_element_serializer<bls12<381>>::point_to_octets_compress` (:951-973)
+  proof            g_A (G1) | g_B (G2) | g_C (G1) = 192 bytes     (:784-828)
+  primary input    count | count x Fr                            (:740-782)
+  sparse_vector    count | count x index | count x G1 | domain_size   (:493-569)
+  accumulation_vector  first (G1) | rest (sparse_vector)         (:571-598)
+  verification key alpha_g1_beta_g2 (Fp12, 576 B) | gamma_g2 | delta_g2 | gamma_ABC_g1   (:600-653)
+  verifier input   proof | primary input | verification key      (:830-890)
+
+`curve_element_serializer` lives in crypto3-algebra (not vendored in the reference).  It implements the ZCash
+BLS12-381 encoding: x big-endian (for G2: x.c1 then x.c0), bit 7 of byte 0 = compressed, bit 6 = point at
+infinity, bit 5 = y is the lexicographically larger of (y, -y) (for Fp2: compare c1, then c0 when c1 == 0).
+The reference's tests hold no byte vector of this format; tests/test_marshalling.py pins it on the published
+encodings of the two generators.
+
+Error behaviour follows the reader: a short buffer raises `NotEnoughData` (status_type::not_enough_data), a
+non-canonical field element or an x with no point on the curve raises `InvalidMsgData`
+(status_type::invalid_msg_data).  Points are affine (x, y) integers ((c0, c1) pairs on G2), None = infinity, as
+in groth16.py.
+"""
+from .fields import FIELD_BY_NAME
+
+P = FIELD_BY_NAME["bls12_381_fq"].p
+R = FIELD_BY_NAME["bls12_381_fr"].p
+
+SIZE_T_BYTES = 4
+FR_BYTES = 32
+FP_BYTES = 48
+G1_BYTES = 48
+G2_BYTES = 96
+GT_BYTES = 2 * 3 * 2 * FP_BYTES
+PROOF_BYTES = G1_BYTES + G2_BYTES + G1_BYTES
+
+_C_BIT, _I_BIT, _S_BIT = 0x80, 0x40, 0x20
+_HALF = (P - 1) // 2
+
+
+class MarshallingError(ValueError):
+    pass
+
+
+class NotEnoughData(MarshallingError):
+    """status_type::not_enough_data"""
+
+
+class InvalidMsgData(MarshallingError):
+    """status_type::invalid_msg_data"""
+
+
+def _need(buf, off, n):
+    if len(buf) - off < n:
+        raise NotEnoughData("need %d bytes at offset %d, have %d" % (n, off, len(buf) - off))
+
+
+# ---- Fp2 helpers for the decompression (u^2 = -1)
+def _f2_mul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def _f2_pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = _f2_mul(r, a)
+        a = _f2_mul(a, a)
+        e >>= 1
+    return r
+
+
+def _f2_sqrt(a):
+    """square root in Fp2 for p = 3 mod 4, or None"""
+    if a == (0, 0):
+        return (0, 0)
+    a1 = _f2_pow(a, (P - 3) // 4)
+    alpha = _f2_mul(_f2_mul(a1, a1), a)
+    x0 = _f2_mul(a1, a)
+    if alpha == (P - 1, 0):
+        x = _f2_mul((0, 1), x0)
+    else:
+        b = _f2_pow(((1 + alpha[0]) % P, alpha[1]), (P - 1) // 2)
+        x = _f2_mul(b, x0)
+    return x if _f2_mul(x, x) == (a[0] % P, a[1] % P) else None
+
+
+def _sign_fp(v):
+    return v > _HALF
+
+
+def _sign_fp2(v):
+    return _sign_fp(v[0]) if v[1] == 0 else _sign_fp(v[1])
+
+
+# ---- scalars
+def size_t_to_bytes(v):
+    if not 0 <= v < 1 << 32:
+        raise MarshallingError("std::size_t value does not fit the 4-byte wire field")
+    return int(v).to_bytes(SIZE_T_BYTES, "big")
+
+
+def size_t_from_bytes(buf, off=0):
+    _need(buf, off, SIZE_T_BYTES)
+    return int.from_bytes(buf[off:off + SIZE_T_BYTES], "big")
+
+
+def field_to_bytes(v, modulus, width):
+    return (int(v) % modulus).to_bytes(width, "little")
+
+
+def field_from_bytes(buf, off, modulus, width):
+    _need(buf, off, width)
+    v = int.from_bytes(buf[off:off + width], "little")
+    if v >= modulus:
+        raise InvalidMsgData("field element is not reduced")
+    return v
+
+
+def fr_to_bytes(v):
+    return field_to_bytes(v, R, FR_BYTES)
+
+
+def fr_from_bytes(buf, off=0):
+    return field_from_bytes(buf, off, R, FR_BYTES)
+
+
+def gt_to_bytes(v):
+    """v: the 12 Fp coefficients in data[] order: ((c00, c01), (c10, c11), (c20, c21)) x 2, flattened or nested."""
+    flat = []
+
+    def walk(x):
+        if isinstance(x, (tuple, list)):
+            for y in x:
+                walk(y)
+        else:
+            flat.append(x)
+    walk(v)
+    if len(flat) != 12:
+        raise MarshallingError("an Fp12 element has 12 coefficients")
+    return b"".join(field_to_bytes(c, P, FP_BYTES) for c in flat)
+
+
+def gt_from_bytes(buf, off=0):
+    _need(buf, off, GT_BYTES)
+    c = [field_from_bytes(buf, off + i * FP_BYTES, P, FP_BYTES) for i in range(12)]
+    return tuple(tuple((c[6 * i + 2 * j], c[6 * i + 2 * j + 1]) for j in range(3)) for i in range(2))
+
+
+# ---- points
+def g1_to_bytes(pt):
+    if pt is None:
+        return bytes([_C_BIT | _I_BIT]) + bytes(G1_BYTES - 1)
+    x, y = int(pt[0]) % P, int(pt[1]) % P
+    out = bytearray(x.to_bytes(FP_BYTES, "big"))
+    out[0] |= _C_BIT | (_S_BIT if _sign_fp(y) else 0)
+    return bytes(out)
+
+
+def g1_from_bytes(buf, off=0):
+    _need(buf, off, G1_BYTES)
+    b = bytes(buf[off:off + G1_BYTES])
+    flags = b[0]
+    if not flags & _C_BIT:
+        raise InvalidMsgData("G1 point is not in compressed form")
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    if flags & _I_BIT:
+        if x or flags & _S_BIT:
+            raise InvalidMsgData("non-zero payload in a point at infinity")
+        return None
+    if x >= P:
+        raise InvalidMsgData("x coordinate is not reduced")
+    rhs = (x * x * x + 4) % P
+    y = pow(rhs, (P + 1) // 4, P)
+    if y * y % P != rhs:
+        raise InvalidMsgData("x is not the abscissa of a curve point")
+    if _sign_fp(y) != bool(flags & _S_BIT):
+        y = P - y
+    return (x, y)
+
+
+def g2_to_bytes(pt):
+    if pt is None:
+        return bytes([_C_BIT | _I_BIT]) + bytes(G2_BYTES - 1)
+    (x0, x1), (y0, y1) = pt
+    out = bytearray((int(x1) % P).to_bytes(FP_BYTES, "big") + (int(x0) % P).to_bytes(FP_BYTES, "big"))
+    out[0] |= _C_BIT | (_S_BIT if _sign_fp2((int(y0) % P, int(y1) % P)) else 0)
+    return bytes(out)
+
+
+def g2_from_bytes(buf, off=0):
+    _need(buf, off, G2_BYTES)
+    b = bytes(buf[off:off + G2_BYTES])
+    flags = b[0]
+    if not flags & _C_BIT:
+        raise InvalidMsgData("G2 point is not in compressed form")
+    x1 = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:FP_BYTES], "big")
+    x0 = int.from_bytes(b[FP_BYTES:], "big")
+    if flags & _I_BIT:
+        if x0 or x1 or flags & _S_BIT:
+            raise InvalidMsgData("non-zero payload in a point at infinity")
+        return None
+    if x0 >= P or x1 >= P:
+        raise InvalidMsgData("x coordinate is not reduced")
+    x = (x0, x1)
+    x3 = _f2_mul(_f2_mul(x, x), x)
+    rhs = ((x3[0] + 4) % P, (x3[1] + 4) % P)
+    y = _f2_sqrt(rhs)
+    if y is None:
+        raise InvalidMsgData("x is not the abscissa of a curve point")
+    if _sign_fp2(y) != bool(flags & _S_BIT):
+        y = ((-y[0]) % P, (-y[1]) % P)
+    return (x, y)
+
+
+# ---- containers
+def g1_sparse_vector_to_bytes(indices, values, domain_size):
+    if len(indices) != len(values):
+        raise MarshallingError("sparse_vector: indices and values differ in length")
+    return (size_t_to_bytes(len(values)) + b"".join(size_t_to_bytes(i) for i in indices)
+            + b"".join(g1_to_bytes(v) for v in values) + size_t_to_bytes(domain_size))
+
+
+def g1_sparse_vector_from_bytes(buf, off=0):
+    """-> (indices, values, domain_size, bytes consumed)"""
+    n = size_t_from_bytes(buf, off)
+    total = SIZE_T_BYTES + n * SIZE_T_BYTES + n * G1_BYTES + SIZE_T_BYTES
+    _need(buf, off, total)
+    o = off + SIZE_T_BYTES
+    indices = [size_t_from_bytes(buf, o + SIZE_T_BYTES * i) for i in range(n)]
+    o += SIZE_T_BYTES * n
+    values = [g1_from_bytes(buf, o + G1_BYTES * i) for i in range(n)]
+    o += G1_BYTES * n
+    return indices, values, size_t_from_bytes(buf, o), total
+
+
+def g1_accumulation_vector_to_bytes(first, rest_values, rest_indices=None, domain_size=None):
+    """accumulation_vector(first, rest): `rest` is dense in a verification key (indices 0..n-1, domain n)."""
+    n = len(rest_values)
+    return g1_to_bytes(first) + g1_sparse_vector_to_bytes(
+        list(range(n)) if rest_indices is None else rest_indices, rest_values, n if domain_size is None else domain_size)
+
+
+def g1_accumulation_vector_from_bytes(buf, off=0):
+    """-> (first, (indices, values, domain_size), bytes consumed)"""
+    first = g1_from_bytes(buf, off)
+    ind, val, dom, used = g1_sparse_vector_from_bytes(buf, off + G1_BYTES)
+    return first, (ind, val, dom), G1_BYTES + used
+
+
+# ---- scheme objects
+def proof_to_bytes(proof):
+    """proof: (g_A, g_B, g_C) as returned by groth16.prove"""
+    g_A, g_B, g_C = proof
+    return g1_to_bytes(g_A) + g2_to_bytes(g_B) + g1_to_bytes(g_C)
+
+
+def proof_from_bytes(buf, off=0):
+    _need(buf, off, PROOF_BYTES)
+    return (g1_from_bytes(buf, off), g2_from_bytes(buf, off + G1_BYTES), g1_from_bytes(buf, off + G1_BYTES + G2_BYTES))
+
+
+def primary_input_to_bytes(pi):
+    return size_t_to_bytes(len(pi)) + b"".join(fr_to_bytes(v) for v in pi)
+
+
+def primary_input_from_bytes(buf, off=0):
+    n = size_t_from_bytes(buf, off)
+    _need(buf, off, SIZE_T_BYTES + n * FR_BYTES)
+    return [fr_from_bytes(buf, off + SIZE_T_BYTES + i * FR_BYTES) for i in range(n)]
+
+
+def verification_key_to_bytes(vk):
+    """vk: dict(alpha_g1_beta_g2 = Fp12 coefficients, gamma_g2, delta_g2, gamma_ABC_g1 = (first, [rest...]))"""
+    first, rest = vk["gamma_ABC_g1"]
+    return (gt_to_bytes(vk["alpha_g1_beta_g2"]) + g2_to_bytes(vk["gamma_g2"]) + g2_to_bytes(vk["delta_g2"])
+            + g1_accumulation_vector_to_bytes(first, rest))
+
+
+def verification_key_from_bytes(buf, off=0):
+    _need(buf, off, GT_BYTES + 2 * G2_BYTES)
+    gt = gt_from_bytes(buf, off)
+    gamma = g2_from_bytes(buf, off + GT_BYTES)
+    delta = g2_from_bytes(buf, off + GT_BYTES + G2_BYTES)
+    first, (ind, val, dom), _ = g1_accumulation_vector_from_bytes(buf, off + GT_BYTES + 2 * G2_BYTES)
+    if ind != list(range(len(val))) or dom != len(val):
+        raise InvalidMsgData("gamma_ABC_g1 is not a dense accumulation vector")
+    return {"alpha_g1_beta_g2": gt, "gamma_g2": gamma, "delta_g2": delta, "gamma_ABC_g1": (first, val)}
+
+
+def verifier_input_to_bytes(vk, pi, proof):
+    """`verifier_input_serializer_tvm::process(vk, pi, proof)`: proof | primary input | verification key"""
+    return proof_to_bytes(proof) + primary_input_to_bytes(pi) + verification_key_to_bytes(vk)
+
+
+def verifier_input_from_bytes(buf):
+    """`verifier_input_deserializer_tvm::verifier_input_process` -> (vk, pi, proof)"""
+    proof = proof_from_bytes(buf, 0)
+    pi = primary_input_from_bytes(buf, PROOF_BYTES)
+    vk = verification_key_from_bytes(buf, PROOF_BYTES + SIZE_T_BYTES + FR_BYTES * len(pi))
+    return vk, pi, proof
