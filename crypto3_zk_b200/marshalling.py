@@ -14,6 +14,13 @@ Mirrors `verifier_input_serializer_tvm` / `verifier_input_deserializer_tvm<r1cs_
   accumulation_vector  first (G1) | rest (sparse_vector)         (:571-598)
   verification key alpha_g1_beta_g2 (Fp12, 576 B) | gamma_g2 | delta_g2 | gamma_ABC_g1   (:600-653)
   verifier input   proof | primary input | verification key      (:830-890)
+  linear_term      index | Fr;  linear_combination  count | terms (:204-258, :1020-1036)
+  r1cs_constraint  byte size of (a | b | c) | a | b | c;  constraint system  #primary | #auxiliary | count | constraints
+                                                                 (:260-372, :1038-1071)
+  kc vector (G2,G1)  count | count x index | count x (G2 | G1) | domain_size     (:374-461, :1073-1115)
+  proving key      alpha_g1 | beta_g1 | beta_g2 | delta_g1 | delta_g2 | count, A_query | byte size, B_query (kc vector)
+                   | count, H_query | count, L_query | constraint system, zero-padded to the writer's buffer size
+                                                                 (:656-738, :1117-1163)
 
 `curve_element_serializer` lives in crypto3-algebra (not vendored in the reference).  It implements the ZCash
 BLS12-381 encoding: x big-endian (for G2: x.c1 then x.c0), bit 7 of byte 0 = compressed, bit 6 = point at
@@ -291,6 +298,143 @@ def verification_key_from_bytes(buf, off=0):
     if ind != list(range(len(val))) or dom != len(val):
         raise InvalidMsgData("gamma_ABC_g1 is not a dense accumulation vector")
     return {"alpha_g1_beta_g2": gt, "gamma_g2": gamma, "delta_g2": delta, "gamma_ABC_g1": (first, val)}
+
+
+# ---- proving key
+def linear_combination_to_bytes(terms):
+    """terms: [(variable index, coefficient), ...]"""
+    return size_t_to_bytes(len(terms)) + b"".join(size_t_to_bytes(i) + fr_to_bytes(c) for i, c in terms)
+
+
+def linear_combination_from_bytes(buf, off=0):
+    """-> (terms, bytes consumed)"""
+    n = size_t_from_bytes(buf, off)
+    term = SIZE_T_BYTES + FR_BYTES
+    _need(buf, off, SIZE_T_BYTES + n * term)
+    o = off + SIZE_T_BYTES
+    return ([(size_t_from_bytes(buf, o + i * term), fr_from_bytes(buf, o + i * term + SIZE_T_BYTES)) for i in range(n)],
+            SIZE_T_BYTES + n * term)
+
+
+def _constraint_bytes(con):
+    return sum(len(side) * (SIZE_T_BYTES + FR_BYTES) + SIZE_T_BYTES for side in con)
+
+
+def r1cs_constraint_to_bytes(con):
+    """con: (a, b, c) linear combinations"""
+    return size_t_to_bytes(_constraint_bytes(con)) + b"".join(linear_combination_to_bytes(side) for side in con)
+
+
+def r1cs_constraint_system_to_bytes(num_inputs, num_aux, constraints):
+    return (size_t_to_bytes(num_inputs) + size_t_to_bytes(num_aux) + size_t_to_bytes(len(constraints))
+            + b"".join(r1cs_constraint_to_bytes(c) for c in constraints))
+
+
+def r1cs_constraint_system_from_bytes(buf, off=0):
+    """-> (num_inputs, num_aux, constraints, bytes consumed)"""
+    num_inputs = size_t_from_bytes(buf, off)
+    num_aux = size_t_from_bytes(buf, off + SIZE_T_BYTES)
+    count = size_t_from_bytes(buf, off + 2 * SIZE_T_BYTES)
+    o = off + 3 * SIZE_T_BYTES
+    constraints = []
+    for _ in range(count):
+        total = size_t_from_bytes(buf, o)
+        o += SIZE_T_BYTES
+        _need(buf, o, total)
+        sides, q = [], o
+        for _k in range(3):
+            terms, used = linear_combination_from_bytes(buf, q)
+            sides.append(terms)
+            q += used
+        if q - o != total:
+            raise InvalidMsgData("r1cs_constraint size field disagrees with its linear combinations")
+        constraints.append(tuple(sides))
+        o += total
+    return num_inputs, num_aux, constraints, o - off
+
+
+def _kc_vector_bytes(n):
+    return (2 + n) * SIZE_T_BYTES + n * (G2_BYTES + G1_BYTES)
+
+
+def kc_vector_to_bytes(indices, g2_values, g1_values, domain_size):
+    """knowledge_commitment_vector<G2, G1> without its leading byte-size field"""
+    if not len(indices) == len(g2_values) == len(g1_values):
+        raise MarshallingError("knowledge_commitment_vector: indices and values differ in length")
+    return (size_t_to_bytes(len(indices)) + b"".join(size_t_to_bytes(i) for i in indices)
+            + b"".join(g2_to_bytes(g) + g1_to_bytes(h) for g, h in zip(g2_values, g1_values)) + size_t_to_bytes(domain_size))
+
+
+def kc_vector_from_bytes(buf, off=0):
+    """-> (indices, g2 values, g1 values, domain_size, bytes consumed)"""
+    n = size_t_from_bytes(buf, off)
+    total = _kc_vector_bytes(n)
+    _need(buf, off, total)
+    o = off + SIZE_T_BYTES
+    indices = [size_t_from_bytes(buf, o + SIZE_T_BYTES * i) for i in range(n)]
+    o += SIZE_T_BYTES * n
+    pair = G2_BYTES + G1_BYTES
+    g2v = [g2_from_bytes(buf, o + pair * i) for i in range(n)]
+    g1v = [g1_from_bytes(buf, o + pair * i + G2_BYTES) for i in range(n)]
+    return indices, g2v, g1v, size_t_from_bytes(buf, o + pair * n), total
+
+
+def _g1_list_to_bytes(pts):
+    return size_t_to_bytes(len(pts)) + b"".join(g1_to_bytes(p) for p in pts)
+
+
+def _g1_list_from_bytes(buf, off):
+    n = size_t_from_bytes(buf, off)
+    _need(buf, off, SIZE_T_BYTES + n * G1_BYTES)
+    return [g1_from_bytes(buf, off + SIZE_T_BYTES + i * G1_BYTES) for i in range(n)], SIZE_T_BYTES + n * G1_BYTES
+
+
+def proving_key_to_bytes(pk, pad=True):
+    """pk: dict(alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, A_query, B_indices, B_g2, B_g1, B_domain_size, H_query,
+    L_query, num_inputs, num_aux, constraints) - the argument names of groth16.ProvingKey.  With `pad` the result has the
+    length of the writer's buffer (twice its size estimate, marshalling.hpp:1119-1129; the tail is zero) so that it equals
+    the reference's output byte for byte; the reader ignores the tail."""
+    nb = len(pk["B_indices"])
+    body = (g1_to_bytes(pk["alpha_g1"]) + g1_to_bytes(pk["beta_g1"]) + g2_to_bytes(pk["beta_g2"])
+            + g1_to_bytes(pk["delta_g1"]) + g2_to_bytes(pk["delta_g2"])
+            + _g1_list_to_bytes(pk["A_query"])
+            + size_t_to_bytes(_kc_vector_bytes(nb))
+            + kc_vector_to_bytes(pk["B_indices"], pk["B_g2"], pk["B_g1"], pk["B_domain_size"])
+            + _g1_list_to_bytes(pk["H_query"]) + _g1_list_to_bytes(pk["L_query"])
+            + r1cs_constraint_system_to_bytes(pk["num_inputs"], pk["num_aux"], pk["constraints"]))
+    if not pad:
+        return body
+    estimate = (3 * G1_BYTES + 2 * G2_BYTES + len(pk["A_query"]) * G1_BYTES + _kc_vector_bytes(nb)
+                + len(pk["H_query"]) * G1_BYTES + len(pk["L_query"]) * G1_BYTES + 2 * SIZE_T_BYTES
+                + sum(_constraint_bytes(c) for c in pk["constraints"]))
+    if len(body) > 2 * estimate:      # cannot happen: the unaccounted size fields are 4 bytes per counted item
+        raise MarshallingError("proving key exceeds the writer's buffer")
+    return body + bytes(2 * estimate - len(body))
+
+
+def proving_key_from_bytes(buf, off=0):
+    out = {}
+    o = off
+    for name, rd, n in (("alpha_g1", g1_from_bytes, G1_BYTES), ("beta_g1", g1_from_bytes, G1_BYTES),
+                        ("beta_g2", g2_from_bytes, G2_BYTES), ("delta_g1", g1_from_bytes, G1_BYTES),
+                        ("delta_g2", g2_from_bytes, G2_BYTES)):
+        out[name] = rd(buf, o)
+        o += n
+    out["A_query"], used = _g1_list_from_bytes(buf, o)
+    o += used
+    total_b = size_t_from_bytes(buf, o)
+    o += SIZE_T_BYTES
+    _need(buf, o, total_b)
+    out["B_indices"], out["B_g2"], out["B_g1"], out["B_domain_size"], used = kc_vector_from_bytes(buf, o)
+    if used != total_b:
+        raise InvalidMsgData("B_query size field disagrees with its contents")
+    o += total_b
+    out["H_query"], used = _g1_list_from_bytes(buf, o)
+    o += used
+    out["L_query"], used = _g1_list_from_bytes(buf, o)
+    o += used
+    out["num_inputs"], out["num_aux"], out["constraints"], _ = r1cs_constraint_system_from_bytes(buf, o)
+    return out
 
 
 def verifier_input_to_bytes(vk, pi, proof):

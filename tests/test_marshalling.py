@@ -134,3 +134,42 @@ def test_sparse_vector():
     ind, val, dom, used = m.g1_sparse_vector_from_bytes(b)
     assert (ind, val, dom, used) == ([1, 4, 7], pts, 9, len(b))
     assert m.g1_sparse_vector_from_bytes(m.g1_sparse_vector_to_bytes([], [], 0))[:3] == ([], [], 0)
+
+
+def _sample_pk():
+    rng = random.Random(13)
+    g1 = G1.random_points(12, 14)
+    g2 = G2.random_points(5, 15)
+    fr = lambda: rng.randrange(m.R)
+    constraints = [([(0, 1), (2, fr())], [(1, fr())], [(3, fr()), (4, fr()), (1, fr())]),
+                   ([], [(2, 1)], [(4, fr())]),
+                   ([(1, fr())], [], [])]
+    return dict(alpha_g1=g1[0], beta_g1=g1[1], beta_g2=g2[0], delta_g1=g1[2], delta_g2=g2[1],
+                A_query=g1[3:6] + [None], B_indices=[0, 2, 3], B_g2=g2[2:5], B_g1=g1[6:9], B_domain_size=5,
+                H_query=g1[9:11], L_query=g1[11:12], num_inputs=1, num_aux=3, constraints=constraints)
+
+
+def test_proving_key_round_trip():
+    pk = _sample_pk()
+    body = m.proving_key_to_bytes(pk, pad=False)
+    blob = m.proving_key_to_bytes(pk)
+    con = [sum(len(s) * 36 + 4 for s in c) for c in pk["constraints"]]
+    kc = (2 + 3) * 4 + 3 * 144
+    assert len(body) == 3 * 48 + 2 * 96 + (4 + 4 * 48) + (4 + kc) + (4 + 2 * 48) + (4 + 48) + 12 + sum(4 + c for c in con)
+    # the writer's buffer: twice its estimate, zero tail (marshalling.hpp:1119-1129)
+    assert len(blob) == 2 * (3 * 48 + 2 * 96 + 4 * 48 + kc + 2 * 48 + 48 + 8 + sum(con))
+    assert blob[:len(body)] == body and not any(blob[len(body):])
+    off_b = 3 * 48 + 2 * 96 + 4 + 4 * 48
+    assert blob[off_b:off_b + 4] == kc.to_bytes(4, "big") and blob[off_b + 4:off_b + 8] == (3).to_bytes(4, "big")
+    for b in (body, blob):
+        back = m.proving_key_from_bytes(b)
+        assert back == pk
+    cs = m.r1cs_constraint_system_to_bytes(1, 3, pk["constraints"])
+    assert cs[:12] == bytes([0, 0, 0, 1, 0, 0, 0, 3, 0, 0, 0, 3]) and cs[12:16] == con[0].to_bytes(4, "big")
+    assert m.r1cs_constraint_system_from_bytes(cs) == (1, 3, pk["constraints"], len(cs))
+    with pytest.raises(m.NotEnoughData):
+        m.proving_key_from_bytes(body[:-5])
+    bad = bytearray(cs)
+    bad[15] ^= 4
+    with pytest.raises(m.MarshallingError):
+        m.r1cs_constraint_system_from_bytes(bytes(bad))
