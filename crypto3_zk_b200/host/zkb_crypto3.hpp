@@ -8,6 +8,8 @@
 //   nil::crypto3::zk::commitments::detail::fold_polynomial (dfs)   (fold_polynomial.hpp:68-93)
 //   nil::crypto3::zk::algorithms::precommit (container<polynomial_dfs>) -> tree with root()
 //                                                                  (basic_fri.hpp:445-496, lpc.hpp:101-106)
+//   nil::marshalling::curve_element_serializer<bls12<381>>, verifier_input_{,de}serializer_tvm (proof)
+//                                                                  (r1cs_gg_ppzksnark/marshalling.hpp, host only)
 //
 // Same names, argument meaning and error behaviour (std::invalid_argument for size errors,
 // std::runtime_error for device errors).  The work is done by the CUDA library; there is no CPU
@@ -1363,4 +1365,259 @@ commitments::device_merkle_tree<HashId> precommit(const Container &polys, std::s
 }  // namespace algorithms
 }  // namespace zk
 }  // namespace crypto3
+}  // namespace nil
+
+// ---- Groth16 wire format, BLS12-381 (r1cs_gg_ppzksnark/marshalling.hpp; host only, no device call) ----
+// `curve_element_serializer<bls12<381>>` is crypto3-algebra's (un-vendored): the ZCash encoding - x big-endian
+// (G2: x.c1 then x.c0), bit 7 of byte 0 = compressed, bit 6 = infinity, bit 5 = y is the larger of (y, -y)
+// (Fp2: by c1, by c0 when c1 == 0).  The proof is g_A | g_B | g_C (marshalling.hpp:784-828, :1236-1256).
+// crypto3_zk_b200/marshalling.py is the same format for the Python layer (keys and verifier input included);
+// tests/test_cpp_host.py compares the two byte for byte.
+namespace nil {
+namespace crypto3 {
+namespace zk {
+namespace snark {
+// proof.hpp:42-95
+template <class CurveType>
+struct r1cs_gg_ppzksnark_proof {
+    typename CurveType::template g1_type<>::value_type g_A;
+    typename CurveType::template g2_type<>::value_type g_B;
+    typename CurveType::template g1_type<>::value_type g_C;
+    r1cs_gg_ppzksnark_proof()
+        : g_A(CurveType::template g1_type<>::value_type::one()), g_B(CurveType::template g2_type<>::value_type::one()),
+          g_C(CurveType::template g1_type<>::value_type::one()) {}
+    r1cs_gg_ppzksnark_proof(const typename CurveType::template g1_type<>::value_type &a,
+                            const typename CurveType::template g2_type<>::value_type &b,
+                            const typename CurveType::template g1_type<>::value_type &c)
+        : g_A(a), g_B(b), g_C(c) {}
+    bool operator==(const r1cs_gg_ppzksnark_proof &o) const { return g_A == o.g_A && g_B == o.g_B && g_C == o.g_C; }
+};
+template <class CurveType>
+struct r1cs_gg_ppzksnark {
+    typedef CurveType curve_type;
+    typedef r1cs_gg_ppzksnark_proof<CurveType> proof_type;
+};
+}  // namespace snark
+}  // namespace zk
+}  // namespace crypto3
+
+namespace marshalling {
+enum class status_type { success, not_enough_data, invalid_msg_data };
+
+template <class CurveType>
+struct curve_element_serializer;
+
+template <>
+struct curve_element_serializer<crypto3::algebra::curves::bls12<381>> {
+    typedef crypto3::algebra::curves::bls12<381> curve_type;
+    typedef curve_type::base_field_type fq_type;
+    typedef crypto3::algebra::fields::zkb_field2<fq_type> fq2_type;
+    typedef curve_type::g1_type<>::value_type g1_value_type;
+    typedef curve_type::g2_type<>::value_type g2_value_type;
+    static constexpr std::size_t sizeof_field_element = 48;
+    typedef std::array<std::uint8_t, sizeof_field_element> compressed_g1_octets;
+    typedef std::array<std::uint8_t, 2 * sizeof_field_element> compressed_g2_octets;
+    static constexpr std::uint8_t C_bit = 0x80, I_bit = 0x40, S_bit = 0x20;
+
+    static compressed_g1_octets point_to_octets_compress(const g1_value_type &point) {
+        compressed_g1_octets out{};
+        if (point.is_zero()) {
+            out[0] = C_bit | I_bit;
+            return out;
+        }
+        g1_value_type a = point.to_affine();
+        std::uint32_t x[12], y[12];
+        a.X.to_canonical_limbs(x);
+        a.Y.to_canonical_limbs(y);
+        put_be(x, out.data());
+        out[0] |= C_bit | (sign(y) ? S_bit : 0);
+        return out;
+    }
+    static compressed_g2_octets point_to_octets_compress(const g2_value_type &point) {
+        compressed_g2_octets out{};
+        if (point.is_zero()) {
+            out[0] = C_bit | I_bit;
+            return out;
+        }
+        g2_value_type a = point.to_affine();
+        std::uint32_t x[24], y[24];
+        a.X.to_canonical_limbs(x);
+        a.Y.to_canonical_limbs(y);
+        put_be(x + 12, out.data());
+        put_be(x, out.data() + sizeof_field_element);
+        out[0] |= C_bit | (sign2(y) ? S_bit : 0);
+        return out;
+    }
+    // throws std::invalid_argument for octets that are not the compressed form of a curve point
+    static g1_value_type octets_to_g1_point(const compressed_g1_octets &in) {
+        std::uint8_t flags = in[0];
+        if (!(flags & C_bit)) throw std::invalid_argument("G1 point is not in compressed form");
+        std::uint32_t xl[12];
+        get_be(in.data(), xl);
+        xl[11] &= 0x1FFFFFFFu;
+        if (flags & I_bit) {
+            if (!all_zero(xl, 12) || (flags & S_bit)) throw std::invalid_argument("non-zero payload in a point at infinity");
+            return g1_value_type::zero();
+        }
+        if (!reduced(xl)) throw std::invalid_argument("x coordinate is not reduced");
+        typedef fq_type::value_type V;
+        V x = V::from_canonical_limbs(xl), rhs = x * x * x + V(4u);
+        std::uint32_t e[12];
+        fq_type::modulus_minus_one_shifted(2, e);   // (p - 3) / 4
+        add_one(e);                                 // (p + 1) / 4
+        V y = rhs.pow_limbs(e, 12);
+        if (y * y != rhs) throw std::invalid_argument("x is not the abscissa of a curve point");
+        std::uint32_t yl[12];
+        y.to_canonical_limbs(yl);
+        if (sign(yl) != bool(flags & S_bit)) y = -y;
+        return g1_value_type::from_affine(x, y);
+    }
+    static g2_value_type octets_to_g2_point(const compressed_g2_octets &in) {
+        std::uint8_t flags = in[0];
+        if (!(flags & C_bit)) throw std::invalid_argument("G2 point is not in compressed form");
+        std::uint32_t xl[24];
+        get_be(in.data(), xl + 12);
+        get_be(in.data() + sizeof_field_element, xl);
+        xl[23] &= 0x1FFFFFFFu;
+        if (flags & I_bit) {
+            if (!all_zero(xl, 24) || (flags & S_bit)) throw std::invalid_argument("non-zero payload in a point at infinity");
+            return g2_value_type::zero();
+        }
+        if (!reduced(xl) || !reduced(xl + 12)) throw std::invalid_argument("x coordinate is not reduced");
+        typedef fq2_type::value_type V2;
+        std::uint32_t bl[24] = {0};
+        bl[0] = 4; bl[12] = 4;
+        V2 x = V2::from_canonical_limbs(xl), rhs = x * x * x + V2::from_canonical_limbs(bl), y;
+        if (!sqrt2(rhs, y)) throw std::invalid_argument("x is not the abscissa of a curve point");
+        std::uint32_t yl[24];
+        y.to_canonical_limbs(yl);
+        if (sign2(yl) != bool(flags & S_bit)) y = -y;
+        return g2_value_type::from_affine(x, y);
+    }
+
+private:
+    static void put_be(const std::uint32_t *l, std::uint8_t *out) {
+        for (int i = 0; i < 48; i++) out[i] = (std::uint8_t)(l[(47 - i) / 4] >> (8 * ((47 - i) % 4)));
+    }
+    static void get_be(const std::uint8_t *in, std::uint32_t *l) {
+        for (int i = 0; i < 12; i++) l[i] = 0;
+        for (int i = 0; i < 48; i++) l[(47 - i) / 4] |= (std::uint32_t)in[i] << (8 * ((47 - i) % 4));
+    }
+    static bool all_zero(const std::uint32_t *l, int n) {
+        for (int i = 0; i < n; i++)
+            if (l[i]) return false;
+        return true;
+    }
+    static void add_one(std::uint32_t *l) {
+        for (int i = 0; i < 12 && ++l[i] == 0; i++) {}
+    }
+    // a < p
+    static bool reduced(const std::uint32_t *a) {
+        std::uint32_t m[12];
+        fq_type::modulus_minus_one_shifted(0, m);   // p - 1
+        for (int i = 11; i >= 0; i--)
+            if (a[i] != m[i]) return a[i] < m[i];
+        return true;                                // a == p - 1
+    }
+    // y > (p - 1) / 2
+    static bool sign(const std::uint32_t *y) {
+        std::uint32_t h[12];
+        fq_type::modulus_minus_one_shifted(1, h);
+        for (int i = 11; i >= 0; i--)
+            if (y[i] != h[i]) return y[i] > h[i];
+        return false;
+    }
+    static bool sign2(const std::uint32_t *y) { return all_zero(y + 12, 12) ? sign(y) : sign(y + 12); }
+    static fq2_type::value_type pow2(fq2_type::value_type b, const std::uint32_t *e) {
+        fq2_type::value_type r = fq2_type::value_type::one();
+        for (int i = 11; i >= 0; i--)
+            for (int k = 31; k >= 0; k--) {
+                r = r * r;
+                if ((e[i] >> k) & 1) r = r * b;
+            }
+        return r;
+    }
+    // square root in Fq2 for p = 3 mod 4
+    static bool sqrt2(const fq2_type::value_type &a, fq2_type::value_type &out) {
+        typedef fq2_type::value_type V2;
+        if (a.is_zero()) {
+            out = a;
+            return true;
+        }
+        std::uint32_t e[12], ul[24] = {0};
+        fq_type::modulus_minus_one_shifted(2, e);   // (p - 3) / 4
+        V2 a1 = pow2(a, e), alpha = a1 * a1 * a, x0 = a1 * a, x;
+        if (alpha == -V2::one()) {
+            ul[12] = 1;
+            x = V2::from_canonical_limbs(ul) * x0;
+        } else {
+            fq_type::modulus_minus_one_shifted(1, e);   // (p - 1) / 2
+            x = pow2(V2::one() + alpha, e) * x0;
+        }
+        if (x * x != a) return false;
+        out = x;
+        return true;
+    }
+};
+
+template <class ProofSystem>
+struct verifier_input_serializer_tvm;
+template <class ProofSystem>
+struct verifier_input_deserializer_tvm;
+
+template <>
+struct verifier_input_serializer_tvm<crypto3::zk::snark::r1cs_gg_ppzksnark<crypto3::algebra::curves::bls12<381>>> {
+    typedef crypto3::algebra::curves::bls12<381> CurveType;
+    typedef crypto3::zk::snark::r1cs_gg_ppzksnark<CurveType> scheme_type;
+    typedef std::uint8_t chunk_type;
+    static constexpr std::size_t g1_byteblob_size = curve_element_serializer<CurveType>::sizeof_field_element;
+    static constexpr std::size_t g2_byteblob_size = 2 * curve_element_serializer<CurveType>::sizeof_field_element;
+    // marshalling.hpp:1236-1256
+    static std::vector<chunk_type> process(const scheme_type::proof_type &pr) {
+        std::vector<chunk_type> out;
+        out.reserve(2 * g1_byteblob_size + g2_byteblob_size);
+        auto a = curve_element_serializer<CurveType>::point_to_octets_compress(pr.g_A);
+        auto b = curve_element_serializer<CurveType>::point_to_octets_compress(pr.g_B);
+        auto c = curve_element_serializer<CurveType>::point_to_octets_compress(pr.g_C);
+        out.insert(out.end(), a.begin(), a.end());
+        out.insert(out.end(), b.begin(), b.end());
+        out.insert(out.end(), c.begin(), c.end());
+        return out;
+    }
+};
+
+template <>
+struct verifier_input_deserializer_tvm<crypto3::zk::snark::r1cs_gg_ppzksnark<crypto3::algebra::curves::bls12<381>>> {
+    typedef crypto3::algebra::curves::bls12<381> CurveType;
+    typedef crypto3::zk::snark::r1cs_gg_ppzksnark<CurveType> scheme_type;
+    typedef std::uint8_t chunk_type;
+    static constexpr std::size_t g1_byteblob_size = curve_element_serializer<CurveType>::sizeof_field_element;
+    static constexpr std::size_t g2_byteblob_size = 2 * curve_element_serializer<CurveType>::sizeof_field_element;
+    // marshalling.hpp:784-828; octets that are no curve point give invalid_msg_data
+    static scheme_type::proof_type proof_process(std::vector<chunk_type>::const_iterator read_iter_begin,
+                                                 std::vector<chunk_type>::const_iterator read_iter_end,
+                                                 status_type &processingStatus) {
+        if ((std::size_t)std::distance(read_iter_begin, read_iter_end) < 2 * g1_byteblob_size + g2_byteblob_size) {
+            processingStatus = status_type::not_enough_data;
+            return {};
+        }
+        curve_element_serializer<CurveType>::compressed_g1_octets a, c;
+        curve_element_serializer<CurveType>::compressed_g2_octets b;
+        std::copy(read_iter_begin, read_iter_begin + g1_byteblob_size, a.begin());
+        std::copy(read_iter_begin + g1_byteblob_size, read_iter_begin + g1_byteblob_size + g2_byteblob_size, b.begin());
+        std::copy(read_iter_begin + g1_byteblob_size + g2_byteblob_size,
+                  read_iter_begin + 2 * g1_byteblob_size + g2_byteblob_size, c.begin());
+        try {
+            scheme_type::proof_type pr(curve_element_serializer<CurveType>::octets_to_g1_point(a),
+                                       curve_element_serializer<CurveType>::octets_to_g2_point(b),
+                                       curve_element_serializer<CurveType>::octets_to_g1_point(c));
+            processingStatus = status_type::success;
+            return pr;
+        } catch (const std::invalid_argument &) {
+            processingStatus = status_type::invalid_msg_data;
+            return {};
+        }
+    }
+};
+}  // namespace marshalling
 }  // namespace nil

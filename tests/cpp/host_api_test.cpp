@@ -331,9 +331,88 @@ static void batch_exp_test() {
     }
 }
 
+// r1cs_gg_ppzksnark/marshalling.hpp:784-828, 1236-1256: the 192-byte proof blob in crypto3-algebra's compressed point
+// encoding.  Host only.  Prints "MARSHAL <name> <hex>" lines that tests/test_cpp_host.py compares with
+// crypto3_zk_b200/marshalling.py and with the published generator encodings.
+static void marshalling_test(bool with_gpu) {
+    typedef algebra::curves::bls12<381> curve;
+    typedef nil::marshalling::curve_element_serializer<curve> ser;
+    typedef zk::snark::r1cs_gg_ppzksnark<curve> scheme;
+    typedef curve::g1_type<>::value_type g1v;
+    typedef curve::g2_type<>::value_type g2v;
+    auto hex = [](const std::uint8_t *b, std::size_t n) {
+        std::string h;
+        static const char *d = "0123456789abcdef";
+        for (std::size_t i = 0; i < n; i++) { h += d[b[i] >> 4]; h += d[b[i] & 15]; }
+        return h;
+    };
+    g1v g = g1v::one(), gneg = g1v::from_affine(g.X, -g.Y);
+    g2v h = g2v::one(), hneg = g2v::from_affine(h.X, -h.Y);
+    auto eg = ser::point_to_octets_compress(g), egn = ser::point_to_octets_compress(gneg);
+    auto eh = ser::point_to_octets_compress(h), ehn = ser::point_to_octets_compress(hneg);
+    std::printf("MARSHAL g1gen %s\n", hex(eg.data(), eg.size()).c_str());
+    std::printf("MARSHAL g2gen %s\n", hex(eh.data(), eh.size()).c_str());
+    CHECK(ser::octets_to_g1_point(eg) == g && ser::octets_to_g1_point(egn) == gneg && !(gneg == g));
+    CHECK(ser::octets_to_g2_point(eh) == h && ser::octets_to_g2_point(ehn) == hneg && !(hneg == h));
+    CHECK((eg[0] ^ egn[0]) == 0x20 && (eh[0] ^ ehn[0]) == 0x20);
+    // a Jacobian representative with Z != 1 encodes like its affine form
+    {
+        auto z = curve::base_field_type::value_type(5u), z2 = z * z;
+        g1v j;
+        j.X = g.X * z2; j.Y = g.Y * z2 * z; j.Z = z;
+        CHECK(ser::point_to_octets_compress(j) == eg);
+    }
+    auto inf1 = ser::point_to_octets_compress(g1v::zero());
+    auto inf2 = ser::point_to_octets_compress(g2v::zero());
+    CHECK(inf1[0] == 0xC0 && inf2[0] == 0xC0 && ser::octets_to_g1_point(inf1).is_zero() && ser::octets_to_g2_point(inf2).is_zero());
+    scheme::proof_type pr(g, hneg, gneg);
+    auto blob = nil::marshalling::verifier_input_serializer_tvm<scheme>::process(pr);
+    CHECK(blob.size() == 192);
+    std::printf("MARSHAL proof %s\n", hex(blob.data(), blob.size()).c_str());
+    nil::marshalling::status_type st;
+    auto back = nil::marshalling::verifier_input_deserializer_tvm<scheme>::proof_process(blob.begin(), blob.end(), st);
+    CHECK(st == nil::marshalling::status_type::success && back == pr);
+    nil::marshalling::verifier_input_deserializer_tvm<scheme>::proof_process(blob.begin(), blob.end() - 1, st);
+    CHECK(st == nil::marshalling::status_type::not_enough_data);
+    {
+        auto bad = blob;
+        bad[0] &= 0x7F;   // not compressed
+        nil::marshalling::verifier_input_deserializer_tvm<scheme>::proof_process(bad.begin(), bad.end(), st);
+        CHECK(st == nil::marshalling::status_type::invalid_msg_data);
+        bad = blob;
+        // walk x upwards to an abscissa without a point
+        bool rejected = false;
+        for (int k = 1; k < 64 && !rejected; k++) {
+            bad[47] = (std::uint8_t)(blob[47] + k);
+            nil::marshalling::verifier_input_deserializer_tvm<scheme>::proof_process(bad.begin(), bad.end(), st);
+            rejected = st == nil::marshalling::status_type::invalid_msg_data;
+        }
+        CHECK(rejected);
+    }
+    if (with_gpu) {
+        // multiples of the generators from the device MSM: round trip of points that are not the generator
+        std::vector<g1v> b1 = {g};
+        std::vector<g2v> b2 = {h};
+        algebra::multiexp_bases<curve::g1_type<>> G1(b1.begin(), b1.end());
+        algebra::multiexp_bases<curve::g2_type<>> G2(b2.begin(), b2.end());
+        typedef curve::scalar_field_type::value_type fr;
+        for (std::uint64_t k : {2ull, 3ull, 12345678901ull, 0xFFFFFFFFFFFFFFFFull}) {
+            std::vector<fr> s = {fr(k)};
+            g1v p1 = G1.multiexp(0, s.begin(), s.end());
+            g2v p2 = G2.multiexp(0, s.begin(), s.end());
+            auto e1 = ser::point_to_octets_compress(p1);
+            auto e2 = ser::point_to_octets_compress(p2);
+            CHECK(ser::octets_to_g1_point(e1) == p1 && ser::octets_to_g2_point(e2) == p2);
+            std::printf("MARSHAL g1x%llu %s\n", (unsigned long long)k, hex(e1.data(), e1.size()).c_str());
+            std::printf("MARSHAL g2x%llu %s\n", (unsigned long long)k, hex(e2.data(), e2.size()).c_str());
+        }
+    }
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !std::strcmp(argv[1], "compile-only")) {
         transcript_and_grinding_test(false);   // host-only part: transcript known answers
+        marshalling_test(false);
         std::printf(failures ? "FAILED %d checks\n" : "compiled\n", failures);
         return failures ? 1 : 0;
     }
@@ -350,6 +429,7 @@ int main(int argc, char **argv) {
         domain_and_fold_test<algebra::fields::pallas_base_field>();
         domain_and_fold_test<algebra::fields::pallas_scalar_field>();
         transcript_and_grinding_test(true);
+        marshalling_test(true);
         batch_exp_test<algebra::curves::bls12<381>>();
         batch_exp_test<algebra::curves::alt_bn128<254>>();
         lpc_scheme_test();

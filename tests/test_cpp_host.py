@@ -26,6 +26,17 @@ def test_host_templates_compile_and_link():
     exe = _build()
     out = subprocess.run([exe, "compile-only"], stdout=subprocess.PIPE, text=True, check=True).stdout
     assert "compiled" in out
+    # the C++ curve_element_serializer / proof blob against the Python layer's wire format (host only)
+    from crypto3_zk_b200 import marshalling as m
+    from oracle import curves
+    g1, g2 = curves.BLS12_381_G1, curves.BLS12_381_G2
+    lines = _marshal_lines(out)
+    assert lines["g1gen"] == m.g1_to_bytes(g1.gen).hex() and lines["g2gen"] == m.g2_to_bytes(g2.gen).hex()
+    assert lines["proof"] == m.proof_to_bytes((g1.gen, g2.neg(g2.gen), g1.neg(g1.gen))).hex()
+
+
+def _marshal_lines(out):
+    return {l.split()[1]: l.split()[2] for l in out.splitlines() if l.startswith("MARSHAL ")}
 
 
 @pytest.mark.gpu
@@ -43,6 +54,14 @@ def test_host_templates_on_gpu():
     want_digest, want_len, want_state = _oracle_lpc_proof_digest()
     assert (got[1], int(got[2])) == (want_digest, want_len)
     assert [l.split()[1] for l in r.stdout.splitlines() if l.startswith("TRANSCRIPT ")][0] == want_state
+    # compressed encodings of device-computed multiples of the generators: same bytes as the Python layer
+    # produces for the oracle's scalar multiples
+    from crypto3_zk_b200 import marshalling as m
+    from oracle import curves
+    lines = _marshal_lines(r.stdout)
+    for k in (2, 3, 12345678901, 0xFFFFFFFFFFFFFFFF):
+        assert lines["g1x%d" % k] == m.g1_to_bytes(curves.BLS12_381_G1.mul(curves.BLS12_381_G1.gen, k)).hex()
+        assert lines["g2x%d" % k] == m.g2_to_bytes(curves.BLS12_381_G2.mul(curves.BLS12_381_G2.gen, k)).hex()
 
 
 def _oracle_lpc_proof_digest():
