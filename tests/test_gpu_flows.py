@@ -605,3 +605,20 @@ def test_groth16_prove_vs_oracle(ctx, curve, kind, nc, ni):
     assert got[0] == G1.mul(G1.gen, a) and got[1] == G2.mul(G2.gen, b) and got[2] == G1.mul(G1.gen, c)
     # zero randomness and a binary assignment exercise the 0/1 scalar paths of the MSM
     assert dg.prove(ctx, dpk, primary, aux, 0, 0) == groth16.prove(pk, primary, aux, 0, 0, G1, G2, F)
+    if curve == "bls12_381":
+        # the reference's wire format on both sides of the prover (r1cs_gg_ppzksnark/marshalling.hpp): proving key read
+        # from its byte blob, proof written as the 192-byte g_A | g_B | g_C blob
+        from crypto3_zk_b200 import marshalling
+        from crypto3_zk_b200.groth16 import ProvingKey, R1csConstraintSystem
+        blob = marshalling.proving_key_to_bytes(dict(
+            alpha_g1=pk.alpha_g1, beta_g1=pk.beta_g1, beta_g2=pk.beta_g2, delta_g1=pk.delta_g1, delta_g2=pk.delta_g2,
+            A_query=pk.A_query, B_indices=pk.B_indices, B_g2=pk.B_g2, B_g1=pk.B_g1, B_domain_size=len(pk.A_query),
+            H_query=pk.H_query, L_query=pk.L_query, num_inputs=pk.cs.num_inputs, num_aux=pk.cs.num_aux,
+            constraints=pk.cs.constraints))
+        k = marshalling.proving_key_from_bytes(blob)
+        dpk2 = ProvingKey(ctx, G1.name, G2.name, R1csConstraintSystem(k["num_inputs"], k["num_aux"], k["constraints"]),
+                          k["alpha_g1"], k["beta_g1"], k["beta_g2"], k["delta_g1"], k["delta_g2"], k["A_query"],
+                          k["B_indices"], k["B_g2"], k["B_g1"], k["H_query"], k["L_query"])
+        wire = marshalling.proof_to_bytes(dg.prove(ctx, dpk2, primary, aux, r, s))
+        assert len(wire) == 192 and wire == marshalling.proof_to_bytes(want)
+        assert marshalling.proof_from_bytes(wire) == want

@@ -173,3 +173,28 @@ def test_proving_key_round_trip():
     bad[15] ^= 4
     with pytest.raises(m.MarshallingError):
         m.r1cs_constraint_system_from_bytes(bytes(bad))
+
+
+def test_oracle_groth16_key_and_proof_through_the_wire():
+    """A real (tiny) BLS12-381 Groth16 key and proof of the oracle prover survive the byte format unchanged."""
+    from oracle import groth16
+    F = fields.BLS12_381_FR
+    cs, primary, aux = groth16.example_with_field_input(F, 13, 2, seed=5)
+    t, alpha, beta, gamma, delta = fields.random_elements(F, 5, 21)
+    pk = groth16.generator(cs, G1, G2, F, t, alpha, beta, gamma, delta)
+    d = dict(alpha_g1=pk.alpha_g1, beta_g1=pk.beta_g1, beta_g2=pk.beta_g2, delta_g1=pk.delta_g1, delta_g2=pk.delta_g2,
+             A_query=pk.A_query, B_indices=pk.B_indices, B_g2=pk.B_g2, B_g1=pk.B_g1, B_domain_size=len(pk.A_query),
+             H_query=pk.H_query, L_query=pk.L_query, num_inputs=pk.cs.num_inputs, num_aux=pk.cs.num_aux,
+             constraints=pk.cs.constraints)
+    k = m.proving_key_from_bytes(m.proving_key_to_bytes(d))
+    norm = lambda cons: [tuple([tuple(x) for x in side] for side in c) for c in cons]
+    for key in d:
+        if key == "constraints":
+            assert norm(k[key]) == norm(d[key])
+        else:
+            assert k[key] == d[key], key
+    r, s = fields.random_elements(F, 2, 22)
+    proof = groth16.prove(pk, primary, aux, r, s, G1, G2, F)
+    wire = m.proof_to_bytes(proof)
+    assert len(wire) == 192 and m.proof_from_bytes(wire) == tuple(proof)
+    assert m.primary_input_from_bytes(m.primary_input_to_bytes(primary)) == list(primary)
