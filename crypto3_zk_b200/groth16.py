@@ -183,3 +183,122 @@ def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None, concurre
     g1_C = ctx.multiexp(tail, _int_rows([1, 1, s % p, r % p, (-r * s) % p]))
     tail.free()
     return g1_A, g2_B, g1_C
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# r1cs_gg_ppzksnark_generator (generator.hpp:83-235): the QAP evaluated at t on the host, every group element by
+# fixed-base batch exponentiation on the device (zkb_batch_exp = algebra::batch_exp / kc_batch_exp of :187-225).
+
+def _batch_inverse(vals, p):
+    """Montgomery's trick: one modular inversion for the whole list (no zero entries)."""
+    pref, acc = [], 1
+    for v in vals:
+        pref.append(acc)
+        acc = acc * v % p
+    inv = pow(acc, p - 2, p)
+    out = [0] * len(vals)
+    for i in range(len(vals) - 1, -1, -1):
+        out[i] = inv * pref[i] % p
+        inv = inv * vals[i] % p
+    return out
+
+
+def _lagrange_at(F, log_m, t):
+    """basic_radix2_domain::evaluate_all_lagrange_polynomials(t): L_i(t) over the size-2^log_m subgroup."""
+    from .fields import omega as _omega
+    p, m = F.p, 1 << log_m
+    w = _omega(F, log_m)
+    pows = [1] * m
+    for i in range(1, m):
+        pows[i] = pows[i - 1] * w % p
+    if pow(t, m, p) == 1:                      # t is a domain element: the indicator vector
+        return [1 if x == t % p else 0 for x in pows]
+    l0 = (pow(t, m, p) - 1) * pow(m, p - 2, p) % p
+    inv = _batch_inverse([(t - x) % p for x in pows], p)
+    return [l0 * pows[i] % p * inv[i] % p for i in range(m)]
+
+
+def qap_instance_evaluation(cs, F, t):
+    """r1cs_to_qap::instance_map_with_evaluation (r1cs_to_qap.hpp:147-204): (At, Bt, Ct, Ht, Zt, m) with the
+    input-consistency rows num_constraints + i added to A."""
+    p = F.p
+    m = cs.num_constraints + cs.num_inputs + 1
+    if m & (m - 1):
+        raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT,
+                                      "num_constraints + num_inputs + 1 must be a power of two (basic_radix2_domain)")
+    u = _lagrange_at(F, m.bit_length() - 1, t)
+    At, Bt, Ct = ([0] * (cs.num_variables + 1) for _ in range(3))
+    for i in range(cs.num_inputs + 1):
+        At[i] = u[cs.num_constraints + i]
+    for row, con in enumerate(cs.constraints):
+        for side, acc in zip(con, (At, Bt, Ct)):
+            for idx, co in side:
+                acc[idx] = (acc[idx] + u[row] * co) % p
+    Ht = [1] * (m + 1)
+    for i in range(1, m + 1):
+        Ht[i] = Ht[i - 1] * t % p
+    return At, Bt, Ct, Ht, (pow(t, m, p) - 1) % p, m
+
+
+def swap_ab_if_beneficial(cs):
+    """r1cs_constraint_system::swap_AB_if_beneficial (generator.hpp:88): B goes to G2, so the side with fewer distinct
+    variables becomes B."""
+    ta = {i for a, _, _ in cs.constraints for i, _ in a}
+    tb = {i for _, b, _ in cs.constraints for i, _ in b}
+    if len(tb) > len(ta):
+        return R1csConstraintSystem(cs.num_inputs, cs.num_aux, [(b, a, c) for a, b, c in cs.constraints])
+    return cs
+
+
+def generator(ctx, curve_g1, curve_g2, cs, t, alpha, beta, gamma, delta, g1_generator=None, g2_generator=None):
+    """basic_process with the toxic waste passed in (the reference draws t, alpha, beta, gamma, delta and the two
+    generators at random, generator.hpp:92-102,152,160).  Returns (key, vk): `key` is a dict with the argument names of
+    ProvingKey / marshalling.proving_key_to_bytes (points affine, None = infinity), `vk` holds gamma_g2, delta_g2,
+    gamma_g1 and gamma_ABC_g1 = (first, rest); alpha_g1_beta_g2 is a pairing value and not computed on this path."""
+    from .api import _affine_from_limbs
+    g1 = CURVE_BY_NAME[curve_g1] if isinstance(curve_g1, str) else curve_g1
+    g2 = CURVE_BY_NAME[curve_g2] if isinstance(curve_g2, str) else curve_g2
+    F = FIELD_BY_NAME[g1.scalar_field]
+    p = F.p
+    t, alpha, beta, gamma, delta = (int(v) % p for v in (t, alpha, beta, gamma, delta))
+    cs = swap_ab_if_beneficial(cs)
+    At, Bt, Ct, Ht, Zt, m = qap_instance_evaluation(cs, F, t)
+    ginv, dinv = pow(gamma, p - 2, p), pow(delta, p - 2, p)
+    ni, nv = cs.num_inputs, cs.num_variables
+    abc = [(beta * At[i] + alpha * Bt[i] + Ct[i]) % p for i in range(nv + 1)]
+    gamma_abc = [v * ginv % p for v in abc[:ni + 1]]
+    Lt = [v * dinv % p for v in abc[ni + 1:]]
+    coeff = Zt * dinv % p
+    Hs = [coeff * h % p for h in Ht[:len(Ht) - 2]]
+    b_idx = [i for i, v in enumerate(Bt) if v]
+    b_sc = [Bt[i] for i in b_idx]
+
+    def exp(curve, base, scalars):
+        cl = coord_limbs(curve)
+        base = (curve.gen_x, curve.gen_y) if base is None else base
+        if not scalars:
+            return []
+        out = np.asarray(ctx.batch_exp(curve.name, base, _int_rows(scalars)), dtype=np.uint32)
+        return [_affine_from_limbs(out[i].reshape(-1), cl, curve.deg) for i in range(len(scalars))]
+
+    head1 = [alpha, beta, delta, gamma]
+    pts1 = exp(g1, g1_generator, head1 + gamma_abc + At + b_sc + Hs + Lt)
+    pts2 = exp(g2, g2_generator, [beta, delta, gamma] + b_sc)
+    parts, o = [], len(head1)
+    for n in (ni + 1, nv + 1, len(b_sc), len(Hs), len(Lt)):
+        parts.append(pts1[o:o + n])
+        o += n
+    gabc_pts, A_query, B_g1, H_query, L_query = parts
+    key = dict(alpha_g1=pts1[0], beta_g1=pts1[1], beta_g2=pts2[0], delta_g1=pts1[2], delta_g2=pts2[1],
+               A_query=A_query, B_indices=b_idx, B_g2=pts2[3:], B_g1=B_g1, B_domain_size=nv + 1,
+               H_query=H_query, L_query=L_query, num_inputs=ni, num_aux=cs.num_aux, constraints=cs.constraints)
+    vk = dict(gamma_g2=pts2[2], delta_g2=pts2[1], gamma_g1=pts1[3], gamma_ABC_g1=(gabc_pts[0], gabc_pts[1:]))
+    return key, vk
+
+
+def proving_key_from_dict(ctx, curve_g1, curve_g2, key, precompute=False):
+    """Device-resident ProvingKey from the dict `generator` returns / marshalling.proving_key_from_bytes reads."""
+    cs = R1csConstraintSystem(key["num_inputs"], key["num_aux"], key["constraints"])
+    return ProvingKey(ctx, curve_g1, curve_g2, cs, key["alpha_g1"], key["beta_g1"], key["beta_g2"], key["delta_g1"],
+                      key["delta_g2"], key["A_query"], key["B_indices"], key["B_g2"], key["B_g1"], key["H_query"],
+                      key["L_query"], precompute=precompute)

@@ -622,3 +622,25 @@ def test_groth16_prove_vs_oracle(ctx, curve, kind, nc, ni):
         wire = marshalling.proof_to_bytes(dg.prove(ctx, dpk2, primary, aux, r, s))
         assert len(wire) == 192 and wire == marshalling.proof_to_bytes(want)
         assert marshalling.proof_from_bytes(wire) == want
+
+
+@pytest.mark.parametrize("curve,nc,ni", [("bls12_381", 13, 2), ("bn254", 27, 4)])
+def test_groth16_generator_vs_oracle(ctx, curve, nc, ni):
+    """r1cs_gg_ppzksnark_generator::basic_process (generator.hpp:83-235): QAP evaluation on the host, every key element by
+    zkb_batch_exp; same key as the oracle's generator, and the device prover proves with it."""
+    from crypto3_zk_b200 import groth16 as dg
+    from oracle import curves, groth16
+    F, G1, G2 = ((fields.BN254_FR, curves.BN254_G1, curves.BN254_G2) if curve == "bn254" else
+                 (fields.BLS12_381_FR, curves.BLS12_381_G1, curves.BLS12_381_G2))
+    cs, primary, aux = groth16.example_with_field_input(F, nc, ni, seed=7)
+    t, alpha, beta, gamma, delta = fields.random_elements(F, 5, 31)
+    pk = groth16.generator(cs, G1, G2, F, t, alpha, beta, gamma, delta)
+    pcs = dg.R1csConstraintSystem(cs.num_inputs, cs.num_aux, list(cs.constraints))
+    key, vk = dg.generator(ctx, G1.name, G2.name, pcs, t, alpha, beta, gamma, delta)
+    for name in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "A_query", "B_indices", "B_g2", "B_g1",
+                 "H_query", "L_query"):
+        assert key[name] == getattr(pk, name), name
+    assert vk["gamma_g2"] == G2.mul(G2.gen, gamma) and vk["delta_g2"] == pk.delta_g2
+    r, s = fields.random_elements(F, 2, 32)
+    dpk = dg.proving_key_from_dict(ctx, G1.name, G2.name, key)
+    assert dg.prove(ctx, dpk, primary, aux, r, s) == groth16.prove(pk, primary, aux, r, s, G1, G2, F)
