@@ -1396,6 +1396,7 @@ template <class CurveType>
 struct r1cs_gg_ppzksnark {
     typedef CurveType curve_type;
     typedef r1cs_gg_ppzksnark_proof<CurveType> proof_type;
+    typedef std::vector<typename CurveType::scalar_field_type::value_type> primary_input_type;
 };
 }  // namespace snark
 }  // namespace zk
@@ -1572,6 +1573,26 @@ struct verifier_input_serializer_tvm<crypto3::zk::snark::r1cs_gg_ppzksnark<crypt
     typedef std::uint8_t chunk_type;
     static constexpr std::size_t g1_byteblob_size = curve_element_serializer<CurveType>::sizeof_field_element;
     static constexpr std::size_t g2_byteblob_size = 2 * curve_element_serializer<CurveType>::sizeof_field_element;
+    static constexpr std::size_t std_size_t_byteblob_size = 4;
+    static constexpr std::size_t fr_byteblob_size = (CurveType::scalar_field_type::modulus_bits + 7) / 8;
+    // marshalling.hpp:975-985: 4 bytes, most significant first
+    static void std_size_t_process(std::size_t v, std::vector<chunk_type> &out) {
+        for (int i = 3; i >= 0; i--) out.push_back((chunk_type)(v >> (8 * i)));
+    }
+    // marshalling.hpp:921-935: fixed width, least significant byte first
+    static void field_type_process(const CurveType::scalar_field_type::value_type &v, std::vector<chunk_type> &out) {
+        std::uint32_t l[CurveType::scalar_field_type::limbs32];
+        v.to_canonical_limbs(l);
+        for (std::size_t i = 0; i < fr_byteblob_size; i++) out.push_back((chunk_type)(l[i / 4] >> (8 * (i % 4))));
+    }
+    // marshalling.hpp:1210-1234
+    static std::vector<chunk_type> process(const scheme_type::primary_input_type &pi) {
+        std::vector<chunk_type> out;
+        out.reserve(std_size_t_byteblob_size + pi.size() * fr_byteblob_size);
+        std_size_t_process(pi.size(), out);
+        for (const auto &v : pi) field_type_process(v, out);
+        return out;
+    }
     // marshalling.hpp:1236-1256
     static std::vector<chunk_type> process(const scheme_type::proof_type &pr) {
         std::vector<chunk_type> out;
@@ -1593,6 +1614,61 @@ struct verifier_input_deserializer_tvm<crypto3::zk::snark::r1cs_gg_ppzksnark<cry
     typedef std::uint8_t chunk_type;
     static constexpr std::size_t g1_byteblob_size = curve_element_serializer<CurveType>::sizeof_field_element;
     static constexpr std::size_t g2_byteblob_size = 2 * curve_element_serializer<CurveType>::sizeof_field_element;
+    static constexpr std::size_t std_size_t_byteblob_size = 4;
+    static constexpr std::size_t fr_byteblob_size = (CurveType::scalar_field_type::modulus_bits + 7) / 8;
+    // marshalling.hpp:465-491
+    static std::size_t std_size_t_process(std::vector<chunk_type>::const_iterator read_iter_begin,
+                                          std::vector<chunk_type>::const_iterator read_iter_end, status_type &processingStatus) {
+        processingStatus = status_type::success;
+        if ((std::size_t)std::distance(read_iter_begin, read_iter_end) < std_size_t_byteblob_size) {
+            processingStatus = status_type::not_enough_data;
+            return 0;
+        }
+        std::size_t v = 0;
+        for (std::size_t i = 0; i < std_size_t_byteblob_size; i++) v = (v << 8) | read_iter_begin[i];
+        return v;
+    }
+    // marshalling.hpp:122-144; a value that is not reduced gives invalid_msg_data
+    static CurveType::scalar_field_type::value_type field_type_process(std::vector<chunk_type>::const_iterator read_iter_begin,
+                                                                       std::vector<chunk_type>::const_iterator read_iter_end,
+                                                                       status_type &processingStatus) {
+        typedef CurveType::scalar_field_type F;
+        processingStatus = status_type::success;
+        if ((std::size_t)std::distance(read_iter_begin, read_iter_end) < fr_byteblob_size) {
+            processingStatus = status_type::not_enough_data;
+            return F::value_type::zero();
+        }
+        std::uint32_t l[F::limbs32] = {0}, m[F::limbs32];
+        for (std::size_t i = 0; i < fr_byteblob_size; i++) l[i / 4] |= (std::uint32_t)read_iter_begin[i] << (8 * (i % 4));
+        F::modulus_minus_one_shifted(0, m);   // p - 1
+        for (int i = F::limbs32 - 1; i >= 0; i--)
+            if (l[i] != m[i]) {
+                if (l[i] > m[i]) {
+                    processingStatus = status_type::invalid_msg_data;
+                    return F::value_type::zero();
+                }
+                break;
+            }
+        return F::value_type::from_canonical_limbs(l);
+    }
+    // marshalling.hpp:740-782
+    static scheme_type::primary_input_type primary_input_process(std::vector<chunk_type>::const_iterator read_iter_begin,
+                                                                 std::vector<chunk_type>::const_iterator read_iter_end,
+                                                                 status_type &processingStatus) {
+        std::size_t pi_count = std_size_t_process(read_iter_begin, read_iter_end, processingStatus);
+        if (processingStatus != status_type::success) return {};
+        if ((std::size_t)std::distance(read_iter_begin, read_iter_end) < std_size_t_byteblob_size + pi_count * fr_byteblob_size) {
+            processingStatus = status_type::not_enough_data;
+            return {};
+        }
+        scheme_type::primary_input_type pi(pi_count);
+        for (std::size_t i = 0; i < pi_count; i++) {
+            pi[i] = field_type_process(read_iter_begin + std_size_t_byteblob_size + i * fr_byteblob_size,
+                                       read_iter_begin + std_size_t_byteblob_size + (i + 1) * fr_byteblob_size, processingStatus);
+            if (processingStatus != status_type::success) return {};
+        }
+        return pi;
+    }
     // marshalling.hpp:784-828; octets that are no curve point give invalid_msg_data
     static scheme_type::proof_type proof_process(std::vector<chunk_type>::const_iterator read_iter_begin,
                                                  std::vector<chunk_type>::const_iterator read_iter_end,

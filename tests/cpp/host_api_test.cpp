@@ -389,6 +389,27 @@ static void marshalling_test(bool with_gpu) {
         }
         CHECK(rejected);
     }
+    {
+        // primary input: count | Fr elements, least significant byte first (marshalling.hpp:740-782, 1210-1234)
+        typedef curve::scalar_field_type::value_type fr;
+        typedef nil::marshalling::verifier_input_deserializer_tvm<scheme> de;
+        scheme::primary_input_type pi = {fr(1u), -fr(1u), fr(12345u), fr(0u)};
+        auto pb = nil::marshalling::verifier_input_serializer_tvm<scheme>::process(pi);
+        CHECK(pb.size() == 4 + 4 * 32);
+        std::printf("MARSHAL pi %s\n", hex(pb.data(), pb.size()).c_str());
+        auto pback = de::primary_input_process(pb.begin(), pb.end(), st);
+        CHECK(st == nil::marshalling::status_type::success && pback == pi);
+        de::primary_input_process(pb.begin(), pb.end() - 1, st);
+        CHECK(st == nil::marshalling::status_type::not_enough_data);
+        auto bad = pb;
+        for (int i = 0; i < 32; i++) bad[4 + i] = 0xFF;   // 2^256 - 1 >= r
+        de::primary_input_process(bad.begin(), bad.end(), st);
+        CHECK(st == nil::marshalling::status_type::invalid_msg_data);
+        bad = pb;
+        bad[4 + 32] = 0x01;   // (r - 1) + 1 = r: the smallest value that is not reduced
+        de::primary_input_process(bad.begin(), bad.end(), st);
+        CHECK(st == nil::marshalling::status_type::invalid_msg_data);
+    }
     if (with_gpu) {
         // multiples of the generators from the device MSM: round trip of points that are not the generator
         std::vector<g1v> b1 = {g};

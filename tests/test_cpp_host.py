@@ -33,6 +33,7 @@ def test_host_templates_compile_and_link():
     lines = _marshal_lines(out)
     assert lines["g1gen"] == m.g1_to_bytes(g1.gen).hex() and lines["g2gen"] == m.g2_to_bytes(g2.gen).hex()
     assert lines["proof"] == m.proof_to_bytes((g1.gen, g2.neg(g2.gen), g1.neg(g1.gen))).hex()
+    assert lines["pi"] == m.primary_input_to_bytes([1, m.R - 1, 12345, 0]).hex()
 
 
 def _marshal_lines(out):
