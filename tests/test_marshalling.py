@@ -2,7 +2,11 @@
 
 The compressed point encoding is crypto3-algebra's `curve_element_serializer<bls12<381>>` (not vendored); the
 reference holds no byte vectors of it, so the encoding is pinned on the published ZCash encodings of the two
-generators and on round trips against the oracle's curve arithmetic."""
+generators and on round trips against the oracle's curve arithmetic.  The reference's own test of this format
+(test/systems/ppzksnark/r1cs_gg_ppzksnark/run_r1cs_gg_ppzksnark_tvm_marshalling.hpp:89-200) is the same kind of check:
+generate, prove, serialise key / input / proof, deserialise, compare field by field - no byte vectors.
+test_oracle_groth16_key_and_proof_through_the_wire mirrors it on CPU, tests/test_gpu_flows.py (wire leg of
+test_groth16_prove_vs_oracle) with the device prover in the middle."""
 import random
 
 import pytest
