@@ -1,4 +1,6 @@
-"""Multi-GPU paths on the GPU box (skipped when fewer than 2 GPUs): point-sharded MSM over NCCL."""
+"""Multi-GPU paths on the GPU box (each world size is skipped when the box has fewer GPUs): point-sharded MSM and
+polynomial-sharded LPC commit over NCCL at 2, 4 and 8 ranks.  `gpurun --gpus N -- python -m pytest tests/test_gpu_multi.py`
+runs them; the logs of those runs are committed under profiles/ (r2_multi_*.log)."""
 import os
 import socket
 
@@ -32,10 +34,11 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_point_sharded_msm_nccl():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_point_sharded_msm_nccl(world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -43,13 +46,13 @@ def test_point_sharded_msm_nccl():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, True) for r in range(world)]
 
 
 def _lpc_worker(rank, world, port, q):
@@ -76,12 +79,13 @@ def _lpc_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_polynomial_sharded_lpc_commit_nccl():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_polynomial_sharded_lpc_commit_nccl(world):
     """LDE sharded by polynomial, one all-to-all regroup by leaf range, per-rank subtrees, top levels
     from the all-gathered subtree roots - same root as the single-GPU commit of the whole batch."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -89,10 +93,10 @@ def test_polynomial_sharded_lpc_commit_nccl():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_lpc_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_lpc_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, True) for r in range(world)]
