@@ -7,9 +7,11 @@ Step  = one batched LDE (polynomial_dfs::resize as in LPC commit, basic_fri.hpp:
 value = extended field elements produced per second, inputs resident in HBM.
 e2e   = the same metric through the C-ABI call zkb_lde with HOST (pinned) buffers: H2D of the 2 GiB
         input and D2H of the 16 GiB result inside the timed region.
-extra = the other two parts of BASELINE.json's metric measured in the same run at N=1:
-        coset NTT 2^24 BLS12-381 Fr (elem/s), G1 MSM 2^20 BLS12-381 (ms), LPC commit of config #2 (ms),
-        each with its roofline fraction and CPU baseline.
+baseline_metric_parts (N=1; mirrored into roofline.parts / cpu_baseline.parts / e2e.parts) = the three numbers
+        BASELINE.json's metric names: G1 MSM 2^20 BLS12-381 (ms), coset NTT 2^24 BLS12-381 Fr (elem/s), LPC commit of
+        config #2 (ms), each with its roofline, its CPU baseline at the full size and an e2e figure with host buffers.
+extra = MSM sweep (configs[2]), Groth16 prover (configs[3]), Placeholder commitment phase (configs[4]); at N>1 the
+        point-sharded MSMs and the polynomial-sharded LPC commit, each verified against the single-GPU result.
 --impl reference : the reference's CPU algorithm (the oracle port, all host threads) on the same config,
         each step a bounded sample (a few whole polynomials), same metric/unit.
 """
@@ -35,6 +37,18 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ntt_sources_hash():
+    """sha256 over the NTT kernel sources (the stamp of profiles/ntt_traffic.json)"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "crypto3_zk_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith("zkb_ntt") or f in ("zkb_field.cuh", "zkb_ptx.cuh"):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
 
 
 class ClockSampler:
@@ -108,33 +122,50 @@ def rand_elems(torch, shape, seed, device):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def host_cores():
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1, so omp_get_max_threads() is not the answer:
+    the CPU legs pass the thread count to every oracle/c call explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
+    """The reference's CPU algorithm (oracle/c port) for the SAME metric on the box's host cores.  One node has one
+    set of host cores whatever N is, so rank 0 alone runs, with every core, and the same single-node number is
+    reported at every N (the GPU arm's value grows with N, the CPU node does not)."""
     import numpy as np
     from oracle import cref
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = cref.threads_available()
-    sample_polys = max(1, min(threads, 32, args.batch))
+    threads = host_cores()
+    sample_polys = max(1, min(threads, args.batch))
     rng = np.random.Generator(np.random.PCG64(0))
     a = rng.integers(0, 1 << 32, size=(sample_polys, 1 << args.log_in, 8), dtype=np.uint64).astype(np.uint32)
     a[..., 7] &= 0x0FFFFFFF
     times = []
     for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         _, t = cref.lde(3, a, args.log_in, args.log_out, threads=threads)
         if it >= args.warmup:
-            times.append(t)
+            times.append(time.perf_counter() - t0)      # wall time of the step, Montgomery conversion included
     tot = sum(times)
     value = sample_polys * (1 << args.log_out) * len(times) / tot
-    sample = "%d of %d polynomials per step (whole 2^%d->2^%d LDEs, one per thread)" % (sample_polys, args.batch, args.log_in, args.log_out)
+    sample = "each step = %d of the %d polynomials of a GPU step (whole 2^%d->2^%d LDEs, one polynomial per thread, %d threads)" % (
+        sample_polys, args.batch, args.log_in, args.log_out, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times) * args.batch / sample_polys, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit prime field, exact)", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (255-bit prime field, exact)", "data": "synthetic",
+        "config": dict(workload_config(args, args.gpus), reference_step=sample),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference cannot be compiled here (Boost + un-vendored crypto3 libs): timed code is oracle/c, a C port of its CPU algorithm; ms_per_step extrapolated from the sample to the full batch",
+        "ms_per_full_gpu_step_at_this_rate": 1e3 * args.batch * (1 << args.log_out) / value,
+        "note": "reference cannot be compiled here (Boost + un-vendored crypto3 libs): timed code is oracle/c, a C port of its "
+                "CPU algorithm; ms_per_step is the measured wall time of one sample step (not extrapolated); the same "
+                "single-node CPU throughput is reported at every --gpus N",
     }
     print(json.dumps(line))
 
@@ -162,50 +193,87 @@ def time_cuda(torch, fn, iters, warmup=1):
     return e0.elapsed_time(e1) / iters   # ms
 
 
-def extras(args, torch, ctx, dev, hbm_peak):
+def time_wall(torch, fn, iters, warmup=1):
+    """Wall-clock ms per call of a host-buffer API call (copies inside), synchronised on both sides."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / iters * 1e3
+
+
+def pinned_like(torch, np, t):
+    h = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+    h.copy_(t)
+    return h, h.numpy().view(np.uint32)
+
+
+def metric_parts(args, torch, ctx, dev, hbm_peak, x_lde):
+    """The three numbers BASELINE.json's metric names - G1 MSM 2^20 BLS12-381 (ms), coset NTT 2^24 Fr (elem/s), LPC
+    commit of config #2 (ms) - each with its roofline, its CPU baseline at the FULL size (no extrapolation for the
+    MSM and the NTT) and an end-to-end figure through the C ABI with pinned HOST buffers."""
     import numpy as np
     from crypto3_zk_b200 import capi
-    from crypto3_zk_b200.fields import CURVE_BY_NAME, FIELD_BY_NAME
-    ex = {}
+    from crypto3_zk_b200.fields import FIELD_BY_NAME
+    parts, aux = {}, {}
     cpu = None
     if not args.no_cpu:
         from oracle import cref
         cpu = cref
-    threads = cpu.threads_available() if cpu else 0
-    # ---- integer-pipe peak (field-mul/s), the MSM/NTT compute roofline denominator
+    cores = host_cores()
+    # ---- integer-pipe peaks: (a) the field multipliers themselves, (b) a bare IMAD.WIDE issue-rate loop that shares no
+    # code with them (the independent ceiling the products are measured against)
     peak_fr = ctx.bench_field_mul("bls12_381_fr", 148 * 8, 256, 2048)
     peak_fq = ctx.bench_field_mul("bls12_381_fq", 148 * 8, 256, 1024)
-    ex["int_pipe_peak"] = {"fr8_mul_per_s": peak_fr, "fq12_mul_per_s": peak_fq,
-                           "how": "register-resident dependent Montgomery products, 4 chains/thread, 148*8 CTAs x 256 thr"}
+    aux["int_pipe_peak"] = {"fr8_mul_per_s": peak_fr, "fq12_mul_per_s": peak_fq,
+                            "how": "register-resident dependent Montgomery products, 4 chains/thread, 148*8 CTAs x 256 thr"}
+    try:
+        wide = ctx.bench_imad_wide(148 * 8, 256, 4096)
+        aux["int_pipe_peak"]["imad_wide_per_s"] = wide
+        aux["int_pipe_peak"]["fq12_ceiling_from_imad_wide"] = wide / 300.0     # 288 products + 12 m_i per Fq product
+        aux["int_pipe_peak"]["fr8_ceiling_from_imad_wide"] = wide / 112.0
+    except Exception as e:
+        aux["int_pipe_peak"]["imad_wide_error"] = repr(e)[:120]
+
     # ---- coset NTT 2^24, BLS12-381 Fr
     log_n = args.ntt_log
-    x = rand_elems(torch, (1, 1 << log_n, 8), 11, dev)
-    g = FIELD_BY_NAME["bls12_381_fr"].generator
-    ms = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n, coset_shift=g), 5, warmup=2)
-    ms_plain = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n), 5, warmup=2)
     n = 1 << log_n
+    x = rand_elems(torch, (1, n, 8), 11, dev)
+    g = FIELD_BY_NAME["bls12_381_fr"].generator
+    ms = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n, coset_shift=g), 10, warmup=3)
+    ms_plain = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n), 10, warmup=3)
     alg = 2 * n * 32
     muls = n * (log_n / 2.0 + 2)      # butterflies + 2 inter-pass twiddles + coset scale (approx.)
-    ex["coset_ntt_2p%d_bls12_381_fr" % log_n] = {
-        "elem_per_s": n / (ms * 1e-3), "ms": ms, "ms_without_coset": ms_plain,
-        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg},
-        "int_pipe": {"field_mul_per_s": muls / (ms * 1e-3), "frac_of_peak": muls / (ms * 1e-3) / peak_fr}}
+    hx, hxn = pinned_like(torch, np, x)
+    e2e_ms = time_wall(torch, lambda: ctx.ntt("bls12_381_fr", hxn, log_n, coset_shift=g), 5, warmup=2)
+    part = {"value": n / (ms * 1e-3), "unit": "elem/s", "ms": ms, "ms_without_coset": ms_plain,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg,
+                         "int_pipe": {"field_mul_per_s": muls / (ms * 1e-3), "peak_field_mul_per_s": peak_fr,
+                                      "frac": muls / (ms * 1e-3) / peak_fr}},
+            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "elem/s", "ms": e2e_ms, "h2d_bytes_per_step": n * 32,
+                    "d2h_bytes_per_step": n * 32, "api": "zkb_ntt(mem=ZKB_MEM_HOST), pinned host buffer, in place"}}
     if cpu:
-        ls = min(log_n, 22)
-        a = np.random.Generator(np.random.PCG64(1)).integers(0, 1 << 32, size=(1, 1 << ls, 8), dtype=np.uint64).astype(np.uint32)
+        a = np.random.Generator(np.random.PCG64(1)).integers(0, 1 << 32, size=(1, n, 8), dtype=np.uint64).astype(np.uint32)
         a[..., 7] &= 0x0FFFFFFF
-        t = cpu.ntt(0, a, ls, shift=g, threads=1)
-        ex["coset_ntt_2p%d_bls12_381_fr" % log_n]["cpu_baseline"] = {
-            "value": (1 << ls) / t, "unit": "elem/s", "cores": 1, "kind": "port", "sample": "one 2^%d coset FFT, 1 thread (a single transform is serial in the reference)" % ls}
-    del x
+        t = cpu.ntt(0, a, log_n, shift=g, threads=1)
+        part["cpu_baseline"] = {"value": n / t, "unit": "elem/s", "cores": 1, "kind": "port",
+                                "sample": "one full 2^%d coset FFT, 1 thread (a single transform is serial in the reference)" % log_n}
+        del a
+    parts["coset_ntt_2p%d_bls12_381_fr" % log_n] = part
+    del x, hx, hxn
+
     # ---- G1 MSM 2^20, BLS12-381
     log_m = args.msm_log
     nm = 1 << log_m
     pts = msm_points(torch, ctx, np, log_m)
     bases = ctx.msm_bases("bls12_381_g1", pts)
     sc = rand_elems(torch, (nm, 8), 13, dev)
-    msm_plain_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 5, warmup=2)
+    msm_plain_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 10, warmup=3)
+    res_plain = ctx.multiexp(bases, sc)
     c = max(2, min(20, log_m - 4))
     W = (255 + 1 + c - 1) // c
     plain_mults = nm * W * 10 + W * (1 << (c - 1)) * 2 * 14 + 255 * 8   # SURVEY 8(d) work model
@@ -215,31 +283,64 @@ def extras(args, torch, ctx, dev, hbm_peak):
     t0 = time.perf_counter()
     bases.precompute(ct, 64 << 30)
     table_build_ms = (time.perf_counter() - t0) * 1e3
-    msm_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 5, warmup=2)
+    msm_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 10, warmup=3)
+    res_table = ctx.multiexp(bases, sc)
     fq_mults = nm * Wt * 10 + (1 << (ct - 1)) * 2 * 14
-    sc_host = sc.cpu().numpy().view(np.uint32)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        ctx.multiexp(bases, sc_host)
-    msm_e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
-    ex["msm_g1_2p%d_bls12_381" % log_m] = {
-        "ms": msm_ms, "e2e_ms_host_scalars": msm_e2e_ms, "variant": "window table (bases resident, built once)",
-        "window_bits": ct, "windows": Wt, "table_bytes": nm * Wt * 96, "table_build_ms": table_build_ms,
-        "work_model_fq_mults": fq_mults,
-        "int_pipe": {"fq_mul_per_s": fq_mults / (msm_ms * 1e-3), "peak_fq_mul_per_s": peak_fq,
-                     "frac_of_peak": fq_mults / (msm_ms * 1e-3) / peak_fq},
-        "without_table": {"ms": msm_plain_ms, "window_bits": c, "windows": W, "work_model_fq_mults": plain_mults,
-                          "int_pipe_frac_of_peak": plain_mults / (msm_plain_ms * 1e-3) / peak_fq},
-        "hbm_traffic_model_bytes": nm * (96 + 32)}
+    hs, hsn = pinned_like(torch, np, sc)
+    msm_e2e_ms = time_wall(torch, lambda: ctx.multiexp(bases, hsn), 10, warmup=2)
+    part = {"value": msm_ms, "unit": "ms", "higher_is_better": False,
+            "variant": "window table (bases resident, built once per key)", "window_bits": ct, "windows": Wt,
+            "table_bytes": nm * Wt * 96, "table_build_ms": table_build_ms, "same_point_both_variants": res_plain == res_table,
+            "roofline": {"bound": "integer pipe (SURVEY 8(d): Fq products of the work model / measured Fq product peak)",
+                         "work_model_fq_mults": fq_mults, "achieved": fq_mults / (msm_ms * 1e-3), "peak": peak_fq,
+                         "unit": "Fq mul/s", "frac": fq_mults / (msm_ms * 1e-3) / peak_fq,
+                         "hbm_traffic_model_bytes": nm * (96 + 32)},
+            "without_table": {"ms": msm_plain_ms, "window_bits": c, "windows": W, "work_model_fq_mults": plain_mults,
+                              "frac": plain_mults / (msm_plain_ms * 1e-3) / peak_fq},
+            "e2e": {"value": msm_e2e_ms, "unit": "ms", "h2d_bytes_per_step": nm * 32, "d2h_bytes_per_step": 96,
+                    "api": "zkb_msm(mem=ZKB_MEM_HOST): pinned host scalars in, affine point out; bases resident"}}
     if cpu:
-        ns = min(nm, 1 << 16)
-        ph = pts[:ns].cpu().numpy().view(np.uint32)
-        _, t = cpu.msm(0, ph, sc_host[:ns], threads=threads)
-        ex["msm_g1_2p%d_bls12_381" % log_m]["cpu_baseline"] = {
-            "value": t * 1e3 * nm / ns, "unit": "ms (extrapolated linearly from the sample to 2^%d)" % log_m, "cores": threads,
-            "kind": "port", "sample": "2^%d of the 2^%d points, BDLO12 bucket MSM, chunks = threads" % (ns.bit_length() - 1, log_m)}
+        ph = pts.cpu().numpy().view(np.uint32)
+        res_cpu, t = cpu.msm(0, ph, hsn, threads=cores)
+        part["cpu_baseline"] = {"value": t * 1e3, "unit": "ms", "cores": cores, "kind": "port",
+                                "sample": "the full 2^%d-point MSM, BDLO12 bucket method, chunks = threads" % log_m,
+                                "same_point_as_gpu": res_cpu == res_table}
+        del ph
+    parts["msm_g1_2p%d_bls12_381" % log_m] = part
     bases.free()
-    del pts, sc
+    del pts, sc, hs, hsn
+    torch.cuda.empty_cache()
+
+    # ---- LPC commit of config #2: 64 x (2^20 -> 2^23) Pallas Fq, step 1 (basic_fri.hpp:445-496)
+    leaf_bytes = args.batch * (32 << args.log_out)
+    alg_lpc = args.batch * ((32 << args.log_in) + (32 << args.log_out))      # fused lower bound: read polys, stream the LDE into the hash
+    hx, hxn = pinned_like(torch, np, x_lde)
+    lp = {}
+    for name, hid in (("keccak256", capi.HASH_KECCAK_256), ("sha256", capi.HASH_SHA2_256)):
+        ms = time_cuda(torch, lambda: ctx.lpc_commit("pallas_fq", hid, x_lde, args.log_in, args.log_out, 1), 3, warmup=1)
+        root_dev = ctx.lpc_commit("pallas_fq", hid, x_lde, args.log_in, args.log_out, 1)
+        e_ms = time_wall(torch, lambda: ctx.lpc_commit("pallas_fq", hid, hxn, args.log_in, args.log_out, 1), 3, warmup=1)
+        root_host = ctx.lpc_commit("pallas_fq", hid, hxn, args.log_in, args.log_out, 1)
+        lp[name] = {"ms": ms, "root": root_dev.hex(), "leaf_bytes_hashed": leaf_bytes, "hash_GBps_incl_lde": leaf_bytes / (ms * 1e-3) / 1e9,
+                    "roofline": {"bound": "hbm", "achieved": alg_lpc / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_lpc / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_lpc},
+                    "e2e": {"value": e_ms, "unit": "ms", "h2d_bytes_per_step": args.batch * (32 << args.log_in),
+                            "d2h_bytes_per_step": len(root_host), "same_root": root_host == root_dev,
+                            "api": "zkb_lpc_commit(mem=ZKB_MEM_HOST): pinned host polynomials in, root out"}}
+    part = {"value": lp["keccak256"]["ms"], "unit": "ms", "higher_is_better": False, "hash": "keccak256 (primary, lpc_performance.cpp:129-130)",
+            "roofline": lp["keccak256"]["roofline"], "e2e": lp["keccak256"]["e2e"], "by_hash": lp}
+    if cpu:
+        sp = min(args.batch, 16)
+        a = x_lde[:sp].cpu().numpy().view(np.uint32)
+        root_cpu, t, lde_s = cpu.lpc_commit(3, 0, a, args.log_in, args.log_out, 1, threads=cores)
+        root_gpu = ctx.lpc_commit("pallas_fq", 0, x_lde[:sp].contiguous(), args.log_in, args.log_out, 1)
+        part["cpu_baseline"] = {"value": t * 1e3 * args.batch / sp, "unit": "ms", "cores": cores, "kind": "port",
+                                "sample": "%d of the %d polynomials committed as one batch (measured %.0f ms, of which LDE %.0f ms), scaled by %d/%d: "
+                                          "both the LDE and the leaf bytes are linear in the polynomial count" % (sp, args.batch, t * 1e3, lde_s * 1e3, args.batch, sp),
+                                "same_root_as_gpu_on_the_sample": root_cpu == root_gpu}
+    parts["lpc_commit_config2"] = part
+    del hx, hxn
+
     # ---- grinding (proof_of_work.hpp:47-68), keccak-256 transcript: expected 2^bits nonce trials of two hashes each
     from crypto3_zk_b200.transcript import FiatShamirSequential
     gr = {}
@@ -249,8 +350,8 @@ def extras(args, torch, ctx, dev, hbm_peak):
         t0 = time.perf_counter()
         nonce = ctx.pow_grind(0, tr.state, (1 << bits) - 1)
         gr["mask_bits_%d" % bits] = {"ms": (time.perf_counter() - t0) * 1e3, "nonce": nonce}
-    ex["pow_grind_keccak256"] = gr
-    return ex
+    aux["pow_grind_keccak256"] = gr
+    return parts, aux
 
 
 def _kg_points(ctx, np, ks):
@@ -329,7 +430,9 @@ def msm_sweep_extra(args, torch, ctx, dev):
 def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
     """G1 MSM of a fixed size sharded by point range over the ranks: every rank keeps its slice of
     the bases resident (with its window table), computes a partial sum, and the <= 192-byte partials are
-    all-gathered and added on the host.  Strong scaling; device time, max over ranks."""
+    all-gathered and added on the host.  Strong scaling; device time, max over ranks.  The inputs depend on the GLOBAL
+    point index only (same points and scalars at every N), and rank 0 recomputes the whole MSM on its own GPU:
+    `matches_single_gpu` compares the sharded result with that one."""
     import numpy as np
     from crypto3_zk_b200.sharding import allgather_combine, shard_range
     out = {}
@@ -341,16 +444,17 @@ def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
         bases = ctx.msm_bases("bls12_381_g1", pts)
         ct = max(8, min(22, (cnt - 1).bit_length()))
         bases.precompute(ct, 64 << 30)
-        sc = rand_elems(torch, (nm, 8), 13, dev)[off:off + cnt].contiguous()
+        sc_all = rand_elems(torch, (nm, 8), 13, dev)
+        sc = sc_all[off:off + cnt].contiguous()
 
         def run():
             return allgather_combine("bls12_381_g1", ctx.multiexp_partial(bases, sc), device=dev)
-        for _ in range(2):
+        for _ in range(3):
             res = run()
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 5 if log_m <= 22 else 2
+        iters = 10 if log_m <= 22 else 3
         e0.record()
         for _ in range(iters):
             res = run()
@@ -358,26 +462,37 @@ def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # every rank holds the same combined point
-        chk = torch.tensor([res[0] & 0xFFFFFFFFFFFF if res else 0], dtype=torch.int64, device=dev)
-        lo, hi = chk.clone(), chk.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        out["msm_g1_2p%d_sharded" % log_m] = {"ms": float(t.item()), "n_gpus": world, "points_per_gpu": cnt, "window_bits": ct,
-                                              "scaling": "strong", "ranks_agree": bool(lo.item() == hi.item()),
-                                              "collective": "all_gather of one XYZZ partial per rank (192 B)"}
         bases.free()
         del pts, sc
+        torch.cuda.empty_cache()
+        entry = {"ms": float(t.item()), "n_gpus": world, "points_per_gpu": cnt, "window_bits": ct, "scaling": "strong",
+                 "collective": "all_gather of one XYZZ partial per rank (192 B)",
+                 "result_x_low64": (res[0] & 0xFFFFFFFFFFFFFFFF) if res else 0}
+        if rank == 0:   # the whole MSM on one GPU, same global inputs, plain variant (no table)
+            full = ctx.msm_bases("bls12_381_g1", msm_points(torch, ctx, np, log_m))
+            single = ctx.multiexp(full, sc_all)
+            full.free()
+            entry["matches_single_gpu"] = bool(single == res)
+        del sc_all
+        torch.cuda.empty_cache()
+        dist.barrier()
+        out["msm_g1_2p%d_sharded" % log_m] = entry
+    ctx.release_caches()
     return out
 
 
 def lpc_sharded_extra(args, torch, ctx, dev, dist, rank, world):
     """LPC commit of config #2 (args.batch polynomials in total) with the polynomials sharded over the ranks
     (SURVEY 8(e)): per-rank LDE, one NCCL all-to-all regroup by leaf range, per-rank subtree, top levels from
-    the all-gathered subtree roots.  Strong scaling; device time, max over ranks."""
+    the all-gathered subtree roots.  Strong scaling; device time, max over ranks.  Polynomial p is seeded by its GLOBAL
+    index (the root is the same at every N) and rank 0 commits the whole batch on its own GPU for `matches_single_gpu`."""
     from crypto3_zk_b200.sharding import lpc_commit_sharded
     per = max(1, args.batch // world)
-    x = rand_elems(torch, (per, 1 << args.log_in, 8), 2000 + rank, dev)
+    total = per * world
+
+    def poly(p):
+        return rand_elems(torch, (1, 1 << args.log_in, 8), 2000 + p, dev)
+    x = torch.cat([poly(rank * per + k) for k in range(per)], dim=0)
     out = {}
     for name, hid in (("keccak256", 0), ("sha256", 1)):
         root = lpc_commit_sharded(ctx, "pallas_fq", hid, x, args.log_in, args.log_out, 1)
@@ -385,14 +500,23 @@ def lpc_sharded_extra(args, torch, ctx, dev, dist, rank, world):
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(2):
+        for _ in range(3):
             root = lpc_commit_sharded(ctx, "pallas_fq", hid, x, args.log_in, args.log_out, 1)
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / 2], dtype=torch.float64, device=dev)
+        t = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[name] = {"ms": float(t.item()), "root": root.hex()}
-    return {"lpc_commit_config2_sharded": {"polys_total": per * world, "polys_per_gpu": per, "n_gpus": world, "scaling": "strong",
+    torch.cuda.empty_cache()
+    if rank == 0:
+        whole = torch.cat([poly(p) for p in range(total)], dim=0)
+        for name, hid in (("keccak256", 0), ("sha256", 1)):
+            single = ctx.lpc_commit("pallas_fq", hid, whole, args.log_in, args.log_out, 1)
+            out[name]["matches_single_gpu"] = bool(single.hex() == out[name]["root"])
+        del whole
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return {"lpc_commit_config2_sharded": {"polys_total": total, "polys_per_gpu": per, "n_gpus": world, "scaling": "strong",
                                            "collective": "all_to_all_single of (N-1)/N of the LDE output, all_gather of N roots", **out}}
 
 
@@ -602,16 +726,6 @@ def placeholder_extra(args, torch, ctx, dev):
     return out
 
 
-def lpc_extra(args, torch, ctx, x, hbm_peak):
-    from crypto3_zk_b200 import capi
-    res = {}
-    for name, hid in (("keccak256", capi.HASH_KECCAK_256), ("sha256", capi.HASH_SHA2_256)):
-        ms = time_cuda(torch, lambda: ctx.lpc_commit("pallas_fq", hid, x, args.log_in, args.log_out, 1), 2, warmup=1)
-        leaf_bytes = args.batch * (32 << args.log_out)
-        res[name] = {"ms": ms, "leaf_bytes_hashed": leaf_bytes, "hash_GBps_incl_lde": leaf_bytes / (ms * 1e-3) / 1e9}
-    return res
-
-
 # ------------------------------------------------------------------------------------------ main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -709,7 +823,7 @@ def main():
         hy.zero_()                    # first touch of every page from the GPU-local CPUs
         os.sched_setaffinity(0, old_aff)
         hxn, hyn = hx.numpy().view(np.uint32), hy.numpy().view(np.uint32)
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 5))
         ctx.lde("pallas_fq", hxn, args.log_in, args.log_out, out=hyn)   # warm-up (allocates staging)
         torch.cuda.synchronize()
         if dist:
@@ -739,15 +853,21 @@ def main():
     # ---- roofline of the dominant kernel (ntt_pass_kernel: every launch of the step is this kernel)
     alg_bytes = args.batch * (n_in + n_out) * 32           # read the 2 GiB input once, write the 16 GiB result once
     per_launch = alg_bytes / max(launches / args.steps, 1)
-    traffic = None   # DRAM read+write bytes per launch from the committed ncu --set full capture
+    # DRAM read+write bytes per launch from the committed ncu --set full capture.  The capture is stamped with the hash of
+    # the NTT sources it was taken from: when they have changed since, the figure is stale and reported as null.
+    traffic, traffic_note = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ntt_traffic.json")))
-        traffic = tj["dram_bytes_per_polynomial"] * args.batch / max(launches / args.steps, 1)
-    except Exception:
-        pass
+        if tj.get("ntt_sources_sha256") == ntt_sources_hash():
+            traffic = tj["dram_bytes_per_polynomial"] * args.batch / max(launches / args.steps, 1)
+            traffic_note = tj.get("source")
+        else:
+            traffic_note = "stale: profiles/ntt_traffic.json was captured from other NTT sources (%s)" % tj.get("ntt_sources_sha256", "unstamped")[:12]
+    except Exception as e:
+        traffic_note = "unavailable: " + repr(e)[:80]
     ach = alg_bytes / (ms_per_step * 1e-3) / 1e9
     line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": traffic, "peak_source": peak_src, "kernel": "ntt_pass_kernel<PallasFq>",
+                        "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "kernel": "ntt_pass_kernel<PallasFq>",
                         "algorithmic_bytes_per_launch": per_launch, "launches_per_step": launches / args.steps,
                         "avg_launch_ms": ms_per_step / max(launches / args.steps, 1)}
     # the co-limiter SURVEY 8(d) asks for next to the HBM figure: modular products per step against the measured peak of
@@ -778,24 +898,32 @@ def main():
     if rank == 0 and world == 1:
         if not args.no_cpu:
             from oracle import cref
-            th = cref.threads_available()
-            sp = max(1, min(th, 32, args.batch))
+            th = host_cores()
+            sp = max(1, min(th, args.batch))
             a = x[:sp].cpu().numpy().view(np.uint32)
-            _, t = cref.lde(3, a, args.log_in, args.log_out, threads=th)
+            t0 = time.perf_counter()
+            cref.lde(3, a, args.log_in, args.log_out, threads=th)
+            t = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": sp * n_out / t, "unit": UNIT, "cores": th, "kind": "port",
-                                    "sample": "%d of the %d polynomials (whole 2^%d->2^%d LDEs, one per thread), oracle/c port of the reference CPU algorithm" % (sp, args.batch, args.log_in, args.log_out)}
+                                    "sample": "%d of the %d polynomials (whole 2^%d->2^%d LDEs, one per thread, wall time), oracle/c port of the reference CPU algorithm" % (sp, args.batch, args.log_in, args.log_out)}
         if not args.no_extras:
             ex = {}
-            try:
-                ex["lpc_commit_config2"] = lpc_extra(args, torch, ctx, x, hbm_peak)
-            except Exception as e:   # extras must never lose the headline
-                ex["lpc_commit_config2"] = {"error": repr(e)}
             del y
             torch.cuda.empty_cache()
             try:
-                ex.update(extras(args, torch, ctx, dev, hbm_peak))
-            except Exception as e:
-                ex["error"] = repr(e)
+                parts, aux = metric_parts(args, torch, ctx, dev, hbm_peak, x)
+                # the three numbers of BASELINE.json's metric: top-level keys AND mirrored inside the objects the
+                # driver's parser is known to keep (roofline / cpu_baseline / e2e)
+                line["baseline_metric_parts"] = parts
+                for k, pt in parts.items():
+                    line["roofline"].setdefault("parts", {})[k] = dict(pt.get("roofline", {}), value=pt["value"], unit=pt["unit"])
+                    if "cpu_baseline" in pt and "cpu_baseline" in line:
+                        line["cpu_baseline"].setdefault("parts", {})[k] = pt["cpu_baseline"]
+                    if "e2e" in pt and line.get("e2e"):
+                        line["e2e"].setdefault("parts", {})[k] = pt["e2e"]
+                ex.update(aux)
+            except Exception as e:   # extras must never lose the headline
+                ex["metric_parts_error"] = repr(e)
             torch.cuda.empty_cache()
             try:
                 ex["msm_g1_sweep_bls12_381"] = msm_sweep_extra(args, torch, ctx, dev)
@@ -825,8 +953,16 @@ def main():
         except Exception as e:
             sh["msm_error"] = repr(e)
         line["extra"] = sh
+        # where the driver's parser keeps them: the strong-scaling figures and their single-GPU verification
+        line["roofline"]["sharded"] = sh
     if rank == 0:
         print(json.dumps(line))
+        try:   # the full line also goes to gpurun_out/ (copied to profiles/ by hand when it is the round's record)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "bench_last_n%d.json" % world), "w") as f:
+                json.dump(line, f, indent=1)
+        except OSError:
+            pass
     ctx.close()
     if dist:
         dist.destroy_process_group()

@@ -607,6 +607,12 @@ class Context:
                                                  _stream_ptr(out, stream)), self._h)
         return out
 
+    def bench_imad_wide(self, blocks, threads=256, iters=4096):
+        """bare IMAD.WIDE issue rate (wide multiply-adds/s): the ceiling behind the field-product peaks"""
+        r = ctypes.c_double()
+        capi.check(capi.lib().zkb_bench_imad_wide(self._h, blocks, threads, iters, ctypes.byref(r)), self._h)
+        return r.value
+
     def bench_field_mul(self, field, blocks, threads=256, iters=4096):
         r = ctypes.c_double()
         capi.check(capi.lib().zkb_bench_field_mul(self._h, _field_id(field), blocks, threads, iters, ctypes.byref(r)), self._h)

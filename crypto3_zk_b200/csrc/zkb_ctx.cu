@@ -6,7 +6,24 @@
 
 using namespace zkb;
 
+#include <mutex>
+#include <set>
+
 namespace zkb {
+
+// Live contexts: handles (Merkle trees, sparse matrices) may outlive the context they were made with (Python frees them
+// from __del__, after Context.close()); their free functions ask here before they touch the context's pools.
+static std::mutex g_ctx_mutex;
+static std::set<const zkb_ctx *> g_live_ctx;
+bool ctx_alive(const zkb_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    return g_live_ctx.count(ctx) != 0;
+}
+static void ctx_register(const zkb_ctx *ctx, bool live) {
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    if (live) g_live_ctx.insert(ctx);
+    else g_live_ctx.erase(ctx);
+}
 
 int ctx_fail(zkb_ctx *ctx, int status, const std::string &msg) {
     if (ctx) ctx->last_error = msg;
@@ -161,6 +178,7 @@ int zkb_ctx_create(int device, zkb_ctx **out) {
     zkb_ctx *c = new zkb_ctx();
     c->device = device;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    zkb::ctx_register(c, true);
     *out = c;
     return ZKB_OK;
 }
@@ -184,6 +202,7 @@ int zkb_ctx_release_caches(zkb_ctx *ctx) {
 
 void zkb_ctx_destroy(zkb_ctx *ctx) {
     if (!ctx) return;
+    zkb::ctx_register(ctx, false);
     zkb_ctx_release_caches(ctx);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -290,6 +309,57 @@ extern "C" int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uin
     if (!ctx || !muls_per_s || threads == 0 || threads > 256 || blocks == 0) return ZKB_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     ZKB_DISPATCH_ANY_FIELD(field, bench_field_mul, ctx, blocks, threads, iters, muls_per_s)
+}
+
+// Bare IMAD.WIDE issue-rate probe: shares no code with the Montgomery multiplier.  Every thread keeps 8 independent
+// 64-bit accumulators and issues mad.wide.u32 on them round-robin (8 chains hide the ~4-cycle dependent latency), with
+// multiplicands that change every round so nothing folds.  wide-multiply-adds/s measured here, divided by the wide
+// count of a product (112 BLS12-381 Fr, 88 Pallas, 300 BLS12-381 Fq), is the ceiling the field-product peaks above are
+// checked against.
+__global__ void __launch_bounds__(256) bench_imad_wide_kernel(uint32_t iters, uint32_t seed, uint64_t *out) {
+    uint64_t acc[8];
+    uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed + blockIdx.x * 40503u + 1u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(k + 1) * 0x9e3779b97f4a7c15ull;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + (uint32_t)k), "r"(b));
+            b = (uint32_t)acc[r] | 1u;       // data dependent multiplicand for the next round (one ALU op per 8 wide ops)
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r ^= acc[k];
+    if (r == 0x123456789abcdef0ull) out[0] = r;   // practically never: keeps the chains live
+}
+
+extern "C" int zkb_bench_imad_wide(zkb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, double *wide_per_s) {
+    if (!ctx || !wide_per_s || threads == 0 || threads > 256 || blocks == 0 || iters == 0) return ZKB_ERR_INVALID_ARGUMENT;
+    ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    void *out;
+    ZKB_TRY(ctx_scratch(ctx, "bench", 64, &out));
+    cudaEvent_t e0, e1;
+    ZKB_CUDA_OK(ctx, cudaEventCreate(&e0));
+    ZKB_CUDA_OK(ctx, cudaEventCreate(&e1));
+    bench_imad_wide_kernel<<<blocks, threads>>>(16, 12345u, (uint64_t *)out);   // warm-up
+    ZKB_CUDA_OK(ctx, cudaEventRecord(e0));
+    bench_imad_wide_kernel<<<blocks, threads>>>(iters, 12345u, (uint64_t *)out);
+    ZKB_CUDA_OK(ctx, cudaEventRecord(e1));
+    ZKB_CUDA_OK(ctx, cudaEventSynchronize(e1));
+    ctx->launches += 2;
+    float ms = 0;
+    ZKB_CUDA_OK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *wide_per_s = 32.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    return ZKB_OK;
+}
+
+extern "C" void zkb_ctx_clear_error(zkb_ctx *ctx) {
+    if (ctx) ctx->last_error.clear();
 }
 
 // ------------------------------------------------------------------------------------ device buffers for host templates

@@ -19,6 +19,7 @@ using namespace zkb;
 
 struct zkb_merkle_tree {
     zkb_ctx *ctx;
+    int device;        // the tree may be freed after its context: then the buffer goes straight back to the driver
     int hash;
     int digest_bytes;
     uint64_t leaves;
@@ -404,6 +405,7 @@ int zkb::merkle_build_device(zkb_ctx *ctx, int hash, int log_d, int fri_step, ui
     if (keep) {
         zkb_merkle_tree *t = new zkb_merkle_tree();
         t->ctx = ctx;
+        t->device = ctx->device;
         t->hash = hash;
         t->digest_bytes = db;
         t->leaves = leaves;
@@ -422,8 +424,9 @@ uint64_t zkb_merkle_leaves(const zkb_merkle_tree *t) { return t ? t->leaves : 0;
 void zkb_merkle_free(zkb_merkle_tree *t) {
     if (!t) return;
     if (t->d_nodes) {
-        cudaSetDevice(t->ctx->device);
-        zkb::ctx_tree_release(t->ctx, t->d_nodes, t->nodes_cap);
+        cudaSetDevice(t->device);
+        if (zkb::ctx_alive(t->ctx)) zkb::ctx_tree_release(t->ctx, t->d_nodes, t->nodes_cap);
+        else cudaFree(t->d_nodes);
     }
     delete t;
 }

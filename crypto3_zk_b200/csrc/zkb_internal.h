@@ -33,6 +33,8 @@ struct zkb_ctx {
 namespace zkb {
 
 int ctx_fail(zkb_ctx *ctx, int status, const std::string &msg);
+// false once zkb_ctx_destroy has run on this pointer (handles that outlive their context must not touch it)
+bool ctx_alive(const zkb_ctx *ctx);
 // returns a device buffer of at least `bytes` (reallocates when too small)
 int ctx_scratch(zkb_ctx *ctx, const char *role, size_t bytes, void **out);
 // device memory of a kept Merkle tree: taken from / returned to ctx->tree_pool (bounded by the scratch limit)

@@ -337,6 +337,7 @@ static int poly_div_linear_t(zkb_ctx *ctx, uint64_t n, const void *d_in, const u
 #define ZKB_SPMV_SEG 4096
 struct zkb_sparse_matrix {
     zkb_ctx *ctx;
+    int device;   // freed with plain cudaFree on this device: the matrix may outlive its context
     int field;
     uint64_t rows, cols, nnz;
     uint64_t *d_row_ptr;
@@ -510,7 +511,7 @@ int zkb_sparse_matrix_create(zkb_ctx *ctx, int field, uint64_t rows, uint64_t co
     ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     zkb_sparse_matrix *m = new zkb_sparse_matrix();
-    m->ctx = ctx; m->field = field; m->rows = rows; m->cols = cols; m->nnz = nnz;
+    m->ctx = ctx; m->device = ctx->device; m->field = field; m->rows = rows; m->cols = cols; m->nnz = nnz;
     m->d_row_ptr = nullptr; m->d_col = nullptr; m->d_val = nullptr;
     m->d_seg = nullptr; m->d_long = nullptr; m->d_partial = nullptr;
     std::vector<uint64_t> segs, longs;
@@ -558,7 +559,7 @@ int zkb_sparse_matrix_create(zkb_ctx *ctx, int field, uint64_t rows, uint64_t co
 
 void zkb_sparse_matrix_free(zkb_sparse_matrix *m) {
     if (!m) return;
-    cudaSetDevice(m->ctx->device);
+    cudaSetDevice(m->device);
     if (m->d_row_ptr) cudaFree(m->d_row_ptr);
     if (m->d_col) cudaFree(m->d_col);
     if (m->d_val) cudaFree(m->d_val);

@@ -102,16 +102,26 @@ class ProvingKey:
         self.mats = [ctx.sparse_matrix(self.F.name, nc, cs.num_variables + 1, *sides[k]) for k in range(3)]
 
 
-def witness_map(ctx, pk, x):
+def witness_map(ctx, pk, x, check_satisfied=False):
     """r1cs_to_qap<F>::witness_map with d1 = d2 = d3 = 0 (prover.hpp:78-82): x = (1, primary, auxiliary) on the device
-    -> coefficients_for_H [m, 8] (the entries m-1 and m of the reference's m+1 vector are zero by construction)."""
+    -> coefficients_for_H [m, 8] (the entries m-1 and m of the reference's m+1 vector are zero by construction).
+    check_satisfied: the reference's precondition `constraint_system.is_satisfied(primary, auxiliary)` (prover.hpp:77,
+    r1cs_to_qap.hpp:225) on the row values <a_i, x> <b_i, x> - <c_i, x> the map computes anyway; raises when it fails
+    (without it an unsatisfying assignment silently yields a garbage proof: the division by Z drops the remainder)."""
     import torch
     F, m, log_m = pk.F, pk.m, pk.log_m
     cs = pk.cs
     nc, ni = cs.num_constraints, cs.num_inputs
+    if tuple(x.shape) != (cs.num_variables + 1, 8):
+        raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "assignment must be [num_variables + 1, 8] limbs (1, primary, auxiliary)")
     abc = torch.zeros((3, m, 8), dtype=torch.int32, device=x.device)
     for k in range(3):
         pk.mats[k].matvec(x, abc[k])
+    if check_satisfied:
+        one = 1
+        resid = ctx.vec(F.name, capi.VEC_MUL_SUB_SCALE, abc[0, :nc], abc[1, :nc], abc[2, :nc], scalar=one)
+        if bool(resid.any().item()) or not bool((x[0] == torch.tensor([1, 0, 0, 0, 0, 0, 0, 0], dtype=torch.int32, device=x.device)).all().item()):
+            raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "the assignment does not satisfy the constraint system (prover.hpp:77)")
     abc[0, nc:nc + ni + 1] = x[:ni + 1]          # the input-consistency constraints input_i * 0 = 0 (:239-242)
     ctx.ntt(F.name, abc, log_m, inverse=True)
     ctx.ntt(F.name, abc, log_m, coset_shift=F.generator)
@@ -121,7 +131,7 @@ def witness_map(ctx, pk, x):
     return h
 
 
-def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None, concurrent=False):
+def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None, concurrent=False, check_satisfied=True):
     """Returns (g1_A, g2_B, g1_C) in affine form.  r, s: the prover's zero-knowledge randomness (the reference draws
     them with algebra::random_element, prover.hpp:91-92).  x_device: optional device tensor with the full assignment
     (1, primary, auxiliary) as [num_variables + 1, 8] limbs; otherwise it is uploaded from the Python integers.
@@ -140,7 +150,7 @@ def prove(ctx, pk, primary_input, auxiliary_input, r, s, x_device=None, concurre
             raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "assignment size does not match the constraint system")
         x_device = torch.from_numpy(_int_rows(full).view(np.int32)).to(dev)
     x = x_device
-    h = witness_map(ctx, pk, x)
+    h = witness_map(ctx, pk, x, check_satisfied=check_satisfied)
 
     def head(*vals):
         return torch.from_numpy(_int_rows([v % p for v in vals]).view(np.int32)).to(dev)
@@ -261,6 +271,8 @@ def generator(ctx, curve_g1, curve_g2, cs, t, alpha, beta, gamma, delta, g1_gene
     F = FIELD_BY_NAME[g1.scalar_field]
     p = F.p
     t, alpha, beta, gamma, delta = (int(v) % p for v in (t, alpha, beta, gamma, delta))
+    if gamma == 0 or delta == 0:
+        raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "gamma and delta must be invertible (generator.hpp:162-163)")
     cs = swap_ab_if_beneficial(cs)
     At, Bt, Ct, Ht, Zt, m = qap_instance_evaluation(cs, F, t)
     ginv, dinv = pow(gamma, p - 2, p), pow(delta, p - 2, p)

@@ -45,6 +45,7 @@ inline void check(int status, zkb_ctx *ctx, const char *what) {
     if (status == ZKB_OK) return;
     std::string msg = std::string(what) + ": " + zkb_status_string(status);
     if (ctx && *zkb_ctx_last_error(ctx)) msg += std::string(" (") + zkb_ctx_last_error(ctx) + ")";
+    if (ctx) zkb_ctx_clear_error(ctx);   // consumed: a later failure that records no message must not show this one
     if (status == ZKB_ERR_INVALID_ARGUMENT || status == ZKB_ERR_DOMAIN_TOO_LARGE) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);
 }

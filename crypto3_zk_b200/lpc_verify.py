@@ -59,7 +59,12 @@ def _correct_order(x_index, domain_size, fri_step, s_indices):
     return out
 
 
-def _merkle_validate(proof, data, h):
+def _merkle_validate(proof, data, h, index, depth):
+    """merkle_proof::validate plus what the reference leaves unchecked: the opened leaf must be the one the query selects
+    (`index`) and the path must span the whole tree (`depth` levels) - without the two a prover may open another leaf,
+    or pass a 64-byte inner node off as a two-element leaf (there is no leaf/node domain separation)."""
+    if proof["index"] != index or len(proof["path"]) != depth:
+        return False
     d, idx = h(data), proof["index"]
     for sib in proof["path"]:
         d = h(sib + d) if idx & 1 else h(d + sib)
@@ -102,6 +107,19 @@ def fri_verify_eval(field, hash_id, fri, proof, commitments, theta, poly_ids, co
     nbytes = (p.bit_length() + 7) // 8
     if not steps or steps[-1] != 1 or any(s < 1 or s > 10 for s in steps):
         return False
+    try:
+        return _fri_verify_eval(F, h, nbytes, fri, proof, commitments, theta, poly_ids, combined_U, denominators, transcript)
+    except (KeyError, IndexError, TypeError, ValueError, AttributeError):
+        return False         # malformed proof structure: reject, never raise
+
+
+def _fri_verify_eval(F, h, nbytes, fri, proof, commitments, theta, poly_ids, combined_U, denominators, transcript):
+    p, steps, log_d0 = F.p, fri.step_list, fri.log_d0
+    if len(proof["fri_roots"]) != len(steps) or len(proof["query_proofs"]) != fri.lambda_:
+        return False
+    for qp in proof["query_proofs"]:
+        if len(qp["round_proofs"]) != len(steps) or set(qp["initial_proof"]) != set(commitments):
+            return False
     fp = proof["final_polynomial"]
     deg = max((i for i, v in enumerate(fp) if v), default=0)
     if deg > 2 ** (fri.degree_log - fri.r + 1) - 1:
@@ -127,7 +145,7 @@ def fri_verify_eval(field, hash_id, fri, proof, commitments, theta, poly_ids, co
             if ip["p"]["root"] != commitments[k]:
                 return False
             data = [v for vals in ip["values"] for pos in order for v in vals[pos]]
-            if not _merkle_validate(ip["p"], _leaf(data, nbytes), h):
+            if not _merkle_validate(ip["p"], _leaf(data, nbytes), h, _folded(x_index, domain_size, steps[0]), log_d0 - steps[0]):
                 return False
         theta_acc = 1
         y = [[0, 0] for _ in range(half)]
@@ -151,7 +169,8 @@ def fri_verify_eval(field, hash_id, fri, proof, commitments, theta, poly_ids, co
                 return False
             s, s_idx = _calculate_s(x_index, step, log_d0 - t, F)
             order = _correct_order(x_index, domain_size, step, s_idx)
-            if not _merkle_validate(rp["p"], _leaf([v for pos in order for v in y[pos]], nbytes), h):
+            if not _merkle_validate(rp["p"], _leaf([v for pos in order for v in y[pos]], nbytes), h,
+                                    _folded(x_index, domain_size, step), log_d0 - t - step):
                 return False
             for _ in range(step - 1):            # colinear checks inside a multi-step round
                 domain_size = sizes(t)
@@ -192,7 +211,17 @@ def fri_verify_eval(field, hash_id, fri, proof, commitments, theta, poly_ids, co
 def lpc_verify_eval(field, hash_id, fri, proof, points, commitments, transcript, fixed_batches=(), etha=None, fixed_values=None):
     """lpc_commitment_scheme::verify_eval (lpc.hpp:202-263).  points: {k: [[point, ..] per polynomial]}."""
     F = FIELD_BY_NAME[field] if isinstance(field, str) else field
-    p, z = F.p, proof["z"]
+    try:
+        p, z = F.p, proof["z"]
+        if set(z) != set(points) or set(z) != set(commitments):
+            return False
+        for k in z:
+            if len(z[k]) != len(points[k]) or any(len(z[k][j]) != len(points[k][j]) for j in range(len(z[k]))):
+                return False
+        if fixed_batches and any(len(fixed_values[k]) != len(z[k]) for k in fixed_batches if k in z):
+            return False
+    except (KeyError, IndexError, TypeError, AttributeError):
+        return False
     for k in sorted(commitments):
         transcript(commitments[k])
     uniq = []

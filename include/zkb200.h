@@ -73,7 +73,10 @@ const char *zkb_status_string(int status);
 int zkb_device_count(void);
 int zkb_ctx_create(int device, zkb_ctx **out);
 void zkb_ctx_destroy(zkb_ctx *ctx);
+/* message of the most recent failing call on this context that recorded one ("" if none); wrappers read it right
+ * after a non-zero status and then call zkb_ctx_clear_error so a later failure without a message cannot show it */
 const char *zkb_ctx_last_error(const zkb_ctx *ctx);
+void zkb_ctx_clear_error(zkb_ctx *ctx);
 /* upper bound for internal scratch (bytes; default 6 GiB): batches are processed in chunks */
 int zkb_ctx_set_scratch_limit(zkb_ctx *ctx, uint64_t bytes);
 /* drops cached twiddle tables and scratch */
@@ -268,6 +271,9 @@ int zkb_g1_grid_points(zkb_ctx *ctx, int curve, uint64_t n, uint32_t m, const vo
 /* ---- micro-benchmarks used for the integer-pipe roofline (bench.py) ------------------ */
 /* runs `iters` dependent Montgomery multiplications per thread on `threads` threads; returns field-mul/s */
 int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uint32_t threads, uint32_t iters, double *muls_per_s);
+/* bare IMAD.WIDE (mad.wide.u32) issue rate, 8 independent chains per thread, no field code: 32 * iters wide
+ * multiply-adds per thread; returns wide multiply-adds/s.  The independent ceiling behind the product peaks. */
+int zkb_bench_imad_wide(zkb_ctx *ctx, uint32_t blocks, uint32_t threads, uint32_t iters, double *wide_per_s);
 
 /* ---- fixed-base batch exponentiation: the Groth16 generator ----------------------------------- */
 /* algebra::batch_exp<G, Fr>(scalar_size, window, table, v) and the windowed_exp calls of kc_batch_exp

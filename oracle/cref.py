@@ -43,6 +43,15 @@ def threads_available():
     return int(lib().orc_threads_available())
 
 
+def host_cores():
+    """Cores this process may run on (sched affinity).  torchrun exports OMP_NUM_THREADS=1, which makes
+    omp_get_max_threads() - threads_available() - answer 1: callers pass this count as `threads` explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 

@@ -66,7 +66,43 @@ def test_product_verifier_on_oracle_proofs(steps, degree_log, expand, grind, hna
         lambda b: b["fri_proof"]["query_proofs"][0]["round_proofs"][-1]["y"][0].__setitem__(
             1, (b["fri_proof"]["query_proofs"][0]["round_proofs"][-1]["y"][0][1] + 1) % p),
         lambda b: b["fri_proof"]["query_proofs"][1]["round_proofs"][0]["p"].__setitem__("index", 0 if b["fri_proof"]["query_proofs"][1]["round_proofs"][0]["p"]["index"] else 1),
+        # malformed structures are rejected, never raised: missing query, missing round, missing batch, short path
+        lambda b: b["fri_proof"]["query_proofs"].pop(),
+        lambda b: b["fri_proof"]["query_proofs"][2]["round_proofs"].pop(),
+        lambda b: b["z"].pop(3),
+        lambda b: b["fri_proof"]["query_proofs"][0]["initial_proof"].pop(1),
+        lambda b: b["fri_proof"]["query_proofs"][0]["initial_proof"][0]["p"]["path"].pop(),
+        lambda b: b["fri_proof"]["fri_roots"].pop(),
     ):
         bad = copy.deepcopy(proof)
         mutate(bad)
         assert not run(bad)[0]
+
+
+def test_merkle_validate_binds_index_and_depth():
+    """a path that is consistent with the root but opens another leaf, or stops one level short (an inner
+    node passed off as a leaf), must not validate."""
+    h = hashes.HASHES["keccak256"][1]
+    leaves = [bytes([i]) * 64 for i in range(8)]
+    lvl = [h(x) for x in leaves]
+    levels = [lvl]
+    while len(lvl) > 1:
+        lvl = [h(lvl[i] + lvl[i + 1]) for i in range(0, len(lvl), 2)]
+        levels.append(lvl)
+    root = levels[-1][0]
+
+    def path(i):
+        out = []
+        for l in levels[:-1]:
+            out.append(l[i ^ 1])
+            i >>= 1
+        return out
+    good = {"index": 5, "path": path(5), "root": root}
+    assert lpc_verify._merkle_validate(good, leaves[5], h, 5, 3)
+    assert not lpc_verify._merkle_validate(good, leaves[5], h, 4, 3)            # not the queried leaf
+    other = {"index": 4, "path": path(4), "root": root}
+    assert not lpc_verify._merkle_validate(other, leaves[4], h, 5, 3)           # a valid opening of another leaf
+    # inner node (h(l4) || h(l5)) presented as a 64-byte leaf with a path one level short
+    inner = {"index": 2, "path": path(5)[1:], "root": root}
+    assert lpc_verify._merkle_validate.__code__.co_argcount == 5
+    assert not lpc_verify._merkle_validate(inner, levels[0][4] + levels[0][5], h, 2, 3)
