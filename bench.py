@@ -274,15 +274,13 @@ def metric_parts(args, torch, ctx, dev, hbm_peak, x_lde):
     sc = rand_elems(torch, (nm, 8), 13, dev)
     msm_plain_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 10, warmup=3)
     res_plain = ctx.multiexp(bases, sc)
-    c = max(2, min(20, log_m - 4))
-    W = (255 + 1 + c - 1) // c
+    c, W, _ = bases.window_plan(nm)
     plain_mults = nm * W * 10 + W * (1 << (c - 1)) * 2 * 14 + 255 * 8   # SURVEY 8(d) work model
     # long-lived bases (KZG key / Groth16 query): one-off window table 2^(c w) P_i, all windows share one bucket set
-    ct = max(8, min(22, log_m))
-    Wt = (255 + 1 + ct - 1) // ct
     t0 = time.perf_counter()
-    bases.precompute(ct, 64 << 30)
+    bases.precompute(0, 64 << 30)
     table_build_ms = (time.perf_counter() - t0) * 1e3
+    ct, Wt, _ = bases.window_plan(nm)
     msm_ms = time_cuda(torch, lambda: ctx.multiexp(bases, sc), 10, warmup=3)
     res_table = ctx.multiexp(bases, sc)
     fq_mults = nm * Wt * 10 + (1 << (ct - 1)) * 2 * 14
@@ -409,13 +407,13 @@ def msm_sweep_extra(args, torch, ctx, dev):
             del pts
             sc = rand_elems(torch, (nm, 8), 13, dev)
             iters = 5 if log_m <= 22 else 2
-            e = {"ms": time_cuda(torch, lambda: ctx.multiexp(bases, sc), iters, warmup=1), "window_bits": max(2, min(20, log_m - 4))}
-            ct = max(8, min(22, log_m))
-            Wt = (255 + 1 + ct - 1) // ct
-            if nm * Wt * 96 <= (24 << 30):
-                bases.precompute(ct, 24 << 30)
+            e = {"ms": time_cuda(torch, lambda: ctx.multiexp(bases, sc), iters, warmup=1), "window_bits": bases.window_plan(nm)[0]}
+            try:
+                bases.precompute(0, 24 << 30)
                 e["ms_window_table"] = time_cuda(torch, lambda: ctx.multiexp(bases, sc), iters, warmup=1)
-                e["table_window_bits"] = ct
+                e["table_window_bits"] = bases.window_plan(nm)[0]
+            except Exception:   # table larger than 24 GiB: plain variant only
+                pass
             e["points_per_s"] = nm / (min(e["ms"], e.get("ms_window_table", e["ms"])) * 1e-3)
             out["2p%d" % log_m] = e
             bases.free()
@@ -442,8 +440,8 @@ def msm_sharded_extra(args, torch, ctx, dev, dist, rank, world):
         off, cnt = off * 1024, cnt * 1024
         pts = msm_points(torch, ctx, np, log_m, off, cnt)
         bases = ctx.msm_bases("bls12_381_g1", pts)
-        ct = max(8, min(22, (cnt - 1).bit_length()))
-        bases.precompute(ct, 64 << 30)
+        bases.precompute(0, 64 << 30)
+        ct = bases.window_plan(cnt)[0]
         sc_all = rand_elems(torch, (nm, 8), 13, dev)
         sc = sc_all[off:off + cnt].contiguous()
 

@@ -184,6 +184,13 @@ class MsmBases:
                                                        _stream_ptr(None, stream)), self._ctx._h)
         return self
 
+    def window_plan(self, n=None):
+        """(widest window in bits, digit windows, bucket sets) zkb_msm uses for n scalars on these bases"""
+        c, w, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        capi.check(capi.lib().zkb_msm_window_plan(self._h, self.n if n is None else n, ctypes.byref(c), ctypes.byref(w),
+                                                  ctypes.byref(b)), self._ctx._h)
+        return c.value, w.value, b.value
+
     def free(self):
         if self._h:
             capi.lib().zkb_msm_bases_free(self._h)

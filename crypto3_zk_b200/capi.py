@@ -20,7 +20,7 @@ SYMBOLS = [
     "zkb_ntt", "zkb_lde", "zkb_vec", "zkb_fri_fold", "zkb_lpc_commit", "zkb_merkle_commit",
     "zkb_merkle_digest_bytes", "zkb_merkle_root_of_digests", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
-    "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul", "zkb_bench_imad_wide", "zkb_ctx_clear_error",
+    "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul", "zkb_bench_imad_wide", "zkb_ctx_clear_error", "zkb_msm_window_plan",
     "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
     "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec", "zkb_pow_grind", "zkb_merkle_paths", "zkb_poly_evaluate_pm",
     "zkb_lde_with_coefficients", "zkb_batch_exp", "zkb_permutation_grand_product", "zkb_lookup_grand_product", "zkb_prefix_product", "zkb_batch_inverse", "zkb_buf_alloc", "zkb_buf_free", "zkb_buf_copy", "zkb_buf_zero", "zkb_gather",
@@ -95,6 +95,7 @@ def lib():
     L.zkb_msm.argtypes = [vp, vp, u64, u64, vp, i, u32p, vp]
     L.zkb_msm_partial.argtypes = [vp, vp, u64, u64, vp, i, u32p, vp]
     L.zkb_msm_combine.argtypes = [i, u32, u32p, u32p]
+    L.zkb_msm_window_plan.argtypes = [vp, u64, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
     L.zkb_msm_g1.argtypes = [vp, i, u64, vp, vp, i, u32p, vp]
     L.zkb_g1_grid_points.argtypes = [vp, i, u64, u32, vp, vp, vp, vp]
     L.zkb_bench_field_mul.argtypes = [vp, i, u32, u32, u32, ctypes.POINTER(ctypes.c_double)]

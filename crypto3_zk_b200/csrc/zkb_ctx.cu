@@ -311,28 +311,32 @@ extern "C" int zkb_bench_field_mul(zkb_ctx *ctx, int field, uint32_t blocks, uin
     ZKB_DISPATCH_ANY_FIELD(field, bench_field_mul, ctx, blocks, threads, iters, muls_per_s)
 }
 
-// Bare IMAD.WIDE issue-rate probe: shares no code with the Montgomery multiplier.  Every thread keeps 8 independent
-// 64-bit accumulators and issues mad.wide.u32 on them round-robin (8 chains hide the ~4-cycle dependent latency), with
-// multiplicands that change every round so nothing folds.  wide-multiply-adds/s measured here, divided by the wide
-// count of a product (112 BLS12-381 Fr, 88 Pallas, 300 BLS12-381 Fq), is the ceiling the field-product peaks above are
-// checked against.
+// Bare IMAD.WIDE issue-rate probe: shares no code with the Montgomery multiplier.  Every thread keeps 16 independent
+// 64-bit accumulators and issues mad.wide.u32 on them round-robin (16 chains cover the dependent-issue latency), with a
+// multiplicand that changes every round (one ALU add per 16 wide ops) so nothing folds.  wide multiply-adds/s measured
+// here, divided by the wide count of a product (112 BLS12-381 Fr, 88 Pallas, 300 BLS12-381 Fq), is the ceiling the
+// field-product peaks above are checked against.
 __global__ void __launch_bounds__(256) bench_imad_wide_kernel(uint32_t iters, uint32_t seed, uint64_t *out) {
-    uint64_t acc[8];
-    uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed + blockIdx.x * 40503u + 1u;
+    uint64_t acc[16];
+    uint32_t a[16];
+    uint32_t b = seed + blockIdx.x * 40503u + 1u;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(k + 1) * 0x9e3779b97f4a7c15ull;
+    for (int k = 0; k < 16; k++) {
+        acc[k] = (uint64_t)(k + 1) * 0x9e3779b97f4a7c15ull;
+        a[k] = (seed ^ (threadIdx.x * 2654435761u)) + 0x01000193u * (uint32_t)k;
+    }
     for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 2; r++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + (uint32_t)k), "r"(b));
-            b = (uint32_t)acc[r] | 1u;       // data dependent multiplicand for the next round (one ALU op per 8 wide ops)
+            for (int k = 0; k < 16; k++)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a[k]), "r"(b));
+            b += 0x9e3779b9u;
         }
     }
     uint64_t r = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) r ^= acc[k];
+    for (int k = 0; k < 16; k++) r ^= acc[k];
     if (r == 0x123456789abcdef0ull) out[0] = r;   // practically never: keeps the chains live
 }
 

@@ -15,12 +15,18 @@
 //                 tasks of a warp run the same number of additions (bucket sizes are Poisson distributed;
 //                 unsorted, a warp waits for its longest bucket: ~30 % of the lanes idle at 32 points/bucket)
 //   5 accumulate  one thread per task: XYZZ += affine point (mixed add, 8M+2S)
-//   6 reduce      per window S_w = sum_k (k+1) B_k by a radix-MSM_RED_L tree: every node turns L children
-//                 (A_j = plain sum, U_j = weighted sum relative to the child's start) into
-//                 A = sum A_j, U = sum U_j + span * sum j A_j  - short running sums at every level,
-//                 65536 threads at the leaves, no serial pass over the 2^(c-1) buckets of a window
+//   6 reduce      per window S_w = sum_k (k+1) B_k.  Level 0: every node turns MSM_RED_L = 8 buckets into
+//                 (A = plain sum, U = sum j B_j, j local) with three short running sums spread over adjacent lanes.
+//                 Tail ("bit tree"): S_w = sum U_s + sum A_s + 8 sum_s s A_s, and sum_s s A_s = sum_b 2^b T_b with
+//                 T_b = sum of the A_s whose index has bit b set.  A stage kernel folds 256 entries per block in shared
+//                 memory, 8 binary levels of mutually independent additions (depth 8, not 8 x 9), and hands on the
+//                 plain sum plus the 8 subset sums; plain rows (U, earlier T_b) are just summed.  Two or three stages
+//                 shrink 2^16 nodes to one, and one warp finishes with a quad-cooperative Horner over the bits.
+//                 (Round 1 ran radix-8 (A, U) levels all the way up: 6 latency-bound launches with growing span
+//                 doublings, 1.14 ms at 2^19 buckets; the tail is now ~0.25 ms.)
 //   7 combine     sum_w 2^(c w) S_w on the host (c W doublings; zkb_msm_host.cpp)
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #ifndef ZKB_MSM_MUL_INLINE
 #define ZKB_MUL_OUTLINE 1
@@ -31,7 +37,25 @@
 using namespace zkb;
 
 namespace zkb {
-int msm_window_combine(int curve, int c, int W, const uint32_t *sums, uint32_t *out);
+int msm_window_combine(int curve, int W, int base, int rem, const uint32_t *sums, uint32_t *out);
+}
+
+// Digit windows.  total = scalar bits + 1 (the spare bit absorbs the last carry of the signed recoding) is cut into
+// W = ceil(total / c) windows of ALMOST EQUAL width: the first `rem` windows have base + 1 bits, the others base bits.
+// With windows at multiples of c the top window of a 255-bit scalar keeps 256 mod c bits - 4 bits for c = 18: eight
+// buckets then hold an eighth of all points each and the MSM waits for them (2^18 points: 4.6 ms instead of 2.6).
+struct MsmWindows {
+    int W, base, rem;
+    __host__ __device__ int width(int w) const { return base + (w < rem ? 1 : 0); }
+    __host__ __device__ int pos(int w) const { return w * base + (w < rem ? w : rem); }
+    __host__ __device__ int max_width() const { return base + (rem ? 1 : 0); }
+};
+static MsmWindows msm_windows(int total_bits, int W) {
+    MsmWindows m;
+    m.W = W;
+    m.base = total_bits / W;
+    m.rem = total_bits % W;
+    return m;
 }
 
 struct zkb_msm_bases {
@@ -76,18 +100,27 @@ __global__ void __launch_bounds__(256) points_to_mont_kernel(uint64_t n, Affine<
 
 // scalars: 8 canonical limbs each.  keys[w * n + i]
 // win_stride = buckets per window (2^(c-1)), or 0 when all windows share one bucket set (window table)
-__global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint32_t *__restrict__ scalars, int c, int W,
-                                                         uint32_t win_stride, uint32_t *__restrict__ keys,
-                                                         uint32_t *__restrict__ counts) {
+// A scalar with a bit at or above `scalar_bits` (not a canonical element of the scalar field) would overflow the top
+// window's bucket range: it is skipped and reported through *bad (the call then fails with ZKB_ERR_INVALID_ARGUMENT).
+__global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint32_t *__restrict__ scalars, MsmWindows win,
+                                                         int scalar_bits, uint32_t win_stride, uint32_t *__restrict__ keys,
+                                                         uint32_t *__restrict__ counts, uint32_t *__restrict__ bad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int W = win.W;
     const uint4 *sp = reinterpret_cast<const uint4 *>(scalars) + 2 * (uint64_t)i;
     uint4 lo = sp[0], hi = sp[1];
     uint32_t l[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0};
-    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    if (scalar_bits < 256 && (hi.w >> (scalar_bits - 224)) != 0) {
+        atomicOr(bad, 1u);
+        for (int w = 0; w < W; w++) keys[(uint64_t)w * n + i] = MSM_SENTINEL;
+        return;
+    }
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
-        uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+        const int c = win.width(w);
+        const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+        uint32_t bit = win.pos(w), limb = bit >> 5, sh = bit & 31;
         uint64_t two = limb < 8 ? ((uint64_t)l[limb] | ((uint64_t)l[limb + 1] << 32)) : 0;
         uint32_t raw = ((uint32_t)(two >> sh) & mask) + carry;
         uint32_t key = MSM_SENTINEL;
@@ -110,12 +143,12 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(uint32_t n, const uint3
 }
 
 // tasks per bucket from the bucket sizes; buckets split into more than MSM_HEAVY_MIN_TASKS tasks are listed in `heavy`
-__global__ void __launch_bounds__(256) msm_ntasks_kernel(uint32_t nb, const uint32_t *__restrict__ counts,
+__global__ void __launch_bounds__(256) msm_ntasks_kernel(uint32_t nb, uint32_t task_cap, const uint32_t *__restrict__ counts,
                                                          uint32_t *__restrict__ ntasks, uint32_t *__restrict__ n_heavy,
                                                          uint32_t *__restrict__ heavy, uint32_t heavy_cap) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    uint32_t nt = (counts[b] + MSM_TASK_CAP - 1) / MSM_TASK_CAP;
+    uint32_t nt = (counts[b] + task_cap - 1) / task_cap;
     ntasks[b] = nt;
     if (nt > MSM_HEAVY_MIN_TASKS) {   // a few tasks are added serially by the level-0 reduce
         uint32_t k = atomicAdd(n_heavy, 1u);
@@ -201,16 +234,16 @@ struct MsmTask {
 };
 
 // one thread per bucket: emit its tasks
-__global__ void __launch_bounds__(256) msm_fill_tasks_kernel(uint32_t nb, const uint32_t *__restrict__ counts,
+__global__ void __launch_bounds__(256) msm_fill_tasks_kernel(uint32_t nb, uint32_t task_cap, const uint32_t *__restrict__ counts,
                                                              const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ task_offsets, MsmTask *tasks) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t cnt = counts[b], off = offsets[b], t = task_offsets[b];
-    for (uint32_t s = 0; s < cnt; s += MSM_TASK_CAP, t++) {
+    for (uint32_t s = 0; s < cnt; s += task_cap, t++) {
         MsmTask k;
         k.start = off + s;
-        k.len = cnt - s < MSM_TASK_CAP ? cnt - s : MSM_TASK_CAP;
+        k.len = cnt - s < task_cap ? cnt - s : task_cap;
         tasks[t] = k;
     }
 }
@@ -345,32 +378,27 @@ __global__ void __launch_bounds__(256) msm_heavy_tree_kernel(const uint32_t *__r
 }
 
 // ------------------------------------------------------------------------------------ reduce
-// One tree level.  Items of a window are (A, U) pairs (level 0: A = bucket value = sum of the bucket's task
-// results, U = 0).  Node (w, s) folds items s*L .. s*L+L-1:
-//     A' = sum_j A_j                                   ("run": running sum from the top item down)
-//     U' = sum_j U_j + 2^span_bits * sum_j j A_j       ("acc" += run after every step but the last; "usum")
-// so that at the root S_w = sum_k (k+1) B_k = U + A (written to outA when `root`).
-// The three running sums of a node are three dependent chains of XYZZ additions, and the upper levels have
-// far fewer nodes than the GPU has lanes, so a node is spread over LPN adjacent lanes of a warp (roles run /
-// usum / acc; acc trails run by one step through shared memory): the chain per level is L + 1 additions
-// instead of 3 L.  Level 0 has no U: LPN = 2.
-template <class F, int LPN>
-__global__ void __launch_bounds__(128) msm_reduce_level_kernel(int W, uint32_t n_in, int span_bits, int root,
-                                                               const uint32_t *__restrict__ task_offsets,
-                                                               const uint32_t *__restrict__ ntasks,
-                                                               const XYZZ<F> *__restrict__ inA,
-                                                               const XYZZ<F> *__restrict__ inU,
-                                                               XYZZ<F> *__restrict__ outA, XYZZ<F> *__restrict__ outU) {
+// Level 0.  Node (w, s) folds the buckets s*L .. s*L+L-1 of window w (bucket value = sum of the bucket's task results):
+//     A = sum_j B_j                       ("run": running sum from the top bucket down)
+//     U = sum_j j B_j,  j local           ("acc" += run after every step but the last)
+// so that S_w = sum_k (k+1) B_k = sum_s (U_s + A_s + L s A_s); when the window has a single node (`root`) S_w = U + A is
+// written directly.  The two running sums of a node are two dependent chains of XYZZ additions; they sit on adjacent
+// lanes (acc trails run by one step through shared memory), so the chain is L + 1 additions long instead of 2 L.
+// Output layout: outA[w * out_stride + s], outU[w * out_stride + s].
+template <class F>
+__global__ void __launch_bounds__(128) msm_reduce_level0_kernel(int W, uint32_t n_in, int root, uint32_t out_stride,
+                                                                const uint32_t *__restrict__ task_offsets,
+                                                                const uint32_t *__restrict__ ntasks,
+                                                                const XYZZ<F> *__restrict__ tout,
+                                                                XYZZ<F> *__restrict__ outA, XYZZ<F> *__restrict__ outU) {
     typedef XYZZ<F> Pt;
-    constexpr bool LEVEL0 = LPN == 2;
-    constexpr int ROLE_RUN = 0, ROLE_ACC = 1, ROLE_USUM = 2;          // LPN == 4: lane 3 idles
-    constexpr int NODES = 128 / LPN;
+    constexpr int ROLE_RUN = 0, ROLE_ACC = 1;
+    constexpr int NODES = 128 / 2;
     __shared__ Pt sh_run[2][NODES];
-    __shared__ Pt sh_usum[LEVEL0 ? 1 : NODES];
     const uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t node = gtid / LPN, ln = threadIdx.x / LPN;
-    const int role = gtid % LPN;
+    const uint32_t node = gtid / 2, ln = threadIdx.x / 2;
+    const int role = gtid % 2;
     const bool live = node < (uint32_t)W * n_out;
     const uint32_t w = live ? node / n_out : 0, s = live ? node % n_out : 0;
     const uint32_t j0 = s << MSM_RED_LOG_L;
@@ -378,38 +406,33 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(int W, uint32_t n
     if (j1 > n_in) j1 = n_in;
     Pt x = Pt::infinity();
     for (uint32_t step = 0; step <= MSM_RED_L; step++) {
-        // step k handles item j = j1-1-k (run, usum) and folds the run value of step k-1 into acc
+        // step k handles bucket j = j1-1-k (run) and folds the run value of step k-1 into acc
         const bool has_item = live && step < j1 - j0;
-        const uint32_t j = j1 - 1 - step;
-        const uint64_t idx = (uint64_t)w * n_in + j;
-        // every role funnels into ONE call site of add() (a warp runs its roles in lockstep)
+        const uint64_t idx = (uint64_t)w * n_in + (j1 - 1 - step);
+        // both roles funnel into ONE call site of add() (a warp runs its roles in lockstep)
         const Pt *src = nullptr;
         uint32_t cnt = 0;
         if (role == ROLE_RUN && has_item) {
-            if (LEVEL0) { src = inA + task_offsets[idx]; cnt = ntasks[idx]; }
-            else { src = inA + idx; cnt = 1; }
-        } else if (role == ROLE_USUM && has_item) {
-            src = inU + idx; cnt = 1;
+            src = tout + task_offsets[idx];
+            cnt = ntasks[idx];
         } else if (role == ROLE_ACC && live && step >= 1 && step < j1 - j0) {
-            src = &sh_run[(step - 1) & 1][ln]; cnt = 1;   // run after item j1-step, which is > j0
+            src = &sh_run[(step - 1) & 1][ln];   // run after bucket j1-step, which is > j0
+            cnt = 1;
         }
         for (uint32_t t = 0; t < cnt; t++) x.add(src[t]);
         if (role == ROLE_RUN && has_item) sh_run[step & 1][ln] = x;
         __syncwarp();
     }
-    if (!LEVEL0 && role == ROLE_USUM && live) sh_usum[ln] = x;
-    __syncwarp();
     if (!live) return;
+    const uint64_t o = (uint64_t)w * out_stride + s;
     if (role == ROLE_RUN) {
-        if (!root) outA[node] = x;
-    } else if (role == ROLE_ACC) {
-        for (int i = 0; i < span_bits; i++) x = x.dbl();
-        if (!LEVEL0) x.add(sh_usum[ln]);
+        if (!root) outA[o] = x;
+    } else {
         if (root) {   // S_w = U + A
             x.add(sh_run[(j1 - j0 - 1) & 1][ln]);
-            outA[node] = x;
+            outA[o] = x;
         } else {
-            outU[node] = x;
+            outU[o] = x;
         }
     }
 }
@@ -431,6 +454,20 @@ __device__ __forceinline__ F quad_pick(int sub, const F &a0, const F &a1, const 
     F r;
 #pragma unroll
     for (int i = 0; i < F::N; i++) r.l[i] = sub == 0 ? a0.l[i] : sub == 1 ? a1.l[i] : sub == 2 ? a2.l[i] : a3.l[i];
+    return r;
+}
+template <class B>
+__device__ __forceinline__ Fp2<B> quad_from(const Fp2<B> &x, int src) {
+    Fp2<B> r;
+    r.c0 = quad_from(x.c0, src);
+    r.c1 = quad_from(x.c1, src);
+    return r;
+}
+template <class B>
+__device__ __forceinline__ Fp2<B> quad_pick(int sub, const Fp2<B> &a0, const Fp2<B> &a1, const Fp2<B> &a2, const Fp2<B> &a3) {
+    Fp2<B> r;
+    r.c0 = quad_pick(sub, a0.c0, a1.c0, a2.c0, a3.c0);
+    r.c1 = quad_pick(sub, a0.c1, a1.c1, a2.c1, a3.c1);
     return r;
 }
 // p + q on every lane of the quad (all 32 lanes of the warp must call it; `sub` = lane & 3)
@@ -475,62 +512,130 @@ __device__ __forceinline__ XYZZ<F> quad_dbl(const XYZZ<F> &p, int sub) {
     return r;
 }
 
-// Same node arithmetic as msm_reduce_level_kernel<F, 4> (roles run / acc / usum) with every role's accumulator
-// replicated over a quad: 16 lanes per node, 8 nodes per 128-thread block.  Upper levels only (inA/inU are
-// (A, U) arrays of the previous level).
+// ---- bit tree: one stage ---------------------------------------------------------------------------
+// in:  [rows_total][n] points, rows_total = W * R, row r of a window: 0 = the A chain (weighted by the entry index),
+//      1 .. R-1 = plain rows (U, and the T_b rows earlier stages produced).
+// out: [W][R + 8][n_blk], n_blk = ceil(n / 256): rows 0 .. R-1 = the block sums of the input rows; rows R + b (b < 8) =
+//      T_b of the A row = sum of the block's entries whose LOCAL index has bit b set.
+// A block folds 256 entries with 8 binary levels in shared memory.  Before level l (nodes of 2^l entries, 2N = 256 >> l
+// of them) the regions are A, T_0 .. T_(l-1), 2N slots each; level l adds sibling pairs in every region (N (l+1)
+// mutually independent additions <= 128 threads) and opens T_l[n] = A[2n+1].  Work: 2 additions per entry; depth: 8.
 template <class F>
-__global__ void __launch_bounds__(128) msm_reduce_level_quad_kernel(int W, uint32_t n_in, int span_bits, int root,
-                                                                    const XYZZ<F> *__restrict__ inA,
-                                                                    const XYZZ<F> *__restrict__ inU,
-                                                                    XYZZ<F> *__restrict__ outA, XYZZ<F> *__restrict__ outU) {
+__global__ void __launch_bounds__(128) msm_bittree_stage_kernel(uint32_t n, uint32_t R, const XYZZ<F> *__restrict__ in,
+                                                                XYZZ<F> *__restrict__ out) {
     typedef XYZZ<F> Pt;
-    constexpr int ROLE_RUN = 0, ROLE_ACC = 1, ROLE_USUM = 2;   // role 3 idles
-    constexpr int NODES = 128 / 16;
-    __shared__ Pt sh_run[2][NODES];
-    __shared__ Pt sh_usum[NODES];
-    const uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t node = gtid >> 4, ln = threadIdx.x >> 4;
-    const int role = (gtid >> 2) & 3, sub = gtid & 3;
-    const bool live = node < (uint32_t)W * n_out;
-    const uint32_t w = live ? node / n_out : 0, s = live ? node % n_out : 0;
-    const uint32_t j0 = s << MSM_RED_LOG_L;
-    uint32_t j1 = j0 + MSM_RED_L;
-    if (j1 > n_in) j1 = n_in;
-    const Pt inf = Pt::infinity();
-    Pt x = inf;
-    for (uint32_t step = 0; step <= MSM_RED_L; step++) {
-        const bool has_item = live && step < j1 - j0;
-        const uint64_t idx = (uint64_t)w * n_in + (j1 - 1 - step);
-        const Pt *src = nullptr;
-        if (role == ROLE_RUN && has_item) src = inA + idx;
-        else if (role == ROLE_USUM && has_item) src = inU + idx;
-        else if (role == ROLE_ACC && live && step >= 1 && step < j1 - j0) src = &sh_run[(step - 1) & 1][ln];
-        // every lane of the warp runs the quad addition (shuffles); lanes without work add infinity
-        x = quad_add(x, src ? *src : inf, sub);
-        if (role == ROLE_RUN && has_item && sub == 0) sh_run[step & 1][ln] = x;
-        __syncwarp();
+    extern __shared__ __align__(16) unsigned char msm_tree_smem[];
+    Pt *X = reinterpret_cast<Pt *>(msm_tree_smem);   // 256 slots
+    const uint32_t n_blk = gridDim.x, j = blockIdx.x;
+    const uint32_t row = blockIdx.y % R, w = blockIdx.y / R;
+    const bool need_t = row == 0;
+    const uint32_t t = threadIdx.x;
+    const Pt *src = in + (uint64_t)blockIdx.y * n + (uint64_t)j * 256;
+    const uint32_t count = n - j * 256 < 256 ? n - j * 256 : 256;
+    {
+        Pt a = 2 * t < count ? src[2 * t] : Pt::infinity();
+        const Pt b = 2 * t + 1 < count ? src[2 * t + 1] : Pt::infinity();
+        a.add(b);
+        X[t] = a;
+        if (need_t) X[128 + t] = b;
     }
-    if (role == ROLE_USUM && live && sub == 0) sh_usum[ln] = x;
-    __syncwarp();
-    // acc: * 2^span_bits, + usum (+ run at the root); the other roles run along on infinity
-    Pt y = role == ROLE_ACC ? x : inf;
-    for (int i = 0; i < span_bits; i++) y = quad_dbl(y, sub);
-    y = quad_add(y, role == ROLE_ACC && live ? sh_usum[ln] : inf, sub);
-    if (root) y = quad_add(y, role == ROLE_ACC && live ? sh_run[(j1 - j0 - 1) & 1][ln] : inf, sub);
-    if (!live || sub != 0) return;
-    if (role == ROLE_RUN && !root) outA[node] = x;
-    if (role == ROLE_ACC) (root ? outA : outU)[node] = y;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t l = 1; l < 8; l++) {
+        const uint32_t log_n = 7 - l, N = 1u << log_n;
+        const uint32_t jobs = need_t ? N * (l + 1) : N;
+        const bool live = t < jobs;
+        const uint32_t r = t >> log_n, k = t & (N - 1);
+        Pt lhs = Pt::infinity(), rhs = Pt::infinity();
+        if (live) {
+            lhs = X[r * 2 * N + 2 * k];
+            rhs = X[r * 2 * N + 2 * k + 1];
+        }
+        __syncthreads();
+        if (live) {
+            lhs.add(rhs);
+            X[r * N + k] = lhs;
+            if (need_t && r == 0) X[(l + 1) * N + k] = rhs;
+        }
+        __syncthreads();
+    }
+    Pt *dst = out + (uint64_t)w * (R + 8) * n_blk + j;
+    if (t == 0) dst[(uint64_t)row * n_blk] = X[0];
+    if (need_t && t >= 1 && t <= 8) dst[(uint64_t)(R + t - 1) * n_blk] = X[t];
+}
+
+// ---- bit tree: finish ---------------------------------------------------------------------------------
+// in: [W][R] points (every row reduced to one value): row 0 = sum A, row 1 = sum U, row 2 + b = T_b.
+// S_w = sum U + sum A + 2^shift * sum_{b < nbits} 2^b T_b.  The doublings are the critical path (a lone warp needs ~7 us
+// per group operation even with the operation spread over a quad), so the sum is folded as a binary tree instead of a
+// Horner chain: Y[i] += 2^s Y[i + s] for s = 1, 2, 4, .. - depth nbits + log2(nbits) operations instead of 2 nbits.
+// One block per window, one quad per pair.
+template <class F>
+__global__ void __launch_bounds__(128) msm_bittree_horner_kernel(uint32_t R, int nbits, int shift, const XYZZ<F> *__restrict__ in,
+                                                                 XYZZ<F> *__restrict__ S) {
+    typedef XYZZ<F> Pt;
+    __shared__ Pt Y[32];
+    const Pt *rows = in + (uint64_t)blockIdx.x * R;
+    const int t = threadIdx.x, sub = t & 3, q = t >> 2, warp = t >> 5;
+    if (t < 32) Y[t] = t < nbits ? rows[2 + t] : Pt::infinity();
+    __syncthreads();
+    for (int s = 1; s < nbits && s < 32; s <<= 1) {
+        const int npairs = 16 / s;
+        if (warp * 8 < npairs) {            // warp-uniform: the quad operations shuffle across the whole warp
+            const bool live = q < npairs;
+            const int i = q * 2 * s;
+            Pt a = live ? Y[i] : Pt::infinity(), b = live ? Y[i + s] : Pt::infinity();
+            for (int k = 0; k < s; k++) b = quad_dbl(b, sub);
+            a = quad_add(a, b, sub);
+            if (live && sub == 0) Y[i] = a;
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        Pt acc = Y[0];
+        for (int i = 0; i < shift; i++) acc = quad_dbl(acc, sub);
+        acc = quad_add(acc, rows[0], sub);
+        acc = quad_add(acc, rows[1], sub);
+        if (t == 0) S[blockIdx.x] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------ host driver
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Window width without a table (every window has its own bucket set).  Large MSMs balance additions (n W) against
+// bucket-reduce work (W 2^(c-1) buckets, two full additions each): c = log2 n - 4.  Small ones are latency bound - the
+// chain of additions per bucket is what the accumulate kernel waits for - and prefer fewer points per bucket
+// (profiles/r2g_msm_tune.txt: 2^16 1.77 ms at c = 15 vs 2.8 ms at c = 12; 2^18 3.0 ms at c = 16 vs 4.1 ms at c = 14).
 static int msm_pick_c(uint64_t n) {
     int lg = 0;
     while ((1ull << lg) < n) lg++;
-    int c = lg - 4;
+    int c = lg >= 20 ? lg - 4 : lg >= 18 ? lg - 2 : lg - 1;
     if (c < 2) c = 2;
     if (c > 20) c = 20;
+    return env_int("ZKB_MSM_C", c);   // tuning experiments only (profiles/quick_msm_tune.py)
+}
+// Default window width of a window table (one bucket set for all windows): about log2 n, a little more for small vectors
+// (2^16: 1.32 ms at c = 18 vs 1.59 ms at c = 16; 2^18: 2.35 ms at c = 19 vs 2.55 ms at c = 18).
+static int msm_pick_table_c(uint64_t n) {
+    int lg = 1;
+    while ((1ull << lg) < n) lg++;
+    int c = lg <= 16 ? lg + 2 : lg <= 18 ? lg + 1 : lg;
+    if (c < 8) c = 8;
+    if (c > 22) c = 22;
     return c;
+}
+
+// Longest run of additions one thread performs in the accumulate kernel.  A task is a dependent chain (one mixed addition
+// takes a lone warp ~15 us), so on a small MSM the cap bounds the kernel's tail; every extra task of a bucket costs one
+// full addition in the level-0 reduce, so large MSMs (whose kernel runs for milliseconds anyway) keep the long cap.
+// Measured (profiles/r2e_msm_tune.txt): 2^20 is fastest with 256, 2^16 / 2^18 with 32-64.
+static uint32_t msm_pick_task_cap(uint64_t total_keys) {
+    const uint32_t cap = total_keys >= (8u << 20) ? MSM_TASK_CAP : 64u;
+    return (uint32_t)env_int("ZKB_MSM_CAP", (int)cap);
 }
 
 template <class F, int SCALAR_BITS>
@@ -539,17 +644,20 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     typedef XYZZ<F> Pt;
     // with a window table every digit window adds 2^(c w) P_i straight into ONE bucket set
     const bool tabled = bases->d_table != nullptr;
-    const int c = tabled ? bases->table_c : msm_pick_c(n);
-    const int W = (SCALAR_BITS + 1 + c - 1) / c;        // digit windows
+    const int c_req = tabled ? bases->table_c : msm_pick_c(n);
+    const int W = tabled ? bases->table_w : (SCALAR_BITS + 1 + c_req - 1) / c_req;   // digit windows
+    const MsmWindows win = msm_windows(SCALAR_BITS + 1, W);
+    const int c = win.max_width();                      // widest window: 2^(c-1) buckets per set
     const int WB = tabled ? 1 : W;                      // bucket sets
     const uint32_t M = 1u << (c - 1);
     const uint32_t nb = (uint32_t)WB * M;
-    if (tabled && (W > bases->table_w || (uint64_t)W * bases->n >= (1ull << 31)))
+    if (tabled && (uint64_t)W * bases->n >= (1ull << 31))
         return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "MSM: window table does not cover the scalar width");
     const uint64_t total_keys = (uint64_t)W * n;
     if (n >= (1ull << 31) || total_keys >= (1ull << 32))
         return ctx_fail(ctx, ZKB_ERR_UNSUPPORTED, "MSM: W*n must be < 2^32 (split the range across calls/GPUs)");
-    const uint64_t max_tasks = (uint64_t)nb + total_keys / MSM_TASK_CAP + 1;
+    const uint32_t task_cap = msm_pick_task_cap(total_keys);
+    const uint64_t max_tasks = (uint64_t)nb + total_keys / task_cap + 1;
 
     // ---- scratch carve-up
     size_t off = 0;
@@ -561,12 +669,22 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     size_t o_tasks = carve(max_tasks * sizeof(MsmTask)), o_tout = carve(max_tasks * sizeof(Pt));
     size_t o_perm = carve(max_tasks * 4), o_bins = carve(3 * MSM_TASK_CAP * 4);
     // at most total_keys / CAP buckets can hold more than CAP points (the list is a superset bound)
-    const uint32_t heavy_cap = (uint32_t)(total_keys / MSM_TASK_CAP + 1);
+    const uint32_t heavy_cap = (uint32_t)(total_keys / task_cap + 1);
     size_t o_heavy = carve((size_t)(heavy_cap + 1) * 4);
-    // reduce tree: level l holds W * ceil(M / L^(l+1)) (A, U) pairs; two ping-pong buffers of the level-0 size
+    // reduce: level 0 leaves (A, U) per node, [WB][2][n_lvl0]; bit-tree stage k turns [WB][R][n] into [WB][R + 8][ceil(n/256)]
     const uint32_t n_lvl0 = (M + MSM_RED_L - 1) >> MSM_RED_LOG_L;
-    size_t o_red = carve((size_t)4 * WB * n_lvl0 * sizeof(Pt));
-    size_t o_S = carve((size_t)WB * sizeof(Pt));
+    size_t o_red = carve((size_t)2 * WB * n_lvl0 * sizeof(Pt));
+    size_t red2_elems = 0;
+    {
+        uint32_t nn = n_lvl0, R = 2;
+        while (nn > 1) {
+            nn = (nn + 255) / 256;
+            R += 8;
+            red2_elems += (size_t)WB * R * nn;
+        }
+    }
+    size_t o_red2 = carve((red2_elems + 1) * sizeof(Pt));
+    size_t o_S = carve((size_t)WB * sizeof(Pt) + 16);
     void *base;
     ZKB_TRY(ctx_scratch(ctx, "msm", off, &base));
     char *B = (char *)base;
@@ -578,18 +696,20 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     uint32_t *n_heavy = (uint32_t *)(B + o_heavy), *heavy = n_heavy + 1;
     uint32_t *perm = (uint32_t *)(B + o_perm), *bins = (uint32_t *)(B + o_bins), *bin_off = bins + MSM_TASK_CAP,
              *bin_cur = bins + 2 * MSM_TASK_CAP;
-    Pt *tout = (Pt *)(B + o_tout), *red = (Pt *)(B + o_red), *S = (Pt *)(B + o_S);
+    Pt *tout = (Pt *)(B + o_tout), *red = (Pt *)(B + o_red), *red2 = (Pt *)(B + o_red2), *S = (Pt *)(B + o_S);
+    uint32_t *bad = (uint32_t *)(B + o_S + (size_t)WB * sizeof(Pt));   // set by the digits kernel on a non-canonical scalar
 
     // counts and cursor are adjacent carve-outs: one memset
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, (size_t)nb * 4, st));
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(cursor, 0, (size_t)nb * 4, st));
-    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, (const uint32_t *)d_scalars, c, W, tabled ? 0u : M, keys, counts);
+    ZKB_CUDA_OK(ctx, cudaMemsetAsync(bad, 0, 4, st));
+    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, (const uint32_t *)d_scalars, win, SCALAR_BITS, tabled ? 0u : M, keys, counts, bad);
     ZKB_CUDA_OK(ctx, cudaMemsetAsync(n_heavy, 0, 4, st));
-    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, ntasks, n_heavy, heavy, heavy_cap);
+    msm_ntasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, task_cap, counts, ntasks, n_heavy, heavy, heavy_cap);
     ctx->launches += 2;
     ZKB_TRY(exclusive_scan(ctx, nb, counts, offsets, bsums, totals, st));
     ZKB_TRY(exclusive_scan(ctx, nb, ntasks, toffs, bsums, totals + 1, st));
-    msm_fill_tasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, counts, offsets, toffs, tasks);
+    msm_fill_tasks_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, task_cap, counts, offsets, toffs, tasks);
     msm_scatter_kernel<<<(unsigned)((total_keys + 255) / 256), 256, 0, st>>>(total_keys, (uint32_t)n, tabled ? (uint32_t)bases->n : 0u, keys, offsets, cursor, sorted);
     const Affine<F> *pts = (const Affine<F> *)(tabled ? bases->d_table : bases->d_points) + offset;
     const unsigned task_blocks = (unsigned)((max_tasks + 255) / 256);
@@ -601,38 +721,39 @@ static int msm_run_t(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, 
     msm_heavy_tree_kernel<F><<<heavy_cap < 1024 ? heavy_cap : 1024, 256, 0, st>>>(n_heavy, heavy, heavy_cap, toffs, ntasks, tout);
     ctx->launches += 7;
     {
-        uint32_t n_in = M;
-        int span_bits = 0, level = 0;
-        const size_t half = (size_t)2 * WB * n_lvl0;   // elements per ping-pong buffer (A then U)
-        while (true) {
-            uint32_t n_out = (n_in + MSM_RED_L - 1) >> MSM_RED_LOG_L;
-            Pt *src = red + (size_t)((level + 1) & 1) * half, *dst = red + (size_t)(level & 1) * half;
-            const Pt *inA = level == 0 ? tout : src, *inU = level == 0 ? nullptr : src + (size_t)WB * n_lvl0;
-            const bool root = n_out == 1;
-            uint32_t cnt = (uint32_t)WB * n_out;
-            if (level == 0) {
-                msm_reduce_level_kernel<F, 2><<<(cnt * 2 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, toffs, ntasks, inA, inU,
-                                                                                   root ? S : dst, dst + (size_t)WB * n_lvl0);
-            } else if (F::N <= 12 && cnt <= 2048) {   // few nodes left: latency matters, quad-cooperative additions
-                if constexpr (F::N <= 12)
-                msm_reduce_level_quad_kernel<F><<<(cnt * 16 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, inA, inU, root ? S : dst,
-                                                                                      dst + (size_t)WB * n_lvl0);
-            } else {
-                msm_reduce_level_kernel<F, 4><<<(cnt * 4 + 127) / 128, 128, 0, st>>>(WB, n_in, span_bits, root, toffs, ntasks, inA, inU,
-                                                                                   root ? S : dst, dst + (size_t)WB * n_lvl0);
+        const bool root = n_lvl0 == 1;
+        msm_reduce_level0_kernel<F><<<((uint32_t)WB * n_lvl0 * 2 + 127) / 128, 128, 0, st>>>(
+            WB, M, root, root ? 1u : 2u * n_lvl0, toffs, ntasks, tout, root ? S : red, red + n_lvl0);
+        ctx->launches++;
+        if (!root) {
+            // bit tree over the n_lvl0 nodes of every window: S_w = sum U + sum A + L * sum_s s A_s
+            const size_t smem = 256 * sizeof(Pt);
+            ZKB_CUDA_OK(ctx, cudaFuncSetAttribute(msm_bittree_stage_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            uint32_t nn = n_lvl0, R = 2;
+            int nbits = 0;
+            while ((1u << nbits) < n_lvl0) nbits++;
+            const Pt *src = red;
+            Pt *dst = red2;
+            while (nn > 1) {
+                const uint32_t nb2 = (nn + 255) / 256;
+                msm_bittree_stage_kernel<F><<<dim3(nb2, (uint32_t)WB * R), 128, smem, st>>>(nn, R, src, dst);
+                ctx->launches++;
+                src = dst;
+                dst += (size_t)WB * (R + 8) * nb2;
+                R += 8;
+                nn = nb2;
             }
+            msm_bittree_horner_kernel<F><<<WB, 128, 0, st>>>(R, nbits, MSM_RED_LOG_L, src, S);
             ctx->launches++;
-            if (root) break;
-            n_in = n_out;
-            span_bits += MSM_RED_LOG_L;
-            level++;
         }
     }
     ZKB_CUDA_OK(ctx, cudaGetLastError());
-    std::vector<uint32_t> hs((size_t)WB * 4 * F::N);
+    std::vector<uint32_t> hs((size_t)WB * 4 * F::N + 4);
     ZKB_CUDA_OK(ctx, cudaMemcpyAsync(hs.data(), S, hs.size() * 4, cudaMemcpyDeviceToHost, st));
     ZKB_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    return msm_window_combine(bases->curve, c, WB, hs.data(), partial_host);
+    if (hs[(size_t)WB * 4 * F::N] != 0)
+        return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "MSM: a scalar is not a canonical element of the scalar field (>= 2^bits)");
+    return msm_window_combine(bases->curve, WB, win.base, win.rem, hs.data(), partial_host);
 }
 
 static int msm_run(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *d_scalars,
@@ -715,20 +836,22 @@ static int batch_exp_t(zkb_ctx *ctx, uint64_t n, const uint32_t *base_affine, co
 }
 
 // ------------------------------------------------------------------------------------ window table
-// table[w * n + i] = 2^(c w) P_i for w = 1 .. W-1 (affine, Montgomery form; row 0 is a copy of the bases).
+// table[w * n + i] = 2^pos(w) P_i for w = 1 .. W-1 (affine, Montgomery form; row 0 is a copy of the bases), pos(w) the
+// bit position of digit window w (MsmWindows: W = ceil((bits+1)/c) windows of almost equal width).
 // A commitment key / proving-key query vector is long-lived, so this is paid once: afterwards every digit
 // window of an MSM adds into the same 2^(c-1) buckets (no per-window bucket sets, no window combine) and c
 // can be as large as log2 n, which cuts the number of windows W = ceil((bits+1)/c).
 template <class F>
-__global__ void __launch_bounds__(128) msm_table_kernel(uint64_t n, int c, int W, const Affine<F> *__restrict__ pts,
+__global__ void __launch_bounds__(128) msm_table_kernel(uint64_t n, MsmWindows win, const Affine<F> *__restrict__ pts,
                                                         Affine<F> *__restrict__ table) {
+    const int W = win.W;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Affine<F> p = pts[i];
     table[i] = p;
     XYZZ<F> acc = XYZZ<F>::from_affine(p);
     for (int w = 1; w < W; w++) {
-        for (int k = 0; k < c; k++) acc = acc.dbl();
+        for (int k = 0; k < win.width(w - 1); k++) acc = acc.dbl();
         p = acc.to_affine();                 // one inversion per point and window (setup cost)
         table[(uint64_t)w * n + i] = p;
         acc = XYZZ<F>::from_affine(p);       // keep ZZ = ZZZ = 1: the next c doublings start cheap
@@ -747,7 +870,7 @@ static int msm_table_t(zkb_ctx *ctx, zkb_msm_bases *b, int c, uint64_t max_bytes
         cudaGetLastError();
         return ctx_fail(ctx, ZKB_ERR_OUT_OF_MEMORY, "cudaMalloc MSM window table");
     }
-    msm_table_kernel<F><<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(b->n, c, W, (const Affine<F> *)b->d_points, (Affine<F> *)t);
+    msm_table_kernel<F><<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(b->n, msm_windows(SCALAR_BITS + 1, W), (const Affine<F> *)b->d_points, (Affine<F> *)t);
     ctx->launches++;
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
@@ -870,17 +993,27 @@ int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *b, int window_bits, ui
     if (!ctx || !b || b->device != ctx->device) return ZKB_ERR_INVALID_ARGUMENT;
     if (b->d_table || b->n == 0) return ZKB_OK;
     int c = window_bits;
-    if (c == 0) {   // one bucket per ~2 points of a full-length MSM
-        c = 1;
-        while ((1ull << c) < b->n) c++;
-        if (c < 8) c = 8;
-        if (c > 22) c = 22;
-    }
+    if (c == 0) c = msm_pick_table_c(b->n);
     if (c < 2 || c > 24) return ctx_fail(ctx, ZKB_ERR_INVALID_ARGUMENT, "zkb_msm_bases_precompute: window_bits out of range");
     ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     ZKB_DISPATCH_CURVE(b->curve, return msm_table_t<CF, SB>(ctx, b, c, max_bytes, st))
     return ZKB_ERR_INVALID_ARGUMENT;
+}
+
+int zkb_msm_window_plan(const zkb_msm_bases *bases, uint64_t n, int *window_bits, int *windows, int *bucket_sets) {
+    if (!bases) return ZKB_ERR_INVALID_ARGUMENT;
+    int sb = 0;
+    ZKB_DISPATCH_CURVE(bases->curve, sb = SB)
+    if (!sb) return ZKB_ERR_INVALID_ARGUMENT;
+    const bool tabled = bases->d_table != nullptr;
+    const int c_req = tabled ? bases->table_c : msm_pick_c(n);
+    const int W = tabled ? bases->table_w : (sb + 1 + c_req - 1) / c_req;
+    const MsmWindows win = msm_windows(sb + 1, W);
+    if (window_bits) *window_bits = win.max_width();
+    if (windows) *windows = W;
+    if (bucket_sets) *bucket_sets = tabled ? 1 : W;
+    return ZKB_OK;
 }
 
 int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,

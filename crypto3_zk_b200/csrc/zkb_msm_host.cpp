@@ -35,12 +35,15 @@ static void store_xyzz(const XYZZ<F> &p, uint32_t *l) {
     store_f(p.ZZZ, l + 3 * F::N);
 }
 
+// Horner over the digit windows: window w has base + (w < rem) bits (MsmWindows in zkb_msm.cu)
 template <class F>
-static void window_combine(int c, int W, const uint32_t *sums, uint32_t *out) {
+static void window_combine(int W, int base, int rem, const uint32_t *sums, uint32_t *out) {
     XYZZ<F> acc = XYZZ<F>::infinity();
     for (int w = W - 1; w >= 0; w--) {
-        if (w != W - 1)
-            for (int i = 0; i < c; i++) acc = acc.dbl();
+        if (w != W - 1) {
+            const int width = base + (w < rem ? 1 : 0);
+            for (int i = 0; i < width; i++) acc = acc.dbl();
+        }
         acc.add(load_xyzz<F>(sums + (size_t)w * 4 * F::N));
     }
     store_xyzz<F>(acc, out);
@@ -70,8 +73,8 @@ typedef HostFp<params::PallasFp> HFpPallas;
 
 namespace zkb {
 // sums: W window sums (XYZZ, Montgomery, 4 * coordinate limbs each) -> one XYZZ partial result
-int msm_window_combine(int curve, int c, int W, const uint32_t *sums, uint32_t *out) {
-    ZKB_HOST_DISPATCH_CURVE(curve, window_combine<CF>(c, W, sums, out); return ZKB_OK)
+int msm_window_combine(int curve, int W, int base, int rem, const uint32_t *sums, uint32_t *out) {
+    ZKB_HOST_DISPATCH_CURVE(curve, window_combine<CF>(W, base, rem, sums, out); return ZKB_OK)
     return ZKB_ERR_INVALID_ARGUMENT;
 }
 }  // namespace zkb

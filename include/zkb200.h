@@ -244,7 +244,8 @@ uint64_t zkb_msm_bases_size(const zkb_msm_bases *bases);
 /* Optional, once per base vector: builds the window table 2^(c w) * P_i (w < ceil((bits+1)/c)) next to the
  * bases so that later zkb_msm / zkb_msm_partial calls on them add every digit window into one bucket set.
  * Same results, fewer windows; costs ceil((bits+1)/c) times the memory of the bases and one inversion per
- * point and window.  window_bits = 0 picks c = log2 n (clamped to [8, 22]); fails with ZKB_ERR_OUT_OF_MEMORY
+ * point and window.  window_bits = 0 picks c ~ log2 n (+2 below 2^17 points, +1 below 2^19; within [8, 22]); the
+ * ceil((bits+1)/c) windows are then made equally wide.  Fails with ZKB_ERR_OUT_OF_MEMORY
  * (bases stay usable) when the table would exceed max_bytes.  For a commitment key that serves many commits
  * (kzg.hpp:100-118 builds it once per params_type). */
 int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *bases, int window_bits, uint64_t max_bytes, void *stream);
@@ -253,11 +254,16 @@ int zkb_msm_bases_precompute(zkb_ctx *ctx, zkb_msm_bases *bases, int window_bits
  * unit scalars cost one mixed addition, so multiexp and multiexp_with_mixed_addition map to the same call. */
 int zkb_msm(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars, int mem,
             uint32_t *result_affine, void *stream);
-/* same, but leaves the result (XYZZ, Montgomery form, 4 coordinates) on the device without synchronising;
- * zkb_msm_combine adds `count` such partial results (e.g. one per GPU) on the host into an affine point */
+/* same, but returns the result un-normalised: XYZZ, Montgomery form, 4 coordinates, written to HOST memory (the call
+ * synchronises the stream: the window sums come back for the host-side window combine); zkb_msm_combine adds `count`
+ * such partial results (e.g. one per GPU) on the host into an affine point.  Scalars must be canonical elements of
+ * the scalar field (< 2^bits): a scalar with higher bits set fails the call with ZKB_ERR_INVALID_ARGUMENT. */
 int zkb_msm_partial(zkb_ctx *ctx, const zkb_msm_bases *bases, uint64_t offset, uint64_t n, const void *scalars,
                     int mem, uint32_t *partial_xyzz_host, void *stream);
 int zkb_msm_combine(int curve, uint32_t count, const uint32_t *partials_xyzz, uint32_t *result_affine);
+/* what zkb_msm would do for n scalars on these bases: widest digit window in bits (2^(bits-1) buckets per set), number
+ * of digit windows, number of bucket sets (1 with a window table).  Host only; for work models (bench.py). */
+int zkb_msm_window_plan(const zkb_msm_bases *bases, uint64_t n, int *window_bits, int *windows, int *bucket_sets);
 /* one-shot convenience (uploads bases every call) */
 int zkb_msm_g1(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, const void *scalars, int mem,
                uint32_t *result_affine, void *stream);
