@@ -35,6 +35,7 @@
 
 #include "../../include/zkb200.h"
 #include "../csrc/zkb_field.cuh"   // Fp2<B> (generic over the base type; compiled for the host here)
+#include "../csrc/zkb_curve.cuh"   // XYZZ<F> group formulas, shared with the device (host tails: proof assembly)
 #include "../csrc/zkb_hostfield.h"
 
 namespace nil {
@@ -242,6 +243,51 @@ struct zkb_curve_g1 {
             return X * z2 == o.X * z1 && Y * z2 * o.Z == o.Y * z1 * Z;
         }
         bool operator!=(const value_type &o) const { return !(*this == o); }
+
+        // Host group law for the O(1) tails the reference runs on the host too (proof assembly prover.hpp:141-157,
+        // kzg.hpp:113-117): the XYZZ formulas of csrc/zkb_curve.cuh on the host field.  (X, Y, Z) <-> XYZZ without
+        // an inversion: ZZ = Z^2, ZZZ = Z^3 and back (X ZZ, Y ZZZ, ZZ).
+        typedef ::zkb::XYZZ<typename BaseField::backend> xyzz_type;
+        xyzz_type to_xyzz() const {
+            if (is_zero()) return xyzz_type::infinity();
+            xyzz_type r;
+            r.X = X.data; r.Y = Y.data;
+            r.ZZ = Z.data * Z.data;
+            r.ZZZ = r.ZZ * Z.data;
+            return r;
+        }
+        static value_type from_xyzz(const xyzz_type &p) {
+            if (p.is_infinity()) return zero();
+            value_type r;
+            r.X.data = p.X * p.ZZ; r.Y.data = p.Y * p.ZZZ; r.Z.data = p.ZZ;
+            return r;
+        }
+        value_type operator+(const value_type &o) const {
+            xyzz_type a = to_xyzz();
+            a.add(o.to_xyzz());
+            return from_xyzz(a);
+        }
+        value_type operator-() const {
+            value_type r = *this;
+            r.Y = -r.Y;
+            return r;
+        }
+        value_type operator-(const value_type &o) const { return *this + (-o); }
+        value_type &operator+=(const value_type &o) { *this = *this + o; return *this; }
+        value_type doubled() const { return from_xyzz(to_xyzz().dbl()); }
+        // k * P, double-and-add over the canonical limbs of k (a handful of these per proof)
+        friend value_type operator*(const typename ScalarField::value_type &k, const value_type &p) {
+            std::uint32_t l[ScalarField::limbs32];
+            k.to_canonical_limbs(l);
+            xyzz_type acc = xyzz_type::infinity(), base = p.to_xyzz();
+            for (int i = ScalarField::limbs32 - 1; i >= 0; i--)
+                for (int b = 31; b >= 0; b--) {
+                    acc = acc.dbl();
+                    if ((l[i] >> b) & 1) acc.add(base);
+                }
+            return from_xyzz(acc);
+        }
+        friend value_type operator*(const value_type &p, const typename ScalarField::value_type &k) { return k * p; }
     };
 };
 template <std::size_t> struct bls12;
@@ -289,6 +335,11 @@ public:
         std::size_t i = 0;
         for (BaseIt it = first; it != last; ++it, ++i) {
             if (it->is_zero()) continue;  // the all-zero encoding is the point at infinity
+            if (it->Z == GroupType::base_field_type::value_type::one()) {   // already affine (generator / deserialiser output): no inversion
+                it->X.to_canonical_limbs(&buf[(2 * i) * CL]);
+                it->Y.to_canonical_limbs(&buf[(2 * i + 1) * CL]);
+                continue;
+            }
             auto a = it->to_affine();
             a.X.to_canonical_limbs(&buf[(2 * i) * CL]);
             a.Y.to_canonical_limbs(&buf[(2 * i + 1) * CL]);
@@ -300,12 +351,43 @@ public:
     multiexp_bases(const multiexp_bases &) = delete;
     multiexp_bases &operator=(const multiexp_bases &) = delete;
     multiexp_bases(multiexp_bases &&o) noexcept : h(o.h), n(o.n) { o.h = nullptr; }
+    multiexp_bases &operator=(multiexp_bases &&o) noexcept {
+        if (this != &o) {
+            if (h) zkb_msm_bases_free(h);
+            h = o.h; n = o.n;
+            o.h = nullptr;
+        }
+        return *this;
+    }
     ~multiexp_bases() { if (h) zkb_msm_bases_free(h); }
+    zkb_msm_bases *handle() const { return h; }
     std::size_t size() const { return n; }
     // one-off window table for a key that serves many multiexps (zkb_msm_bases_precompute)
     void precompute(int window_bits = 0, std::uint64_t max_bytes = 8ull << 30) {
         zkb_ctx *ctx = zkb_detail::context();
         zkb_detail::check(zkb_msm_bases_precompute(ctx, h, window_bits, max_bytes, nullptr), ctx, "zkb_msm_bases_precompute");
+    }
+
+    // sum_i scalars[i] * bases[offset + i] for scalars already laid out as canonical limbs: in a DEVICE buffer (the
+    // witness map leaves the assignment and H there) or in host memory
+    typename GroupType::value_type multiexp_raw(std::size_t offset, std::size_t cnt, const void *scalars, int mem) const {
+        typedef typename GroupType::base_field_type BF;
+        constexpr int CL = BF::limbs32;
+        if (offset + cnt > n) throw std::invalid_argument("multiexp: scalar range longer than the base range");
+        std::uint32_t res[2 * 24] = {0};
+        zkb_ctx *ctx = zkb_detail::context();
+        zkb_detail::check(zkb_msm(ctx, h, offset, cnt, scalars, mem, res, nullptr), ctx, "zkb_msm");
+        bool inf = true;
+        for (int k = 0; k < 2 * CL; k++) inf = inf && res[k] == 0;
+        if (inf) return GroupType::value_type::zero();
+        return GroupType::value_type::from_affine(BF::value_type::from_canonical_limbs(res),
+                                                  BF::value_type::from_canonical_limbs(res + CL));
+    }
+    typename GroupType::value_type multiexp_device(std::size_t offset, std::size_t cnt, const void *d_scalars) const {
+        return multiexp_raw(offset, cnt, d_scalars, ZKB_MEM_DEVICE);
+    }
+    typename GroupType::value_type multiexp_limbs(std::size_t offset, std::size_t cnt, const std::uint32_t *scalars) const {
+        return multiexp_raw(offset, cnt, scalars, ZKB_MEM_HOST);
     }
 
     // sum_i scalars[i] * bases[offset + i]

@@ -10,7 +10,11 @@
 #include <cstring>
 #include <iostream>
 
+#include <fstream>
+#include <sstream>
+
 #include "../../crypto3_zk_b200/host/zkb_crypto3.hpp"
+#include "../../crypto3_zk_b200/host/zkb_r1cs_gg_ppzksnark.hpp"
 
 using namespace nil::crypto3;
 
@@ -430,7 +434,173 @@ static void marshalling_test(bool with_gpu) {
     }
 }
 
+// ---- r1cs_gg_ppzksnark_prover::process (prover.hpp:73-158) and r1cs_to_qap::witness_map (r1cs_to_qap.hpp:219-325) ----
+// The proving key, the assignment and (r, s) come from a text file written by tests/test_cpp_host.py with the oracle's
+// generator; the proof and the H coefficients printed here are compared there with the oracle prover's.
+template <class V>
+static V parse_elem(const std::string &hex) {   // big-endian hex of the canonical integer
+    std::uint32_t l[V::field_type::limbs32] = {0};
+    std::size_t n = hex.size();
+    for (std::size_t i = 0; i < n; i++) {
+        char ch = hex[n - 1 - i];
+        std::uint32_t d = ch <= '9' ? ch - '0' : (ch | 0x20) - 'a' + 10;
+        l[i / 8] |= d << (4 * (i % 8));
+    }
+    return V::from_canonical_limbs(l);
+}
+template <class V>
+static std::string elem_hex(const V &v) {
+    std::uint32_t l[V::field_type::limbs32];
+    v.to_canonical_limbs(l);
+    std::string s;
+    char buf[9];
+    for (int i = V::field_type::limbs32 - 1; i >= 0; i--) {
+        std::snprintf(buf, sizeof buf, "%08x", l[i]);
+        s += buf;
+    }
+    return s;
+}
+template <class G>
+static typename G::value_type parse_g1(std::istream &in) {
+    std::string x, y;
+    in >> x;
+    if (x == "inf") return G::value_type::zero();
+    in >> y;
+    typedef typename G::base_field_type::value_type B;
+    return G::value_type::from_affine(parse_elem<B>(x), parse_elem<B>(y));
+}
+template <class G>
+static typename G::value_type parse_g2(std::istream &in) {
+    std::string t[4];
+    in >> t[0];
+    if (t[0] == "inf") return G::value_type::zero();
+    in >> t[1] >> t[2] >> t[3];
+    typedef typename G::base_field_type::underlying_field_type BF;
+    typedef typename G::base_field_type::value_type B2;
+    std::uint32_t l[2][2 * BF::limbs32];
+    for (int k = 0; k < 4; k++) parse_elem<typename BF::value_type>(t[k]).to_canonical_limbs(&l[k / 2][(k % 2) * BF::limbs32]);
+    return G::value_type::from_affine(B2::from_canonical_limbs(l[0]), B2::from_canonical_limbs(l[1]));
+}
+template <class G>
+static std::string g1_hex(const typename G::value_type &p) {
+    if (p.is_zero()) return "inf";
+    auto a = p.to_affine();
+    return elem_hex(a.X) + " " + elem_hex(a.Y);
+}
+template <class G>
+static std::string g2_hex(const typename G::value_type &p) {
+    if (p.is_zero()) return "inf";
+    typedef typename G::base_field_type::underlying_field_type BF;
+    auto a = p.to_affine();
+    std::uint32_t l[2][2 * BF::limbs32];
+    a.X.to_canonical_limbs(l[0]);
+    a.Y.to_canonical_limbs(l[1]);
+    std::string s;
+    for (int k = 0; k < 4; k++)
+        s += (k ? " " : "") + elem_hex(BF::value_type::from_canonical_limbs(&l[k / 2][(k % 2) * BF::limbs32]));
+    return s;
+}
+
+template <class Curve>
+static void groth16_prover_test(std::istream &in) {
+    using namespace zk::snark;
+    typedef typename Curve::scalar_field_type F;
+    typedef typename F::value_type V;
+    typedef typename Curve::template g1_type<> G1;
+    typedef typename Curve::template g2_type<> G2;
+    r1cs_gg_ppzksnark_proving_key<Curve> pk;
+    std::size_t ni, naux, nc;
+    in >> ni >> naux >> nc;
+    pk.constraint_system.primary_input_size = ni;
+    pk.constraint_system.auxiliary_input_size = naux;
+    for (std::size_t i = 0; i < nc; i++) {
+        r1cs_constraint<F> con;
+        for (int side = 0; side < 3; side++) {
+            std::size_t k;
+            in >> k;
+            auto &lc = side == 0 ? con.a : side == 1 ? con.b : con.c;
+            for (std::size_t j = 0; j < k; j++) {
+                std::size_t idx;
+                std::string co;
+                in >> idx >> co;
+                lc.add_term(idx, parse_elem<V>(co));
+            }
+        }
+        pk.constraint_system.add_constraint(con);
+    }
+    pk.alpha_g1 = parse_g1<G1>(in);
+    pk.beta_g1 = parse_g1<G1>(in);
+    pk.beta_g2 = parse_g2<G2>(in);
+    pk.delta_g1 = parse_g1<G1>(in);
+    pk.delta_g2 = parse_g2<G2>(in);
+    std::size_t n;
+    in >> n;
+    for (std::size_t i = 0; i < n; i++) pk.A_query.push_back(parse_g1<G1>(in));
+    in >> n >> pk.B_query.domain_size_;
+    for (std::size_t i = 0; i < n; i++) {
+        std::size_t idx;
+        in >> idx;
+        auto g = parse_g2<G2>(in);
+        auto h = parse_g1<G1>(in);
+        pk.B_query.indices.push_back(idx);
+        pk.B_query.values.emplace_back(g, h);
+    }
+    in >> n;
+    for (std::size_t i = 0; i < n; i++) pk.H_query.push_back(parse_g1<G1>(in));
+    in >> n;
+    for (std::size_t i = 0; i < n; i++) pk.L_query.push_back(parse_g1<G1>(in));
+    std::vector<V> primary, aux;
+    std::string t;
+    for (std::size_t i = 0; i < ni; i++) { in >> t; primary.push_back(parse_elem<V>(t)); }
+    for (std::size_t i = 0; i < naux; i++) { in >> t; aux.push_back(parse_elem<V>(t)); }
+    std::string rs, ss;
+    in >> rs >> ss;
+    CHECK(pk.constraint_system.is_valid());
+    CHECK(pk.constraint_system.is_satisfied(primary, aux));
+    // witness map alone, d1 = d2 = d3 = 0 and a non-zero patch
+    auto w = reductions::r1cs_to_qap<F>::witness_map(pk.constraint_system, primary, aux, V::zero(), V::zero(), V::zero());
+    CHECK(w.coefficients_for_H.size() == w.degree + 1 && w.coefficients_for_H[w.degree].is_zero() && w.coefficients_for_H[w.degree - 1].is_zero());
+    std::printf("G16H");
+    for (const auto &v : w.coefficients_for_H) std::printf(" %s", elem_hex(v).c_str());
+    std::printf("\n");
+    auto wd = reductions::r1cs_to_qap<F>::witness_map(pk.constraint_system, primary, aux, V(3), V(5), V(7));
+    std::printf("G16HD");
+    for (const auto &v : wd.coefficients_for_H) std::printf(" %s", elem_hex(v).c_str());
+    std::printf("\n");
+    auto proof = r1cs_gg_ppzksnark_prover<Curve>::process(pk, primary, aux, parse_elem<V>(rs), parse_elem<V>(ss));
+    std::printf("G16PROOF %s | %s | %s\n", g1_hex<G1>(proof.g_A).c_str(), g2_hex<G2>(proof.g_B).c_str(), g1_hex<G1>(proof.g_C).c_str());
+    // the same proof again from the cached device key, with window tables
+    pk.device(true);
+    auto proof2 = r1cs_gg_ppzksnark_prover<Curve>::process(pk, primary, aux, parse_elem<V>(rs), parse_elem<V>(ss));
+    CHECK(proof2 == proof);
+    // an unsatisfying assignment is refused (prover.hpp:77)
+    std::vector<V> bad = aux;
+    bad[0] += V::one();
+    bool threw = false;
+    try {
+        r1cs_gg_ppzksnark_prover<Curve>::process(pk, primary, bad, V(1), V(2));
+    } catch (const std::invalid_argument &) { threw = true; }
+    CHECK(threw);
+    // host group law used by the proof assembly: (a + b) G = a G + b G, -(a G) + a G = 0
+    auto Gen = G1::value_type::one();
+    CHECK(V(5) * Gen + V(7) * Gen == V(12) * Gen && (V(5) * Gen - V(5) * Gen).is_zero() && Gen.doubled() == Gen + Gen);
+}
+
 int main(int argc, char **argv) {
+    if (argc > 2 && !std::strcmp(argv[1], "groth16")) {
+        try {
+            std::ifstream f(argv[2]);
+            std::string curve;
+            f >> curve;
+            if (curve == "bn254") groth16_prover_test<algebra::curves::alt_bn128<254>>(f);
+            else groth16_prover_test<algebra::curves::bls12<381>>(f);
+        } catch (const std::exception &e) {
+            std::printf("EXCEPTION %s\n", e.what());
+            return 2;
+        }
+        std::printf(failures ? "FAILED %d checks\n" : "ALL OK\n", failures);
+        return failures ? 1 : 0;
+    }
     if (argc > 1 && !std::strcmp(argv[1], "compile-only")) {
         transcript_and_grinding_test(false);   // host-only part: transcript known answers
         marshalling_test(false);

@@ -15,7 +15,8 @@ def _build():
     from crypto3_zk_b200 import build
     build.build()
     src = os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp")
-    deps = [src, os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_crypto3.hpp"), os.path.join(ROOT, "include", "zkb200.h")]
+    deps = [src, os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_crypto3.hpp"),
+            os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_r1cs_gg_ppzksnark.hpp"), os.path.join(ROOT, "include", "zkb200.h")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         lib = os.path.join(ROOT, "crypto3_zk_b200")
         subprocess.check_call(["g++", "-O2", "-std=c++17", src, "-o", EXE, "-L" + lib, "-lzkb200", "-Wl,-rpath," + lib])
@@ -118,3 +119,57 @@ def _oracle_lpc_proof_digest():
                 val(pr[1])
             mp(rp["p"])
     return hashes.keccak256(bytes(d)).hex(), len(d), tr.state.hex()
+
+
+def _g(pt, deg=1):
+    if pt is None:
+        return "inf"
+    if deg == 1:
+        return "%x %x" % (pt[0], pt[1])
+    return "%x %x %x %x" % (pt[0][0], pt[0][1], pt[1][0], pt[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve,kind,nc,ni", [("bn254", "field", 28, 3), ("bls12_381", "binary", 59, 4)])
+def test_cpp_groth16_prover_vs_oracle(tmp_path, curve, kind, nc, ni):
+    """C++ r1cs_gg_ppzksnark_prover<Curve>::process and r1cs_to_qap<F>::witness_map (host/zkb_r1cs_gg_ppzksnark.hpp, the
+    counterparts of prover.hpp:73-158 and r1cs_to_qap.hpp:219-325) on a key made by the oracle's generator: same H
+    coefficients (with and without the d1/d2/d3 patch) and the same proof (affine) as the oracle prover."""
+    from oracle import curves, groth16
+    F, G1, G2 = ((fields.BN254_FR, curves.BN254_G1, curves.BN254_G2) if curve == "bn254" else
+                 (fields.BLS12_381_FR, curves.BLS12_381_G1, curves.BLS12_381_G2))
+    make = groth16.example_with_field_input if kind == "field" else groth16.example_with_binary_input
+    cs, primary, aux = make(F, nc, ni, seed=11)
+    t, alpha, beta, gamma, delta = fields.random_elements(F, 5, 41)
+    pk = groth16.generator(cs, G1, G2, F, t, alpha, beta, gamma, delta)
+    r, s = fields.random_elements(F, 2, 42)
+    cs = pk.cs       # the generator may have swapped A and B (swap_AB_if_beneficial, generator.hpp:104-106)
+    lines = [curve, "%d %d %d" % (cs.num_inputs, cs.num_aux, cs.num_constraints)]
+    for con in cs.constraints:
+        for side in con:
+            lines.append(" ".join([str(len(side))] + ["%d %x" % (i, co % F.p) for i, co in side]))
+    lines += [_g(pk.alpha_g1), _g(pk.beta_g1), _g(pk.beta_g2, 2), _g(pk.delta_g1), _g(pk.delta_g2, 2)]
+    lines.append(str(len(pk.A_query)))
+    lines += [_g(q) for q in pk.A_query]
+    lines.append("%d %d" % (len(pk.B_indices), len(pk.A_query)))
+    lines += ["%d %s %s" % (i, _g(g2, 2), _g(g1)) for i, g2, g1 in zip(pk.B_indices, pk.B_g2, pk.B_g1)]
+    lines.append(str(len(pk.H_query)))
+    lines += [_g(q) for q in pk.H_query]
+    lines.append(str(len(pk.L_query)))
+    lines += [_g(q) for q in pk.L_query]
+    lines.append(" ".join("%x" % v for v in primary))
+    lines.append(" ".join("%x" % v for v in aux))
+    lines.append("%x %x" % (r, s))
+    path = tmp_path / "groth16_key.txt"
+    path.write_text("\n".join(lines) + "\n")
+    exe = _build()
+    res = subprocess.run([exe, "groth16", str(path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0 and "ALL OK" in res.stdout, res.stdout[-2000:]
+    out = {l.split()[0]: l.split()[1:] for l in res.stdout.splitlines() if l.startswith("G16")}
+    m, full, H = groth16.witness_map(pk.cs, primary, aux, F)
+    assert [int(v, 16) for v in out["G16H"]] == H[:m + 1]
+    _, _, HD = groth16.witness_map(pk.cs, primary, aux, F, 3, 5, 7)
+    assert [int(v, 16) for v in out["G16HD"]] == HD[:m + 1]
+    want = groth16.prove(pk, primary, aux, r, s, G1, G2, F)
+    got = [[int(v, 16) for v in part.split()] for part in " ".join(out["G16PROOF"]).split(" | ")]
+    assert got[0] == list(want[0]) and got[1] == [want[1][0][0], want[1][0][1], want[1][1][0], want[1][1][1]] and got[2] == list(want[2])
