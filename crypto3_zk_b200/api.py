@@ -626,6 +626,78 @@ class Context:
         return r.value
 
 
+class MultiContext:
+    """zkb_multi: one process driving several GPUs (include/zkb200.h, multi-GPU section).  Host buffers in, results out."""
+
+    def __init__(self, devices):
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        self._h = ctypes.c_void_p()
+        capi.check(capi.lib().zkb_multi_create(devs, len(devices), ctypes.byref(self._h)))
+        self.devices = list(devices)
+
+    def _check(self, status):
+        if status != capi.OK:
+            detail = capi.lib().zkb_multi_last_error(self._h).decode()
+            try:
+                capi.check(status)
+            except capi.ZkbError as e:
+                raise type(e)(status, str(e) + (": " + detail if detail else "")) from None
+
+    def close(self):
+        if self._h:
+            capi.lib().zkb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def msm_bases(self, curve, points_host, precompute=False, max_bytes_per_device=8 << 30):
+        c = _curve(curve)
+        pts = np.ascontiguousarray(points_host, dtype=np.uint32)
+        cl = coord_limbs(c)
+        n = pts.size // (2 * cl)
+        h = ctypes.c_void_p()
+        self._check(capi.lib().zkb_msm_bases_multi_create(self._h, c.cid, n, pts.ctypes.data, ctypes.byref(h)))
+        if precompute:
+            self._check(capi.lib().zkb_msm_bases_multi_precompute(self._h, h, 0, max_bytes_per_device))
+        return _MultiBases(h, c, n)
+
+    def multiexp(self, bases, scalars_host):
+        sc = np.ascontiguousarray(scalars_host, dtype=np.uint32)
+        cl = coord_limbs(bases.curve)
+        res = (ctypes.c_uint32 * (2 * cl))()
+        self._check(capi.lib().zkb_msm_multi(self._h, bases._h, sc.size // 8, sc.ctypes.data, res))
+        return _affine_from_limbs(res, cl, bases.curve.deg)
+
+    def lpc_commit(self, field, hash_id, polys_host, log_n_in, log_n_out, fri_step):
+        a = np.ascontiguousarray(polys_host, dtype=np.uint32)
+        batch = a.size // (8 << log_n_in)
+        db = capi.lib().zkb_merkle_digest_bytes(hash_id)
+        root = (ctypes.c_uint8 * max(db, 1))()
+        self._check(capi.lib().zkb_lpc_commit_multi(self._h, _field_id(field), hash_id, log_n_in, log_n_out, fri_step, batch,
+                                                    a.ctypes.data, root))
+        return bytes(root)
+
+
+class _MultiBases:
+    def __init__(self, h, curve, n):
+        self._h, self.curve, self.n = h, curve, n
+
+    def free(self):
+        if self._h:
+            capi.lib().zkb_msm_bases_multi_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def _affine_from_limbs(res, cl, deg=1):
     """(x, y) as Python ints ((c0, c1) tuples per coordinate on the G2 groups); None = infinity."""
     if deg == 2:

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libzkb200.so")
 
-CU_SOURCES = ["zkb_ctx.cu", "zkb_ntt.cu", "zkb_msm.cu", "zkb_hash.cu", "zkb_poly.cu", "zkb_scan.cu"]
+CU_SOURCES = ["zkb_ctx.cu", "zkb_ntt.cu", "zkb_msm.cu", "zkb_hash.cu", "zkb_poly.cu", "zkb_scan.cu", "zkb_multi.cu"]
 CXX_SOURCES = ["zkb_msm_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         jobs.append(["g++", "-O2", "-std=c++17", "-fPIC", "-c", os.path.join(CSRC, s), "-o", o])
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(jobs)) as ex:
         list(ex.map(lambda c: _run(c, verbose, log), jobs))
-    _run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], verbose, log)
+    _run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread"], verbose, log)
     with open(os.path.join(OBJ, "build.log"), "w") as f:
         f.write("\n".join(log))
     return LIB

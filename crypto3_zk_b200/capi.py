@@ -21,6 +21,8 @@ SYMBOLS = [
     "zkb_merkle_digest_bytes", "zkb_merkle_root_of_digests", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
     "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul", "zkb_bench_imad_wide", "zkb_ctx_clear_error", "zkb_msm_window_plan",
+    "zkb_multi_create", "zkb_multi_destroy", "zkb_multi_size", "zkb_multi_ctx", "zkb_multi_last_error", "zkb_msm_bases_multi_create",
+    "zkb_msm_bases_multi_precompute", "zkb_msm_bases_multi_free", "zkb_msm_multi", "zkb_lpc_commit_multi",
     "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
     "zkb_sparse_matrix_create", "zkb_sparse_matrix_free", "zkb_sparse_matvec", "zkb_pow_grind", "zkb_merkle_paths", "zkb_poly_evaluate_pm",
     "zkb_lde_with_coefficients", "zkb_batch_exp", "zkb_permutation_grand_product", "zkb_lookup_grand_product", "zkb_prefix_product", "zkb_batch_inverse", "zkb_buf_alloc", "zkb_buf_free", "zkb_buf_copy", "zkb_buf_zero", "zkb_gather",
@@ -102,6 +104,21 @@ def lib():
     L.zkb_bench_imad_wide.argtypes = [vp, u32, u32, u32, ctypes.POINTER(ctypes.c_double)]
     L.zkb_ctx_clear_error.argtypes = [vp]
     L.zkb_ctx_clear_error.restype = None
+    L.zkb_multi_create.argtypes = [ctypes.POINTER(i), u32, ctypes.POINTER(vp)]
+    L.zkb_multi_destroy.argtypes = [vp]
+    L.zkb_multi_destroy.restype = None
+    L.zkb_multi_size.argtypes = [vp]
+    L.zkb_multi_size.restype = u32
+    L.zkb_multi_ctx.argtypes = [vp, u32]
+    L.zkb_multi_ctx.restype = vp
+    L.zkb_multi_last_error.argtypes = [vp]
+    L.zkb_multi_last_error.restype = ctypes.c_char_p
+    L.zkb_msm_bases_multi_create.argtypes = [vp, i, u64, vp, ctypes.POINTER(vp)]
+    L.zkb_msm_bases_multi_precompute.argtypes = [vp, vp, i, u64]
+    L.zkb_msm_bases_multi_free.argtypes = [vp]
+    L.zkb_msm_bases_multi_free.restype = None
+    L.zkb_msm_multi.argtypes = [vp, vp, u64, vp, u32p]
+    L.zkb_lpc_commit_multi.argtypes = [vp, i, i, i, i, i, u32, vp, u8p]
     L.zkb_fri_commit_phase.argtypes = [vp, i, i, i, vp, i, u32p, u32, FRI_CHALLENGE_FN, vp, u8p, ctypes.POINTER(vp), vp,
                                        u32p, u32p, vp]
     L.zkb_poly_evaluate.argtypes = [vp, i, i, u64, u32, vp, i, u32, u32p, u32p, vp]

@@ -268,6 +268,30 @@ int zkb_msm_window_plan(const zkb_msm_bases *bases, uint64_t n, int *window_bits
 int zkb_msm_g1(zkb_ctx *ctx, int curve, uint64_t n, const void *points_affine, const void *scalars, int mem,
                uint32_t *result_affine, void *stream);
 
+/* ---- multi-GPU (SURVEY.md 8(b) "zkb_*_multi taking a device list", 8(e)) ---------------------------- */
+/* One host process drives several GPUs of a node: a zkb_multi owns one context per listed device (and enables peer
+ * access between them).  Calls fan out on one host thread per device and return when all devices are done.
+ *   MSM (kzg.hpp:146, prover.hpp:108-139): the bases are split into contiguous point ranges, one per device, resident
+ *     there (zkb_msm_bases_multi_precompute adds the per-device window tables); zkb_msm_multi sends every device its
+ *     slice of the host scalars, the XYZZ partial sums are added on the host.  scalars: host, n x 8 limbs, n <= bases.
+ *   LPC commit (basic_fri.hpp:445-496): polynomials split over the devices for the resize; the extended evaluations are
+ *     regrouped by leaf range with device-to-device copies, every device commits the subtree of its leaves, the top
+ *     log2(devices) levels come from the subtree roots.  The device count must be a power of two dividing `batch` and
+ *     the leaf count; polys: HOST, [batch][2^log_n_in].  Same root as zkb_lpc_commit on one device. */
+typedef struct zkb_multi zkb_multi;
+typedef struct zkb_msm_bases_multi zkb_msm_bases_multi;
+int zkb_multi_create(const int *devices, uint32_t count, zkb_multi **out);
+void zkb_multi_destroy(zkb_multi *m);
+uint32_t zkb_multi_size(const zkb_multi *m);
+zkb_ctx *zkb_multi_ctx(zkb_multi *m, uint32_t i);          /* the context of the i-th listed device (owned by m) */
+const char *zkb_multi_last_error(const zkb_multi *m);
+int zkb_msm_bases_multi_create(zkb_multi *m, int curve, uint64_t n, const void *points_affine_host, zkb_msm_bases_multi **out);
+int zkb_msm_bases_multi_precompute(zkb_multi *m, zkb_msm_bases_multi *bases, int window_bits, uint64_t max_bytes_per_device);
+void zkb_msm_bases_multi_free(zkb_msm_bases_multi *bases);
+int zkb_msm_multi(zkb_multi *m, const zkb_msm_bases_multi *bases, uint64_t n, const void *scalars_host, uint32_t *result_affine);
+int zkb_lpc_commit_multi(zkb_multi *m, int field, int hash, int log_n_in, int log_n_out, int fri_step, uint32_t batch,
+                         const void *polys_host, uint8_t *root_out);
+
 /* ---- synthetic inputs (benchmarks/tests; SURVEY.md 8(d) "generate on GPU") ------------------------ */
 /* out_device[i] = table_a[i % m] + table_b[i / m]: n valid affine points from two small host tables
  * (m and ceil(n/m) affine points, canonical limbs).  out_device is DEVICE memory, n * 2 * coord limbs. */

@@ -100,3 +100,40 @@ def test_polynomial_sharded_lpc_commit_nccl(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_single_process_multi_gpu_abi(world):
+    """zkb_msm_multi / zkb_lpc_commit_multi (include/zkb200.h, multi-GPU section): one process, a device
+    list, host threads and peer copies inside the library - same MSM result as the oracle and the same LPC root as the
+    single-GPU commit (and as the CPU port) on identical inputs."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from crypto3_zk_b200 import Context
+    from crypto3_zk_b200.api import MultiContext
+    from oracle import cref, curves, fields
+    mc = MultiContext(list(range(world)))
+    C = curves.BLS12_381_G1
+    n = 1000
+    pts = C.random_points(n, 31)
+    sc = fields.random_elements(C.scalar_field, n, 32)
+    sc[3], sc[4] = 0, 1
+    pa = fields.ints_to_u32_array([c for P in pts for c in P], 12).reshape(n, 2, 12)
+    sa = fields.ints_to_u32_array(sc, 8)
+    want = C.msm_bdlo12(pts, sc)
+    for pre in (False, True):
+        b = mc.msm_bases(C.name, pa, precompute=pre)
+        assert mc.multiexp(b, sa) == want
+        assert mc.multiexp(b, sa[:777]) == C.msm_bdlo12(pts[:777], sc[:777])     # a prefix: later devices get short or empty slices
+        b.free()
+    ctx = Context(0)
+    for hid, fri_step, log_in, log_out, batch in ((0, 1, 10, 13, 8), (1, 2, 9, 12, 8), (2, 1, 12, 15, 16)):
+        rng = np.random.Generator(np.random.PCG64(100 + log_in))
+        a = rng.integers(0, 1 << 32, size=(batch, 1 << log_in, 8), dtype=np.uint64).astype(np.uint32)
+        a[..., 7] &= 0x0FFFFFFF
+        got = mc.lpc_commit("pallas_fq", hid, a, log_in, log_out, fri_step)
+        assert got == ctx.lpc_commit("pallas_fq", hid, a, log_in, log_out, fri_step)
+        assert got == cref.lpc_commit(3, hid, a, log_in, log_out, fri_step, threads=cref.host_cores())[0]
+    ctx.close()
+    mc.close()
