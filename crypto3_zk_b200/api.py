@@ -550,6 +550,44 @@ class Context:
         capi.check(capi.lib().zkb_batch_inverse(self._h, fid, b.nbytes // 32, b.ptr, o.ptr, _stream_ptr(x, stream)), self._h)
         return out
 
+    # ------------------------------------------------------------------ Placeholder argument builders
+    def expr_eval(self, field, cols, program, constants, out, out_stride=1, out_offset=0, accumulate=False, stream=None):
+        """zkb_expr_eval: postfix `program` (list of (op, a, b)) over cols [ncols, n, 8] (device) -> out (device)."""
+        fid = _field_id(field)
+        b = _Buf(cols)
+        ncols, n = int(cols.shape[0]), int(cols.shape[1])
+        prog = np.zeros((len(program), 3), dtype=np.int32)
+        for k, ins in enumerate(program):
+            prog[k] = (ins[0], ins[1], ins[2] if len(ins) > 2 else 0)
+        cs = _int_rows(list(constants)) if len(constants) else np.zeros((1, 8), dtype=np.uint32)
+        o = _Buf(out, writable=True)
+        if b.mem != capi.MEM_DEVICE or o.mem != capi.MEM_DEVICE:
+            raise ValueError("expr_eval works on device tensors")
+        capi.check(capi.lib().zkb_expr_eval(self._h, fid, n, ncols, b.ptr, prog.ctypes.data, len(program), capi.u32_ptr(cs), len(constants),
+                                            o.ptr, out_stride, out_offset, int(bool(accumulate)), _stream_ptr(cols, stream)), self._h)
+        return out
+
+    def quotient_split(self, field, f_coefficients, log_n, log_ext, nchunks, out=None, stream=None):
+        import torch
+        fid = _field_id(field)
+        b = _Buf(f_coefficients)
+        if out is None:
+            out = torch.empty((nchunks, 1 << log_n, 8), dtype=torch.int32, device=f_coefficients.device)
+        o = _Buf(out, writable=True)
+        capi.check(capi.lib().zkb_quotient_split(self._h, fid, log_n, log_ext, b.ptr, nchunks, o.ptr, _stream_ptr(f_coefficients, stream)), self._h)
+        return out
+
+    def lookup_sort(self, field, inputs, values, usable_rows, out=None, stream=None):
+        """sort_polynomials (lookup_argument.hpp:565-633): inputs [ni, n, 8], values [nv, n, 8] -> sorted [ni + nv, n, 8]"""
+        import torch
+        fid = _field_id(field)
+        ni, nv, n = (int(inputs.shape[0]) if inputs is not None else 0), int(values.shape[0]), int(values.shape[1])
+        if out is None:
+            out = torch.empty((ni + nv, n, 8), dtype=torch.int32, device=values.device)
+        capi.check(capi.lib().zkb_lookup_sort(self._h, fid, n, usable_rows, ni, _Buf(inputs).ptr if ni else None, nv, _Buf(values).ptr,
+                                              _Buf(out, writable=True).ptr, _stream_ptr(values, stream)), self._h)
+        return out
+
     # ------------------------------------------------------------------ R1CS rows (r1cs_to_qap.hpp:245-248,289-291)
     def sparse_matrix(self, field, rows, cols, row_ptr, col_idx, values, stream=None):
         return SparseMatrix(self, field, rows, cols, row_ptr, col_idx, values, stream)

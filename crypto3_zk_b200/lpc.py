@@ -123,6 +123,20 @@ class LpcCommitmentScheme:
     def mark_batch_as_fixed(self, index):
         self._fixed[index] = True
 
+    def has_batch(self, index):
+        return index in self._polys
+
+    def fixed_batch_values(self, index):
+        """values of a fixed batch's polynomials at etha, evaluated the way eval_polys evaluates (the reference's
+        preprocessor stores them in the commitment scheme's preprocessed data, lpc.hpp:83-93); call after setup()"""
+        batch, n = self._batch_tensor(index)
+        co = self.ctx.ntt(self.F.name, batch.clone(), n.bit_length() - 1, inverse=True)
+        vals = [v[0] for v in self.ctx.poly_evaluate(self.F.name, co, n, [self._etha])]
+        if self._fixed_values is None:
+            self._fixed_values = {}
+        self._fixed_values[index] = vals
+        return vals
+
     def setup(self, transcript, fixed_values):
         self._etha = transcript.challenge(self.F.p)
         self._fixed_values = fixed_values

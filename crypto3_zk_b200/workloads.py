@@ -122,3 +122,75 @@ def placeholder_batches(shape=PLACEHOLDER_CIRCUIT5, quotient_chunks=4):
     permuted = shape["witness"] + shape["public"] + shape["constant"]
     return {0: 2 * permuted + 2 + shape["constant"] + shape["selector"],
             1: shape["witness"] + shape["public"], 2: 1, 3: quotient_chunks}
+
+
+def _const_column(torch, value, n, device):
+    row = torch.from_numpy(_int_rows([int(value)]).view(np.int32)).to(device)
+    return row.expand(n, 8).contiguous()
+
+
+def _rand_column(torch, shape, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randint(-2**31, 2**31 - 1, shape, dtype=torch.int32, device=device, generator=g)
+    x[..., 7] &= 0x0FFFFFFF      # uniform 252-bit values: canonical in every field of the table
+    return x
+
+
+def placeholder_chain_circuit(ctx, field, log_n, triples=1, usable_rows=None, seed=1, device="cuda", rotation_gate=True,
+                              max_quotient_chunks=0):
+    """A satisfiable synthetic Placeholder circuit with its assignment, all columns built on the device.
+
+    Witness columns (a_k, b_k, c_k) for k < triples, one public-input column, one selector.  On every usable row the gate
+    a_k * b_k - c_k = 0 holds, and (with rotation_gate) a_k(next row) - c_k = 0 on the usable rows but the last; the copy
+    constraints a_k[j+1] = c_k[j] tie the same cells through the permutation argument, and public[0] = a_0[0].  Rows from
+    `usable_rows` on hold random blinding values (q_last at usable_rows, q_blind after it: preprocessor.hpp:463-476).
+    Identity / sigma polynomials as preprocessor.hpp:418-460 builds them (S_id[i][j] = delta^i omega^j, delta = the
+    multiplicative generator).  Returns (PlaceholderCircuit, witness [3*triples, n, 8], public_input [1, n, 8])."""
+    import torch
+    from . import capi
+    from .fields import omega
+    from .placeholder import PlaceholderCircuit, col, mul, sub
+    F = FIELD_BY_NAME[field] if isinstance(field, str) else field
+    n = 1 << log_n
+    usable = n - 4 if usable_rows is None else usable_rows
+    assert 2 <= usable < n
+    nw = 3 * triples
+    witness = _rand_column(torch, (nw, n, 8), seed, device)
+    for k in range(triples):
+        b = witness[3 * k + 1]
+        excl = ctx.prefix_product(F.name, b)                                  # [1, b0, b0 b1, ..]
+        a = ctx.vec(F.name, capi.VEC_MUL, excl, witness[3 * k, 0].expand(n, 8).contiguous())
+        c = ctx.vec(F.name, capi.VEC_MUL, a, b)
+        witness[3 * k, :usable] = a[:usable]
+        witness[3 * k + 2, :usable] = c[:usable]
+    public = torch.zeros((1, n, 8), dtype=torch.int32, device=device)
+    public[0, 0] = witness[0, 0]
+    # selectors
+    selector = torch.zeros((2 if rotation_gate else 1, n, 8), dtype=torch.int32, device=device)
+    selector[0, :usable, 0] = 1
+    if rotation_gate:
+        selector[1, :usable - 1, 0] = 1
+    q_last = torch.zeros((n, 8), dtype=torch.int32, device=device)
+    q_last[usable, 0] = 1
+    q_blind = torch.zeros((n, 8), dtype=torch.int32, device=device)
+    q_blind[usable + 1:, 0] = 1
+    lagrange_0 = torch.zeros((n, 8), dtype=torch.int32, device=device)
+    lagrange_0[0, 0] = 1
+    # permutation polynomials
+    npc = nw + 1
+    powers = ctx.prefix_product(F.name, _const_column(torch, omega(F, log_n), n, device))
+    s_id = torch.empty((npc, n, 8), dtype=torch.int32, device=device)
+    for i in range(npc):
+        s_id[i] = ctx.vec(F.name, capi.VEC_MUL, powers, _const_column(torch, pow(F.generator, i, F.p), n, device))
+    s_sigma = s_id.clone()
+    for k in range(triples):
+        s_sigma[3 * k, 1:usable] = s_id[3 * k + 2, 0:usable - 1]
+        s_sigma[3 * k + 2, 0:usable - 1] = s_id[3 * k, 1:usable]
+    s_sigma[nw, 0] = s_id[0, 0]
+    s_sigma[0, 0] = s_id[nw, 0]
+    gates = [(0, [sub(mul(col(3 * k), col(3 * k + 1)), col(3 * k + 2)) for k in range(triples)])]
+    if rotation_gate:
+        gates.append((1, [sub(col(3 * k, 1), col(3 * k + 2)) for k in range(triples)]))
+    circuit = PlaceholderCircuit(F, log_n, nw, 1, 0, selector.shape[0], gates, list(range(npc)), s_id, s_sigma, q_last, q_blind,
+                                 lagrange_0, None, selector, usable, max_quotient_chunks=max_quotient_chunks)
+    return circuit, witness, public

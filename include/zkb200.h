@@ -340,6 +340,39 @@ int zkb_lookup_grand_product(zkb_ctx *ctx, int field, uint64_t n, uint64_t usabl
 int zkb_prefix_product(zkb_ctx *ctx, int field, uint64_t n, const void *in_device, void *out_device, int exclusive, void *stream);
 int zkb_batch_inverse(zkb_ctx *ctx, int field, uint64_t n, const void *in_device, void *out_device, void *stream);
 
+/* ---- Placeholder argument builders: expressions over an extended domain, quotient, lookup sort ------ */
+/* A postfix program evaluated once per point i < n (n a power of two) over DEVICE column arrays [ncols][n] of canonical
+ * elements: the gate expression of zk/snark/systems/plonk/placeholder/gates_argument.hpp:76-217 (selector * sum theta^k
+ * constraint, times the mask) and the F parts of the permutation / lookup arguments (permutation_argument.hpp:170-215) are
+ * such expressions.  The arrays hold the columns on ONE coset w_E^j H of the extended domain (one zkb_ntt with a coset
+ * shift per coset, from the coefficient form); a rotation by r rows is the index shift (i + r) mod n.  The result goes to
+ * out[out_offset + i * out_stride] (accumulate != 0 adds): offset j, stride D interleaves the D cosets into the evaluation
+ * form on the size-(D n) subgroup that polynomial_dfs holds upstream.  At most 16 stack slots. */
+typedef enum {
+    ZKB_EXPR_PUSH_COL = 0,   /* a = column, b = rotation in rows (may be negative) */
+    ZKB_EXPR_PUSH_CONST = 1, /* a = index into `constants` */
+    ZKB_EXPR_ADD = 2, ZKB_EXPR_SUB = 3, ZKB_EXPR_MUL = 4, /* pop b, pop a, push a (op) b */
+    ZKB_EXPR_NEG = 5
+} zkb_expr_op;
+typedef struct { uint32_t op; uint32_t a; int32_t b; } zkb_expr_instr;
+int zkb_expr_eval(zkb_ctx *ctx, int field, uint64_t n, uint32_t ncols, const void *cols_device, const zkb_expr_instr *program,
+                  uint32_t n_instr, const uint32_t *constants, uint32_t nconst, void *out_device, uint64_t out_stride,
+                  uint64_t out_offset, int accumulate, void *stream);
+/* quotient_polynomial + split (placeholder/prover.hpp:220-283, detail::split_polynomial :47-70): T = F / (X^n - 1) for F
+ * in COEFFICIENT form (2^log_ext coefficients, DEVICE; the remainder is dropped like upstream's polynomial division), cut
+ * into `nchunks` chunks of n = 2^log_n coefficients (missing ones are zero), every chunk taken to evaluation form on the
+ * n-subgroup (from_coefficients, :255-257).  out: DEVICE, [nchunks][n]. */
+int zkb_quotient_split(zkb_ctx *ctx, int field, int log_n, int log_ext, const void *f_coefficients_device, uint32_t nchunks,
+                       void *out_dfs_device, void *stream);
+/* sort_polynomials of the lookup argument (lookup_argument.hpp:565-633): inputs / values = reduced_input / reduced_value,
+ * DEVICE [count][n]; only rows < usable_rows take part.  sorted: DEVICE, [n_inputs + n_values][n], receives every table
+ * value as often as it occurs in the table and the inputs together, in table order (a single zero first, zero runs once),
+ * usable_rows values per column, sorted[i][usable_rows] = sorted[i+1][0], zero elsewhere.  Counting is a device hash table
+ * instead of the reference's unordered_map.  ZKB_ERR_INVALID_ARGUMENT when a lookup input is not in the table (the reference
+ * asserts, :577) or the values do not fit (equal table values that are not adjacent are emitted once per run). */
+int zkb_lookup_sort(zkb_ctx *ctx, int field, uint64_t n, uint64_t usable_rows, uint32_t n_inputs, const void *inputs_device,
+                    uint32_t n_values, const void *values_device, void *sorted_device, void *stream);
+
 /* ---- device buffers for host templates ------------------------------------------------------------ */
 /* lpc_commitment_scheme keeps its polynomials as members between commit / eval_polys / proof_eval
  * (zk/commitments/polynomial/lpc.hpp:66-200, batched_commitment.hpp:60-250: `_polys`, `_z`); a host template over this ABI
