@@ -246,7 +246,8 @@ def metric_parts(args, torch, ctx, dev, hbm_peak, x_lde):
     ms = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n, coset_shift=g), 10, warmup=3)
     ms_plain = time_cuda(torch, lambda: ctx.ntt("bls12_381_fr", x, log_n), 10, warmup=3)
     alg = 2 * n * 32
-    muls = n * (log_n / 2.0 + 2)      # butterflies + 2 inter-pass twiddles + coset scale (approx.)
+    from crypto3_zk_b200.csrc_plan import ntt_products_per_element
+    muls = n * ntt_products_per_element(log_n, coset=True)   # exact count of the pass kernels (unit twiddles of block 0 are skipped)
     hx, hxn = pinned_like(torch, np, x)
     e2e_ms = time_wall(torch, lambda: ctx.ntt("bls12_381_fr", hxn, log_n, coset_shift=g), 5, warmup=2)
     part = {"value": n / (ms * 1e-3), "unit": "elem/s", "ms": ms, "ms_without_coset": ms_plain,
@@ -721,7 +722,54 @@ def placeholder_extra(args, torch, ctx, dev):
             except Exception as e:
                 res["retain_lde"] = {"error": repr(e)[:200]}
         out[name] = res
+    # the prover's commitment side with every column resident and the argument polynomials built on the device
+    # (crypto3_zk_b200/placeholder.py: V_P and its parts, gate / permutation expressions over the extended domain,
+    # quotient, the four commits, evaluation proof) on a satisfiable synthetic circuit of the same width
+    try:
+        del cols
+        torch.cuda.empty_cache()
+        out["prover_resident_columns"] = placeholder_prover_extra(args, torch, ctx, dev)
+    except Exception as e:
+        out["prover_resident_columns"] = {"error": repr(e)[:300]}
     return out
+
+
+def placeholder_prover_extra(args, torch, ctx, dev):
+    from crypto3_zk_b200 import placeholder as P
+    from crypto3_zk_b200 import workloads as W
+    from crypto3_zk_b200.lpc import FriParams
+    from crypto3_zk_b200.transcript import FiatShamirSequential
+    rows_log = args.placeholder_log
+    n = 1 << rows_log
+    mqc = 4
+    circuit, witness, public = W.placeholder_chain_circuit(ctx, "pallas_fp", rows_log, triples=10, seed=5, max_quotient_chunks=mqc)
+    fri = FriParams.with_max_step_one(rows_log, 40, 3)
+    res, best = None, None
+    for it in range(3):
+        tr = FiatShamirSequential(0, b"placeholder-prover")
+        tm = {}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = P.placeholder_prove(ctx, circuit, 0, fri, witness, public, tr, timings=tm)
+        torch.cuda.synchronize()
+        total = (time.perf_counter() - t0) * 1e3
+        cur = {"ms_total_with_preprocessing": total, "ms_prover": total - tm.get("preprocess_fixed_batch", 0.0), "stages_ms": tm}
+        if it >= 1 and (best is None or cur["ms_prover"] < best["ms_prover"]):
+            best = cur
+        y, z, nchunks = res["challenge"], res["eval_proof"]["z"], res["quotient_chunks"]
+        exact = all(r == 0 for r in res["eval_proof"]["remainders"])
+        log_d = res["log_d"]
+        del res
+        torch.cuda.empty_cache()
+    p = circuit.F.p
+    t_y = sum(pow(y, n * k, p) * z[P.QUOTIENT_BATCH][k][0] for k in range(nchunks)) % p
+    best.update({"rows": n, "witness_columns": circuit.n_witness, "public_columns": circuit.n_public, "selectors": circuit.n_selector,
+                 "permuted_columns": len(circuit.permuted_columns), "max_quotient_chunks": mqc, "permutation_parts": circuit.permutation_parts,
+                 "extended_domain_log_blowup": log_d, "quotient_chunks": nchunks, "evaluation_quotients_exact": exact,
+                 "T_at_challenge_nonzero": t_y != 0,
+                 "note": "gates a*b=c and a(next)=c over 10 column triples, copy constraints a[j+1]=c[j]; keccak-256, fri_params(1, rows_log, 40, 3); "
+                         "the verifier identity F(y) = Z(y) T(y) on the opened values is checked by tests/test_gpu_placeholder.py at small sizes"})
+    return best
 
 
 # ------------------------------------------------------------------------------------------ main arm
@@ -869,23 +917,16 @@ def main():
                         "algorithmic_bytes_per_launch": per_launch, "launches_per_step": launches / args.steps,
                         "avg_launch_ms": ms_per_step / max(launches / args.steps, 1)}
     # the co-limiter SURVEY 8(d) asks for next to the HBM figure: modular products per step against the measured peak of
-    # this field's multiplier.  Products per polynomial: inverse transform = butterflies log_in/2 per
-    # element + one inter-pass twiddle per pass boundary; forward transform = the same on 2^log_out elements minus the
-    # zero levels of pass 1 (half a product per element and level) and minus the known outputs in every later pass.
+    # this field's multiplier.  Products per polynomial, counted exactly as the pass kernels execute them
+    # (csrc_plan.ntt_products_per_element): tile butterflies with the unit twiddles of block 0 skipped, one inter-pass
+    # twiddle per pass boundary, minus the zero levels of pass 1 and the known outputs of the later passes.
     try:
-        from crypto3_zk_b200.csrc_plan import ntt_radices
-        lr_in, lr_out = ntt_radices(args.log_in), ntt_radices(args.log_out, small_first=True)
+        from crypto3_zk_b200.csrc_plan import ntt_products_per_element, ntt_radices
         z = args.log_out - args.log_in
-        known = z >= 3 and len(lr_out) >= 2 and z + 3 <= lr_out[0]
-        prod = n_in * (args.log_in / 2.0 + len(lr_in) - 1)
-        fwd = 0.0
-        for i, r in enumerate(lr_out):
-            per = r / 2.0 + (1 if i + 1 < len(lr_out) else 0)
-            if i == 0:
-                per -= min(z, r) / 2.0
-            frac = (1 - 2.0 ** -z) if (known and i > 0) else 1.0
-            fwd += per * frac
-        prod += n_out * fwd
+        lr_out = ntt_radices(args.log_out, small_first=True)
+        zl = z if 0 <= args.log_in - (args.log_out - lr_out[0]) < lr_out[0] else 0
+        prod = n_in * ntt_products_per_element(args.log_in, inverse=True)
+        prod += n_out * ntt_products_per_element(args.log_out, small_first=True, zero_levels=zl, known_log=z)
         peak_mul = ctx.bench_field_mul("pallas_fq", 148 * 8, 256, 2048)
         line["roofline"]["int_pipe"] = {"field_mul_per_step": prod * args.batch, "field_mul_per_s": prod * args.batch / (ms_per_step * 1e-3),
                                         "peak_field_mul_per_s": peak_mul, "frac": prod * args.batch / (ms_per_step * 1e-3) / peak_mul,
