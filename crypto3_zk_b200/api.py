@@ -637,6 +637,39 @@ class Context:
         capi.check(capi.lib().zkb_batch_exp(self._h, c.cid, n, b, sb.ptr, o.ptr, sb.mem, _stream_ptr(scalars, stream)), self._h)
         return out
 
+    def points_decompress(self, curve, octets, n, offset=0, stride=None, status=False, stream=None):
+        """zkb_points_decompress: n compressed points of the reference's wire format (48-byte G1 / 96-byte G2 encodings,
+        `stride` bytes apart, starting at byte `offset` of `octets`: bytes-like, a uint8 numpy array or a uint8 device
+        tensor) -> affine points [n, 2, coord_limbs] (device tensor when `octets` is one, else a numpy array).  Raises
+        ZkbInvalidArgument when an encoding is not a point (invalid_msg_data upstream); with status=True returns
+        (points, status bytes) instead and leaves the judgement to the caller."""
+        import torch
+        c = _curve(curve)
+        cl = coord_limbs(c)
+        width = 4 * cl
+        stride = width if stride is None else int(stride)
+        if _is_torch(octets):
+            if octets.dtype != torch.uint8 or not octets.is_cuda or not octets.is_contiguous():
+                raise ValueError("octets must be a contiguous uint8 CUDA tensor")
+            total, ptr, mem = octets.numel(), octets.data_ptr() + offset, capi.MEM_DEVICE
+            out = torch.empty((n, 2, cl), dtype=torch.int32, device=octets.device)
+            st = torch.empty((n,), dtype=torch.uint8, device=octets.device) if status else None
+            optr, sptr = out.data_ptr(), (st.data_ptr() if status else None)
+        else:
+            arr = np.frombuffer(octets, dtype=np.uint8) if not isinstance(octets, np.ndarray) else np.ascontiguousarray(octets, dtype=np.uint8)
+            total, ptr, mem = arr.size, arr.ctypes.data + offset, capi.MEM_HOST
+            out = np.zeros((n, 2, cl), dtype=np.uint32)
+            st = np.zeros((n,), dtype=np.uint8) if status else None
+            optr, sptr = out.ctypes.data, (st.ctypes.data if status else None)
+        if n and offset + (n - 1) * stride + width > total:
+            raise ValueError("octets too short for %d points" % n)
+        rc = capi.lib().zkb_points_decompress(self._h, c.cid, n, ptr, stride, optr, sptr, mem, _stream_ptr(octets if _is_torch(octets) else None, stream))
+        if status and rc == capi.ERR_INVALID_ARGUMENT:
+            capi.lib().zkb_ctx_clear_error(self._h)
+            return out, st
+        capi.check(rc, self._h)
+        return (out, st) if status else out
+
     def grid_points(self, curve, n, table_a, table_b, stream=None):
         """Synthetic bases on the device: out[i] = table_a[i % m] + table_b[i // m] (torch int32 [n,2,cl])."""
         import torch

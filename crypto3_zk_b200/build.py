@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libzkb200.so")
 
-CU_SOURCES = ["zkb_ctx.cu", "zkb_ntt.cu", "zkb_msm.cu", "zkb_hash.cu", "zkb_poly.cu", "zkb_scan.cu", "zkb_multi.cu", "zkb_plonk.cu"]
+CU_SOURCES = ["zkb_ctx.cu", "zkb_ntt.cu", "zkb_msm.cu", "zkb_hash.cu", "zkb_poly.cu", "zkb_scan.cu", "zkb_multi.cu", "zkb_plonk.cu", "zkb_points.cu"]
 CXX_SOURCES = ["zkb_msm_host.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

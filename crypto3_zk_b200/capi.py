@@ -20,7 +20,7 @@ SYMBOLS = [
     "zkb_ntt", "zkb_lde", "zkb_vec", "zkb_fri_fold", "zkb_lpc_commit", "zkb_merkle_commit",
     "zkb_merkle_digest_bytes", "zkb_merkle_root_of_digests", "zkb_merkle_leaves", "zkb_merkle_path", "zkb_merkle_free",
     "zkb_msm_bases_create", "zkb_msm_bases_free", "zkb_msm_bases_size", "zkb_msm_bases_precompute", "zkb_msm", "zkb_msm_partial",
-    "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul", "zkb_bench_imad_wide", "zkb_ctx_clear_error", "zkb_msm_window_plan", "zkb_expr_eval", "zkb_quotient_split", "zkb_lookup_sort",
+    "zkb_msm_combine", "zkb_msm_g1", "zkb_g1_grid_points", "zkb_bench_field_mul", "zkb_bench_imad_wide", "zkb_ctx_clear_error", "zkb_msm_window_plan", "zkb_expr_eval", "zkb_quotient_split", "zkb_lookup_sort", "zkb_points_decompress",
     "zkb_multi_create", "zkb_multi_destroy", "zkb_multi_size", "zkb_multi_ctx", "zkb_multi_last_error", "zkb_msm_bases_multi_create",
     "zkb_msm_bases_multi_precompute", "zkb_msm_bases_multi_free", "zkb_msm_multi", "zkb_lpc_commit_multi",
     "zkb_fri_commit_phase", "zkb_poly_evaluate", "zkb_poly_lincomb", "zkb_poly_div_linear",
@@ -108,6 +108,7 @@ def lib():
     L.zkb_expr_eval.argtypes = [vp, i, u64, u32, vp, vp, u32, u32p, u32, vp, u64, u64, i, vp]
     L.zkb_quotient_split.argtypes = [vp, i, i, i, vp, u32, vp, vp]
     L.zkb_lookup_sort.argtypes = [vp, i, u64, u64, u32, vp, u32, vp, vp, vp]
+    L.zkb_points_decompress.argtypes = [vp, i, u64, vp, u64, vp, vp, i, vp]
     L.zkb_multi_create.argtypes = [ctypes.POINTER(i), u32, ctypes.POINTER(vp)]
     L.zkb_multi_destroy.argtypes = [vp]
     L.zkb_multi_destroy.restype = None

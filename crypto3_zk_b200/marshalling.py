@@ -33,6 +33,8 @@ non-canonical field element or an x with no point on the curve raises `InvalidMs
 (status_type::invalid_msg_data).  Points are affine (x, y) integers ((c0, c1) pairs on G2), None = infinity, as
 in groth16.py.
 """
+import numpy as np
+
 from .fields import FIELD_BY_NAME
 
 P = FIELD_BY_NAME["bls12_381_fq"].p
@@ -412,7 +414,28 @@ def proving_key_to_bytes(pk, pad=True):
     return body + bytes(2 * estimate - len(body))
 
 
-def proving_key_from_bytes(buf, off=0):
+def _device_points(ctx, curve, buf, off, n, stride=None):
+    """n compressed points starting at byte `off` of the host blob -> device tensor [n, 2, limbs] (one square root per
+    point on the GPU: zkb_points_decompress); a malformed encoding raises InvalidMsgData like the scalar readers"""
+    import torch
+    from . import capi
+    width = G2_BYTES if curve.endswith("g2") else G1_BYTES
+    stride = width if stride is None else stride
+    if n == 0:
+        return torch.empty((0, 2, width // 4), dtype=torch.int32, device="cuda:%d" % ctx.device)
+    _need(buf, off, (n - 1) * stride + width)
+    raw = np.frombuffer(buf, dtype=np.uint8, count=(n - 1) * stride + width, offset=off)
+    octets = torch.from_numpy(raw.copy()).to("cuda:%d" % ctx.device)
+    try:
+        return ctx.points_decompress(curve, octets, n, stride=stride)
+    except capi.ZkbInvalidArgument as e:
+        raise InvalidMsgData(str(e))
+
+
+def proving_key_from_bytes(buf, off=0, ctx=None):
+    """With `ctx` the query vectors (A, B, H, L: one compressed point per variable / constraint) are decompressed on the
+    device and returned as [n, 2, limbs] device tensors - the form groth16.ProvingKey takes; without it as lists of
+    Python-integer points."""
     out = {}
     o = off
     for name, rd, n in (("alpha_g1", g1_from_bytes, G1_BYTES), ("beta_g1", g1_from_bytes, G1_BYTES),
@@ -420,18 +443,37 @@ def proving_key_from_bytes(buf, off=0):
                         ("delta_g2", g2_from_bytes, G2_BYTES)):
         out[name] = rd(buf, o)
         o += n
-    out["A_query"], used = _g1_list_from_bytes(buf, o)
+
+    def g1_list(o):
+        if ctx is None:
+            return _g1_list_from_bytes(buf, o)
+        n = size_t_from_bytes(buf, o)
+        return _device_points(ctx, "bls12_381_g1", buf, o + SIZE_T_BYTES, n), SIZE_T_BYTES + n * G1_BYTES
+
+    out["A_query"], used = g1_list(o)
     o += used
     total_b = size_t_from_bytes(buf, o)
     o += SIZE_T_BYTES
     _need(buf, o, total_b)
-    out["B_indices"], out["B_g2"], out["B_g1"], out["B_domain_size"], used = kc_vector_from_bytes(buf, o)
+    if ctx is None:
+        out["B_indices"], out["B_g2"], out["B_g1"], out["B_domain_size"], used = kc_vector_from_bytes(buf, o)
+    else:
+        n = size_t_from_bytes(buf, o)
+        used = _kc_vector_bytes(n)
+        _need(buf, o, used)
+        idx = np.frombuffer(buf, dtype=">u4", count=n, offset=o + SIZE_T_BYTES).astype(np.int64)
+        po = o + SIZE_T_BYTES * (1 + n)
+        pair = G2_BYTES + G1_BYTES
+        out["B_indices"] = idx
+        out["B_g2"] = _device_points(ctx, "bls12_381_g2", buf, po, n, stride=pair)
+        out["B_g1"] = _device_points(ctx, "bls12_381_g1", buf, po + G2_BYTES, n, stride=pair)
+        out["B_domain_size"] = size_t_from_bytes(buf, po + pair * n)
     if used != total_b:
         raise InvalidMsgData("B_query size field disagrees with its contents")
     o += total_b
-    out["H_query"], used = _g1_list_from_bytes(buf, o)
+    out["H_query"], used = g1_list(o)
     o += used
-    out["L_query"], used = _g1_list_from_bytes(buf, o)
+    out["L_query"], used = g1_list(o)
     o += used
     out["num_inputs"], out["num_aux"], out["constraints"], _ = r1cs_constraint_system_from_bytes(buf, o)
     return out

@@ -373,6 +373,19 @@ int zkb_quotient_split(zkb_ctx *ctx, int field, int log_n, int log_ext, const vo
 int zkb_lookup_sort(zkb_ctx *ctx, int field, uint64_t n, uint64_t usable_rows, uint32_t n_inputs, const void *inputs_device,
                     uint32_t n_values, const void *values_device, void *sorted_device, void *stream);
 
+/* ---- compressed points of the Groth16 wire format ---------------------------------------------- */
+/* Batched curve_element_serializer<bls12<381>>::octets_to_g1_point / octets_to_g2_point: the readers of
+ * zk/snark/systems/ppzksnark/r1cs_gg_ppzksnark/marshalling.hpp:97-198 call it once per element of a proving key's query
+ * vectors (:656-738) and every call is a square root in Fq (G1) or Fq2 (G2).  octets: n encodings of 48 (G1) / 96 (G2)
+ * bytes, stride_bytes apart (a knowledge-commitment vector interleaves G2 | G1: stride 144); out: n affine points,
+ * canonical limbs, (0, 0) for the point at infinity - the layout zkb_msm_bases_create takes.  status_out (optional, n
+ * bytes, same memory space): 0 ok, 1 infinity, 2 not in compressed form, 3 infinity flag with a payload, 4 coordinate not
+ * reduced, 5 x is not the abscissa of a curve point.  Any status >= 2 makes the call return ZKB_ERR_INVALID_ARGUMENT
+ * (the reader's status_type::invalid_msg_data); the message names the first such point.  curve: ZKB_CURVE_BLS12_381_G1 /
+ * _G2 (ZKB_ERR_UNSUPPORTED otherwise: upstream serializes no other curve in this format). */
+int zkb_points_decompress(zkb_ctx *ctx, int curve, uint64_t n, const uint8_t *octets, uint64_t stride_bytes,
+                          void *points_affine_out, uint8_t *status_out, int mem, void *stream);
+
 /* ---- device buffers for host templates ------------------------------------------------------------ */
 /* lpc_commitment_scheme keeps its polynomials as members between commit / eval_polys / proof_eval
  * (zk/commitments/polynomial/lpc.hpp:66-200, batched_commitment.hpp:60-250: `_polys`, `_z`); a host template over this ABI

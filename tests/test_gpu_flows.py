@@ -622,6 +622,17 @@ def test_groth16_prove_vs_oracle(ctx, curve, kind, nc, ni):
         wire = marshalling.proof_to_bytes(dg.prove(ctx, dpk2, primary, aux, r, s))
         assert len(wire) == 192 and wire == marshalling.proof_to_bytes(want)
         assert marshalling.proof_from_bytes(wire) == want
+        # the same blob with the query vectors decompressed on the device (zkb_points_decompress): same points, same proof
+        kd = marshalling.proving_key_from_bytes(blob, ctx=ctx)
+        from crypto3_zk_b200.api import _affine_from_limbs
+        for name, cl, deg in (("A_query", 12, 1), ("B_g1", 12, 1), ("H_query", 12, 1), ("L_query", 12, 1), ("B_g2", 24, 2)):
+            arr = kd[name].cpu().numpy().view(np.uint32)
+            assert [_affine_from_limbs(arr[i].reshape(-1), cl, deg) for i in range(arr.shape[0])] == list(k[name]), name
+        assert list(kd["B_indices"]) == list(k["B_indices"]) and kd["B_domain_size"] == k["B_domain_size"]
+        dpk3 = ProvingKey(ctx, G1.name, G2.name, R1csConstraintSystem(kd["num_inputs"], kd["num_aux"], kd["constraints"]),
+                          kd["alpha_g1"], kd["beta_g1"], kd["beta_g2"], kd["delta_g1"], kd["delta_g2"], kd["A_query"],
+                          kd["B_indices"], kd["B_g2"], kd["B_g1"], kd["H_query"], kd["L_query"])
+        assert marshalling.proof_to_bytes(dg.prove(ctx, dpk3, primary, aux, r, s)) == wire
 
 
 @pytest.mark.parametrize("curve,nc,ni", [("bls12_381", 13, 2), ("bn254", 27, 4)])
