@@ -590,12 +590,84 @@ def groth16_extra(args, torch, ctx, dev):
             "msm_B_g2": time_cuda(torch, lambda: ctx.multiexp(pk.B2, sc[:pk.B2.n]), 3)}
     except Exception as e:   # e.g. not enough memory for the tables next to the other extras
         tables["error"] = str(e)[:200]
-    return {"ms_per_proof": prove_ms, "with_window_tables": tables, "e2e_ms_host_assignment": e2e_ms, "witness_map_ms": wm_ms, "parts_ms_random_scalars": parts,
-            "domain": m, "constraints": nc, "variables": cs.num_variables, "inputs": ni,
-            "msm_sizes": {"A": pk.A.n, "B": pk.B2.n, "H": m - 1, "L": pk.L.n},
+    sizes = {"A": pk.A.n, "B": pk.B2.n, "H": m - 1, "L": pk.L.n}
+    nvars = cs.num_variables
+    del pk, sc
+    torch.cuda.empty_cache()
+    try:
+        gen = groth16_generator_extra(args, torch, ctx, dev, cs, sides, x, xd, r, s)
+    except Exception as e:
+        gen = {"error": repr(e)[:300]}
+    return {"ms_per_proof": prove_ms, "with_window_tables": tables, "generator_on_device": gen, "e2e_ms_host_assignment": e2e_ms, "witness_map_ms": wm_ms, "parts_ms_random_scalars": parts,
+            "domain": m, "constraints": nc, "variables": nvars, "inputs": ni,
+            "msm_sizes": sizes,
             "h_degree_check": h_ok, "proof_x_limb": (proof[0][0] & 0xFFFFFFFF) if proof[0] else None,
             "host_prep_s": {"r1cs_example": t_build, "synthetic_key": t_key},
             "reference_published": "docs/perf.md:24-25: 84.01 s for 10^6 constraints on an i7-4770, 1 thread (other hardware)"}
+
+
+def groth16_generator_extra(args, torch, ctx, dev, cs, sides, x, xd, r, s):
+    """SURVEY 8(f)-4 at the size of configs[3]: the generator with the QAP evaluation and all key vectors on the device
+    (groth16.generator_device), the prover on that REAL key, g_A checked against its exponent
+    alpha + <x, A(t)> + r delta computed on the host from the device's A(t); and the key-blob reader's square roots
+    (zkb_points_decompress) on 2^20 compressed BLS12-381 G1 points."""
+    import numpy as np
+    from crypto3_zk_b200 import groth16 as dg, workloads as W
+    from crypto3_zk_b200.api import _ints
+    from crypto3_zk_b200.fields import FIELD_BY_NAME
+    F = FIELD_BY_NAME["bn254_fr"]
+    p = F.p
+    nc, ni, nv = cs.num_constraints, cs.num_inputs, cs.num_variables
+    toxic = [0x1111111111111111111111111111 + 7 * k * 0x123456789abcdef for k in range(5)]
+    t, alpha, beta, gamma, delta = toxic
+    out = {}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    at = dg.qap_instance_evaluation_device(ctx, F, nc, ni, nv, sides, t)[0]
+    torch.cuda.synchronize()
+    out["qap_instance_evaluation_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    key, vk = dg.generator_device(ctx, "bn254_g1", "bn254_g2", nc, ni, nv, sides, t, alpha, beta, gamma, delta)
+    torch.cuda.synchronize()
+    out["generator_ms"] = (time.perf_counter() - t0) * 1e3
+    out["key_points"] = {k: int(key[k].shape[0]) for k in ("A_query", "B_g2", "B_g1", "H_query", "L_query")}
+    pk = dg.ProvingKey(ctx, "bn254_g1", "bn254_g2", cs, key["alpha_g1"], key["beta_g1"], key["beta_g2"], key["delta_g1"],
+                       key["delta_g2"], key["A_query"], key["B_indices"], key["B_g2"], key["B_g1"], key["H_query"],
+                       key["L_query"], csr=sides)
+    proof = dg.prove(ctx, pk, None, None, r, s, x_device=xd)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dg.prove(ctx, pk, None, None, r, s, x_device=xd)
+    torch.cuda.synchronize()
+    out["ms_per_proof_real_key"] = (time.perf_counter() - t0) * 1e3
+    # g_A = (alpha + sum_i x_i A_i(t) + r delta) G (prover.hpp:141-143): the exponent from the device's A(t), on the host
+    a_t, xs = _ints(at.cpu().numpy().view(np.uint32)), _ints(x)
+    expo = (alpha + sum(a * b for a, b in zip(a_t, xs)) + r * delta) % p
+    from crypto3_zk_b200.fields import CURVE_BY_NAME
+    g = CURVE_BY_NAME["bn254_g1"]
+    from crypto3_zk_b200.api import _affine_from_limbs, _int_rows
+    ga = np.asarray(ctx.batch_exp("bn254_g1", (g.gen_x, g.gen_y), _int_rows([expo])), dtype=np.uint32)
+    out["g_A_matches_its_exponent"] = _affine_from_limbs(ga[0].reshape(-1), 8, 1) == proof[0]
+    del pk, key, at
+    torch.cuda.empty_cache()
+    # compressed points of a BLS12-381 key blob: 2^20 G1 encodings made from device points, decompressed on the device
+    n = 1 << 20
+    pts = W.curve_grid_points(ctx, "bls12_381_g1", n, seed=11)
+    a = pts.cpu().numpy().view(np.uint32)
+    blob = np.frombuffer(a[:, 0, ::-1].astype(">u4").tobytes(), dtype=np.uint8).reshape(n, 48).copy()
+    half = np.array([((FIELD_BY_NAME["bls12_381_fq"].p - 1) // 2 >> (32 * k)) & 0xFFFFFFFF for k in range(12)], dtype=np.uint32)
+    y = a[:, 1, :]
+    gt = np.zeros(n, dtype=bool)
+    decided = np.zeros(n, dtype=bool)
+    for k in range(11, -1, -1):                                 # y > (p - 1) / 2, limb by limb from the top
+        gt |= ~decided & (y[:, k] > half[k])
+        decided |= y[:, k] != half[k]
+    blob[:, 0] |= np.where(gt, 0xA0, 0x80).astype(np.uint8)
+    d = torch.from_numpy(blob.reshape(-1)).to(dev)
+    got = ctx.points_decompress("bls12_381_g1", d, n)
+    ms = time_cuda(torch, lambda: ctx.points_decompress("bls12_381_g1", d, n), 3, warmup=1)
+    out["bls12_381_g1_decompress_2p20"] = {"ms": ms, "points_per_s": n / (ms * 1e-3), "same_points": bool(torch.equal(got, pts))}
+    return out
 
 
 def placeholder_extra(args, torch, ctx, dev):

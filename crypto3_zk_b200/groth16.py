@@ -308,6 +308,110 @@ def generator(ctx, curve_g1, curve_g2, cs, t, alpha, beta, gamma, delta, g1_gene
     return key, vk
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The generator with every vector on the device: nothing below touches a Python integer per element.
+def csr_transpose(row_ptr, col_idx, values, ncols):
+    """CSR arrays of the transposed matrix (numpy; stable in the row index, so every output row keeps constraint order)"""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    col_idx = np.asarray(col_idx, dtype=np.int64)
+    rows = np.repeat(np.arange(row_ptr.size - 1, dtype=np.int64), np.diff(row_ptr))
+    order = np.argsort(col_idx, kind="stable")
+    tp = np.zeros(ncols + 1, dtype=np.uint64)
+    tp[1:] = np.cumsum(np.bincount(col_idx, minlength=ncols)).astype(np.uint64)
+    return tp, rows[order].astype(np.uint32), np.ascontiguousarray(np.asarray(values)[order])
+
+
+def _const_rows(ctx, value, n):
+    import torch
+    row = torch.from_numpy(_int_rows([int(value)]).view(np.int32)).to("cuda:%d" % ctx.device)
+    return row.expand(n, 8).contiguous()
+
+
+def qap_instance_evaluation_device(ctx, F, num_constraints, num_inputs, num_variables, csr_sides, t):
+    """r1cs_to_qap::instance_map_with_evaluation (r1cs_to_qap.hpp:138-204) on the device: u = all Lagrange polynomials at
+    t (powers of omega by a product scan, one batched inversion), At / Bt / Ct = transposed sparse mat-vec of the three
+    sides with u (plus the input-consistency rows on A), Ht = powers of t.  csr_sides = [(row_ptr, col, values)] x 3 of
+    the constraint system (rows = constraints).  Returns device tensors (At, Bt, Ct [num_variables + 1, 8],
+    Ht [m + 1, 8]) and the integers Zt, m."""
+    import torch
+    from .fields import omega as _omega
+    p = F.p
+    nc, ni, nv = num_constraints, num_inputs, num_variables
+    m = nc + ni + 1
+    if m & (m - 1):
+        raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT,
+                                      "num_constraints + num_inputs + 1 must be a power of two (basic_radix2_domain)")
+    log_m = m.bit_length() - 1
+    t = int(t) % p
+    zt = (pow(t, m, p) - 1) % p
+    if zt == 0:
+        raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "t lies in the evaluation domain (Z(t) = 0: no quotient, generator.hpp draws t at random)")
+    pows = ctx.prefix_product(F.name, _const_rows(ctx, _omega(F, log_m), m))                 # omega^i
+    inv = ctx.batch_inverse(F.name, ctx.vec(F.name, capi.VEC_SUB, _const_rows(ctx, t, m), pows))
+    u = ctx.vec(F.name, capi.VEC_MUL, pows, inv)
+    u = ctx.poly_lincomb(F.name, u, m, [zt * pow(m, p - 2, p) % p])                           # L_i(t) = Z(t)/m omega^i / (t - omega^i)
+    sides = []
+    x = u[:nc].contiguous()
+    for row_ptr, col, vals in csr_sides:
+        tp, tc, tv = csr_transpose(row_ptr, col, vals, nv + 1)
+        mat = ctx.sparse_matrix(F.name, nv + 1, nc, tp, tc, tv)
+        out = torch.empty((nv + 1, 8), dtype=torch.int32, device=u.device)
+        mat.matvec(x, out)
+        mat.free()
+        sides.append(out)
+    at = sides[0]
+    at[:ni + 1] = ctx.vec(F.name, capi.VEC_ADD, at[:ni + 1].contiguous(), u[nc:nc + ni + 1].contiguous())
+    ht = ctx.prefix_product(F.name, _const_rows(ctx, t, m + 1))
+    return at, sides[1], sides[2], ht, zt, m
+
+
+def generator_device(ctx, curve_g1, curve_g2, num_constraints, num_inputs, num_variables, csr_sides, t, alpha, beta, gamma,
+                     delta, g1_generator=None, g2_generator=None):
+    """r1cs_gg_ppzksnark_generator::basic_process (generator.hpp:83-235) with the QAP evaluation, the key scalars and every
+    key element on the device; the caller applies swap_AB_if_beneficial to csr_sides beforehand (workloads does).
+    Returns (key, vk) like `generator`, but the query vectors are device tensors [n, 2, limbs] ((0, 0) = infinity) and
+    B_indices a numpy array - the form ProvingKey / proving_key_from_dict take."""
+    import torch
+    from .api import _affine_from_limbs
+    g1 = CURVE_BY_NAME[curve_g1] if isinstance(curve_g1, str) else curve_g1
+    g2 = CURVE_BY_NAME[curve_g2] if isinstance(curve_g2, str) else curve_g2
+    F = FIELD_BY_NAME[g1.scalar_field]
+    p = F.p
+    t, alpha, beta, gamma, delta = (int(v) % p for v in (t, alpha, beta, gamma, delta))
+    if gamma == 0 or delta == 0:
+        raise capi.ZkbInvalidArgument(capi.ERR_INVALID_ARGUMENT, "gamma and delta must be invertible (generator.hpp:162-163)")
+    ni, nv = num_inputs, num_variables
+    at, bt, ct, ht, zt, m = qap_instance_evaluation_device(ctx, F, num_constraints, ni, nv, csr_sides, t)
+    ginv, dinv = pow(gamma, p - 2, p), pow(delta, p - 2, p)
+    abc = ctx.poly_lincomb(F.name, torch.stack([at, bt, ct]), nv + 1, [beta, alpha, 1])
+    gamma_abc = ctx.poly_lincomb(F.name, abc[:ni + 1].contiguous(), ni + 1, [ginv])
+    lt = ctx.poly_lincomb(F.name, abc[ni + 1:].contiguous(), nv - ni, [dinv]) if nv > ni else abc[:0]
+    hs = ctx.poly_lincomb(F.name, ht[:m - 1].contiguous(), m - 1, [zt * dinv % p])
+    b_idx = torch.nonzero((bt != 0).any(dim=1)).flatten()
+    b_sc = bt.index_select(0, b_idx)
+    head1 = torch.from_numpy(_int_rows([alpha, beta, delta, gamma]).view(np.int32)).to(at.device)
+    head2 = torch.from_numpy(_int_rows([beta, delta, gamma]).view(np.int32)).to(at.device)
+    base1 = (g1.gen_x, g1.gen_y) if g1_generator is None else g1_generator
+    base2 = (g2.gen_x, g2.gen_y) if g2_generator is None else g2_generator
+    pts1 = ctx.batch_exp(g1.name, base1, torch.cat([head1, gamma_abc, at, b_sc, hs, lt]).contiguous())
+    pts2 = ctx.batch_exp(g2.name, base2, torch.cat([head2, b_sc]).contiguous())
+    cl1, cl2 = coord_limbs(g1), coord_limbs(g2)
+    h1 = pts1[:4].cpu().numpy().view(np.uint32)
+    h2 = pts2[:3].cpu().numpy().view(np.uint32)
+    pt1 = [_affine_from_limbs(h1[i].reshape(-1), cl1, g1.deg) for i in range(4)]
+    pt2 = [_affine_from_limbs(h2[i].reshape(-1), cl2, g2.deg) for i in range(3)]
+    parts, o = [], 4
+    for n in (ni + 1, nv + 1, int(b_idx.numel()), m - 1, nv - ni):
+        parts.append(pts1[o:o + n])
+        o += n
+    gabc, a_query, b_g1, h_query, l_query = parts
+    key = dict(alpha_g1=pt1[0], beta_g1=pt1[1], beta_g2=pt2[0], delta_g1=pt1[2], delta_g2=pt2[1], A_query=a_query,
+               B_indices=b_idx.cpu().numpy(), B_g2=pts2[3:], B_g1=b_g1, B_domain_size=nv + 1, H_query=h_query, L_query=l_query,
+               num_inputs=ni, num_aux=nv - ni)
+    vk = dict(gamma_g2=pt2[2], delta_g2=pt2[1], gamma_g1=pt1[3], gamma_ABC_g1=gabc)
+    return key, vk
+
+
 def proving_key_from_dict(ctx, curve_g1, curve_g2, key, precompute=False):
     """Device-resident ProvingKey from the dict `generator` returns / marshalling.proving_key_from_bytes reads."""
     cs = R1csConstraintSystem(key["num_inputs"], key["num_aux"], key["constraints"])

@@ -655,3 +655,46 @@ def test_groth16_generator_vs_oracle(ctx, curve, nc, ni):
     r, s = fields.random_elements(F, 2, 32)
     dpk = dg.proving_key_from_dict(ctx, G1.name, G2.name, key)
     assert dg.prove(ctx, dpk, primary, aux, r, s) == groth16.prove(pk, primary, aux, r, s, G1, G2, F)
+    # the same generator with the QAP evaluation and every key vector on the device (generator_device)
+    from crypto3_zk_b200.api import _affine_from_limbs
+    cs2 = dg.swap_ab_if_beneficial(pcs)
+    dkey, dvk = dg.generator_device(ctx, G1.name, G2.name, cs2.num_constraints, cs2.num_inputs, cs2.num_variables,
+                                    [cs2.csr(k) for k in range(3)], t, alpha, beta, gamma, delta)
+
+    def pts(tensor, curve):
+        a = tensor.cpu().numpy().view(np.uint32)
+        return [_affine_from_limbs(a[i].reshape(-1), curve.coord_limbs32, 2 if curve is G2 else 1) for i in range(a.shape[0])]
+
+    for name in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2"):
+        assert dkey[name] == getattr(pk, name), name
+    for name, curve in (("A_query", G1), ("B_g1", G1), ("H_query", G1), ("L_query", G1), ("B_g2", G2)):
+        assert pts(dkey[name], curve) == list(getattr(pk, name)), name
+    assert list(dkey["B_indices"]) == list(pk.B_indices)
+    assert pts(dvk["gamma_ABC_g1"], G1) == [vk["gamma_ABC_g1"][0]] + list(vk["gamma_ABC_g1"][1]) and dvk["gamma_g2"] == vk["gamma_g2"]
+    dkey["constraints"] = cs2.constraints
+    dpk2 = dg.proving_key_from_dict(ctx, G1.name, G2.name, dkey)
+    assert dg.prove(ctx, dpk2, primary, aux, r, s) == groth16.prove(pk, primary, aux, r, s, G1, G2, F)
+
+
+def test_qap_instance_evaluation_device_at_2p12(ctx):
+    """instance_map_with_evaluation (r1cs_to_qap.hpp:138-204) on the device against the host evaluation on Python integers,
+    4093 constraints from the numpy CSR builder of the 2^22 workload (transposed mat-vec, batched inversion, product scans)"""
+    from crypto3_zk_b200 import groth16 as dg
+    from crypto3_zk_b200 import workloads as W
+    F = fields.BN254_FR
+    ni = 2
+    nc = (1 << 12) - ni - 1
+    shape, sides, full = W.groth16_field_input_example(F.name, nc, ni, seed=3)
+    t = fields.random_elements(F, 1, 77)[0]
+    at, bt, ct, ht, zt, m = dg.qap_instance_evaluation_device(ctx, dg.FIELD_BY_NAME[F.name], nc, ni, shape.num_variables, sides, t)
+    cons = []
+    for row in range(nc):
+        con = []
+        for row_ptr, col, vals in sides:
+            lo, hi = int(row_ptr[row]), int(row_ptr[row + 1])
+            con.append([(int(col[k]), fields.u32_array_to_ints(vals[k:k + 1])[0]) for k in range(lo, hi)])
+        cons.append(tuple(con))
+    host_cs = dg.R1csConstraintSystem(ni, shape.num_aux, cons)
+    At, Bt, Ct, Ht, Zt, mm = dg.qap_instance_evaluation(host_cs, dg.FIELD_BY_NAME[F.name], t)
+    assert (zt, m) == (Zt, mm)
+    assert from_arr(host(at)) == At and from_arr(host(bt)) == Bt and from_arr(host(ct)) == Ct and from_arr(host(ht)) == Ht
