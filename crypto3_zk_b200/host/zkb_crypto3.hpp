@@ -1160,6 +1160,19 @@ public:
     }
     template <class Container>
     void append_to_batch(std::size_t index, const Container &polys) { for (const auto &q : polys) append_to_batch(index, q); }
+    // a whole batch that already lives on the device ([count][n] canonical limbs, e.g. columns an argument builder left
+    // there): copied into the scheme's own buffer, never through the host
+    void append_device_batch(std::size_t index, const void *device_polys, std::size_t count, std::size_t n) {
+        if (_locked[index] || _polys.count(index)) throw std::logic_error("lpc: batch already exists");
+        zkb_detail::log2_exact(n);
+        dbuf d(count * n * 32);
+        ck(zkb_buf_copy(ctx(), d.p, ZKB_MEM_DEVICE, device_polys, ZKB_MEM_DEVICE, count * n * 32, nullptr), "zkb_buf_copy");
+        _dev[index] = std::move(d);
+        _n[index] = n;
+        _polys[index].assign(count, poly_type());      // placeholders: only their number is read once the batch is uploaded
+        _points[index].assign(count, {});
+    }
+    bool has_batch(std::size_t index) const { return _polys.count(index) != 0; }
     void append_eval_point(std::size_t batch, const value_type &point) { for (auto &pts : _points.at(batch)) pts.push_back(point); }
     void append_eval_point(std::size_t batch, std::size_t poly, const value_type &point) { _points.at(batch).at(poly).push_back(point); }
     const std::map<std::size_t, std::vector<std::vector<value_type>>> &get_z() const { return _z; }

@@ -15,6 +15,7 @@
 
 #include "../../crypto3_zk_b200/host/zkb_crypto3.hpp"
 #include "../../crypto3_zk_b200/host/zkb_r1cs_gg_ppzksnark.hpp"
+#include "../../crypto3_zk_b200/host/zkb_placeholder.hpp"
 
 using namespace nil::crypto3;
 
@@ -586,6 +587,76 @@ static void groth16_prover_test(std::istream &in) {
     CHECK(V(5) * Gen + V(7) * Gen == V(12) * Gen && (V(5) * Gen - V(5) * Gen).is_zero() && Gen.doubled() == Gen + Gen);
 }
 
+// placeholder_prover (host/zkb_placeholder.hpp, after placeholder/prover.hpp:133-217) on the chain circuit of
+// crypto3_zk_b200/workloads.py: the Python wrapper writes the columns, this prints the commitments, the challenge, the
+// opened values and the transcript state, and the wrapper compares them with the Python driver's.
+static void placeholder_prover_test(std::istream &in) {
+    using namespace zk::snark;
+    typedef algebra::fields::pallas_base_field F;
+    typedef F::value_type V;
+    typedef hashes::keccak_1600<256> hash_type;
+    typedef placeholder_prover<F, hash_type, hash_type> prover;
+    typedef plonk_expression<V> expr;
+    typedef prover::dbuf dbuf;
+    std::size_t log_n, triples, usable, mqc, lambda, expand;
+    in >> log_n >> triples >> usable >> mqc >> lambda >> expand;
+    const std::size_t n = std::size_t(1) << log_n, nw = 3 * triples, npc = nw + 1;
+    auto read_cols = [&](std::size_t count) {
+        std::vector<std::uint32_t> limbs(count * n * 8);
+        std::string t;
+        for (std::size_t i = 0; i < count * n; i++) {
+            in >> t;
+            parse_elem<V>(t).to_canonical_limbs(&limbs[8 * i]);
+        }
+        dbuf d(limbs.size() * 4);
+        zkb_ctx *ctx = zkb_detail::context();
+        zkb_detail::check(zkb_buf_copy(ctx, d.p, ZKB_MEM_DEVICE, limbs.data(), ZKB_MEM_HOST, limbs.size() * 4, nullptr), ctx, "zkb_buf_copy");
+        return d;
+    };
+    prover::circuit_type c;
+    c.log_n = log_n; c.witness_columns = nw; c.public_input_columns = 1; c.constant_columns = 0; c.selector_columns = 2;
+    c.usable_rows = usable; c.max_quotient_chunks = mqc;
+    dbuf witness = read_cols(nw), pub = read_cols(1);
+    c.selectors = read_cols(2);
+    c.s_id = read_cols(npc);
+    c.s_sigma = read_cols(npc);
+    c.q_last = read_cols(1);
+    c.q_blind = read_cols(1);
+    c.lagrange_0 = read_cols(1);
+    for (std::size_t i = 0; i < npc; i++) c.permuted_columns.push_back(i);
+    plonk_gate<V> g0, g1;
+    g0.selector_index = 0; g1.selector_index = 1;
+    for (std::uint32_t k = 0; k < triples; k++) {
+        g0.constraints.push_back(expr::var(3 * k) * expr::var(3 * k + 1) - expr::var(3 * k + 2));
+        g1.constraints.push_back(expr::var(3 * k, 1) - expr::var(3 * k + 2));
+    }
+    c.gates = {g0, g1};
+    auto fp = zk::commitments::fri_params_type::with_max_step_one(log_n, lambda, expand);
+    prover::commitment_scheme_type scheme(fp);
+    std::vector<std::uint8_t> init = {'p', 'l', 'a', 'c', 'e', 'h', 'o', 'l', 'd', 'e', 'r', '-', 't', 'e', 's', 't'};
+    prover::transcript_type tr(init);
+    auto fixed_root = prover::preprocess(c, scheme, tr);
+    auto proof = prover::process(c, witness, pub, scheme, tr);
+    CHECK(proof.commitments.size() == 3);
+    auto hex = [](const std::vector<std::uint8_t> &v) { std::string o; char b[3]; for (auto x : v) { std::snprintf(b, 3, "%02x", x); o += b; } return o; };
+    std::printf("PLH fixed %s\n", hex(fixed_root).c_str());
+    for (const auto &kv : proof.commitments) std::printf("PLH root%zu %s\n", kv.first, hex(kv.second).c_str());
+    std::printf("PLH y %s\n", elem_hex(proof.challenge).c_str());
+    std::printf("PLH chunks %zu %zu\n", proof.quotient_chunks, proof.log_extension);
+    for (const auto &kv : proof.eval_proof.z) {
+        std::printf("PLH z%zu", kv.first);
+        for (const auto &pz : kv.second) {
+            std::printf(" |");
+            for (const auto &v : pz) std::printf(" %s", elem_hex(v).c_str());
+        }
+        std::printf("\n");
+    }
+    std::printf("PLH fri");
+    for (const auto &r : proof.eval_proof.fri_proof.fri_roots) std::printf(" %s", hex(r).c_str());
+    std::printf("\n");
+    std::printf("PLH transcript %s\n", hex(tr.state()).c_str());
+}
+
 int main(int argc, char **argv) {
     if (argc > 2 && !std::strcmp(argv[1], "groth16")) {
         try {
@@ -594,6 +665,17 @@ int main(int argc, char **argv) {
             f >> curve;
             if (curve == "bn254") groth16_prover_test<algebra::curves::alt_bn128<254>>(f);
             else groth16_prover_test<algebra::curves::bls12<381>>(f);
+        } catch (const std::exception &e) {
+            std::printf("EXCEPTION %s\n", e.what());
+            return 2;
+        }
+        std::printf(failures ? "FAILED %d checks\n" : "ALL OK\n", failures);
+        return failures ? 1 : 0;
+    }
+    if (argc > 2 && !std::strcmp(argv[1], "placeholder")) {
+        try {
+            std::ifstream f(argv[2]);
+            placeholder_prover_test(f);
         } catch (const std::exception &e) {
             std::printf("EXCEPTION %s\n", e.what());
             return 2;

@@ -16,7 +16,8 @@ def _build():
     build.build()
     src = os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp")
     deps = [src, os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_crypto3.hpp"),
-            os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_r1cs_gg_ppzksnark.hpp"), os.path.join(ROOT, "include", "zkb200.h")]
+            os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_r1cs_gg_ppzksnark.hpp"),
+            os.path.join(ROOT, "crypto3_zk_b200", "host", "zkb_placeholder.hpp"), os.path.join(ROOT, "include", "zkb200.h")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         lib = os.path.join(ROOT, "crypto3_zk_b200")
         subprocess.check_call(["g++", "-O2", "-std=c++17", src, "-o", EXE, "-L" + lib, "-lzkb200", "-Wl,-rpath," + lib])
@@ -173,3 +174,51 @@ def test_cpp_groth16_prover_vs_oracle(tmp_path, curve, kind, nc, ni):
     want = groth16.prove(pk, primary, aux, r, s, G1, G2, F)
     got = [[int(v, 16) for v in part.split()] for part in " ".join(out["G16PROOF"]).split(" | ")]
     assert got[0] == list(want[0]) and got[1] == [want[1][0][0], want[1][0][1], want[1][1][0], want[1][1][1]] and got[2] == list(want[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n,triples,mqc", [(4, 1, 0), (6, 2, 4)])
+def test_cpp_placeholder_prover_vs_python_driver(tmp_path, log_n, triples, mqc):
+    """C++ placeholder_prover<F, Hash, Hash>::preprocess / process (host/zkb_placeholder.hpp, after placeholder/prover.hpp:
+    133-217, permutation_argument.hpp:95-215, gates_argument.hpp:133-217) on the chain circuit: the same commitments,
+    challenge, opened values, FRI roots and transcript state as crypto3_zk_b200.placeholder.placeholder_prove, which
+    tests/test_gpu_placeholder.py checks against the oracle and the verifier's identity."""
+    import numpy as np
+    from crypto3_zk_b200 import Context, placeholder as P, workloads as W
+    from crypto3_zk_b200.lpc import FriParams
+    from crypto3_zk_b200.transcript import FiatShamirSequential
+    F = fields.PALLAS_FP
+    ctx = Context(0)
+    try:
+        circuit, witness, public = W.placeholder_chain_circuit(ctx, F.name, log_n, triples=triples, seed=log_n, max_quotient_chunks=mqc)
+
+        def dump(t):
+            a = t.cpu().numpy().view(np.uint32).reshape(-1, 8)
+            return " ".join("%x" % v for v in fields.u32_array_to_ints(a))
+
+        lam, expand = 4, 3
+        lines = ["%d %d %d %d %d %d" % (log_n, triples, circuit.usable_rows, mqc, lam, expand)]
+        lines += [dump(witness), dump(public), dump(circuit.selectors), dump(circuit.s_id), dump(circuit.s_sigma),
+                  dump(circuit.q_last), dump(circuit.q_blind), dump(circuit.lagrange_0)]
+        path = tmp_path / "placeholder.txt"
+        path.write_text("\n".join(lines) + "\n")
+        tr = FiatShamirSequential(0, b"placeholder-test")
+        res = P.placeholder_prove(ctx, circuit, 0, FriParams.with_max_step_one(log_n, lam, expand), witness, public, tr)
+        state = tr.state
+    finally:
+        ctx.close()
+    exe = _build()
+    r = subprocess.run([exe, "placeholder", str(path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:]
+    out = {l.split()[1]: l.split()[2:] for l in r.stdout.splitlines() if l.startswith("PLH ")}
+    assert out["fixed"][0] == res["commitments"][0].hex()
+    for k in (1, 2, 3):
+        assert out["root%d" % k][0] == res["commitments"][k].hex(), k
+    assert int(out["y"][0], 16) == res["challenge"]
+    assert [int(v) for v in out["chunks"]] == [res["quotient_chunks"], res["log_d"]]
+    z = res["eval_proof"]["z"]
+    for k in (0, 1, 2, 3):
+        got = [[int(v, 16) for v in part.split()] for part in " ".join(out["z%d" % k]).split("|")[1:]]
+        assert got == [list(v) for v in z[k]], k
+    assert out["fri"] == [rt.hex() for rt in res["eval_proof"]["fri"]["roots"]]
+    assert out["transcript"][0] == bytes(state).hex()
