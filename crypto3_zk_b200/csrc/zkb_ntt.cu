@@ -3,6 +3,7 @@
 // zkb_ntt_tables.cuh.  See include/zkb200.h for the reference call sites each entry point serves.
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include "zkb_internal.h"
 #include "zkb_ntt_plan.h"
 #include "zkb_ntt_tables.cuh"
@@ -95,11 +96,14 @@ static int ntt_tables(zkb_ctx *ctx, const NttPlan &pl, int inverse, const uint32
 
 template <class P>
 static int ntt_launch(zkb_ctx *ctx, const NttPassParams &q, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per DEVICE: one bit per device id (a process-wide flag left every device but the first
+    // without the opt-in shared-memory size - zkb_multi with four or more devices, found by the 8-GPU run of round 2)
+    static std::atomic<uint64_t> attr_set{0};
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         ZKB_CUDA_OK(ctx, cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)ntt_smem_bytes(ZKB_NTT_MAX_LOG_R)));
-        attr_set = true;
+        attr_set.fetch_or(bit, std::memory_order_release);
     }
     uint64_t tiles = ntt_pass_tiles(q);
     if (tiles == 0) return ZKB_OK;
