@@ -84,7 +84,7 @@ static void replay_pass(const NttPassParams &p) {
     for (uint64_t tile = 0; tile < tiles; tile++) {
         const NttTile t = ntt_tile(p, tile);
 #define H_ALL(stmt) for (uint32_t tid = 0; tid < nt; tid++) { stmt; }
-#define H_L H_ALL(ntt_phase_load<F>(p, t, smem.data(), tid, nt))
+#define H_L H_ALL(if (p.tw_in_smem) ntt_phase_stage_tw<F>(p, smem.data(), tid, nt); ntt_phase_load<F>(p, t, smem.data(), tid, nt))
 #define H_PM H_ALL(ntt_phase_premul<F>(p, t, smem.data(), tid, nt))
 #define H_R2(lh) H_ALL(ntt_phase_radix2<F>(p, smem.data(), lh, tid, nt))
 #define H_R4(lh) H_ALL(ntt_phase_radix4<F>(p, smem.data(), lh, tid, nt))
@@ -110,6 +110,7 @@ static int host_ntt(int log_n, int log_n_in, int inverse, const uint32_t *shift,
     std::vector<std::vector<F>> inter(ZKB_NTT_MAX_PASSES);
     NttTables tb = {};
     tb.tw = tw.data();
+    tb.tw_in_smem = 1;
     for (int i = 0; i + 1 < pl.n_passes; i++) {
         int lmp = pl.log_m(i), lm = pl.log_m(i + 1);
         F base = wN;

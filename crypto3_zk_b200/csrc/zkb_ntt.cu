@@ -2,6 +2,7 @@
 // Kernel bodies are in zkb_ntt_pass.cuh; the plan and table definitions in zkb_ntt_plan.h /
 // zkb_ntt_tables.cuh.  See include/zkb200.h for the reference call sites each entry point serves.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include "zkb_internal.h"
@@ -55,6 +56,10 @@ static int ntt_tables(zkb_ctx *ctx, const NttPlan &pl, int inverse, const uint32
     if (created) ZKB_TRY(fill_powtab<P>(ctx, ntt_omega<F, P>(ZKB_NTT_TW_LOG, inverse), F::one(), 0, 0,
                                         1ull << (ZKB_NTT_TW_LOG - 1), p, st));
     tb->tw = p;
+    {
+        const char *v = getenv("ZKB_NTT_TW_SMEM");      // A/B switch for profiles/; default on
+        tb->tw_in_smem = v && *v ? atoi(v) : 1;
+    }
     // inter-pass twiddles
     F ninv = ntt_n_inv<F>(log_n);
     for (int i = 0; i + 1 < pl.n_passes; i++) {

@@ -55,6 +55,7 @@ struct NttPassParams {
     const void *store_tab;        // optional: out[o] *= store_tab[o & store_mask]
     uint64_t store_mask;
     const void *tw;               // master twiddles w_{2^ZKB_NTT_TW_LOG}^j (direction specific)
+    int tw_in_smem;               // the tile's R/2 twiddles are staged in shared memory by the load phase
     // LDE: the outputs at multiples of 2^known_log are the input evaluations themselves (the coset of index 0 of the
     // larger domain is the smaller domain), out[poly][j 2^known_log] = known_src[poly][j].  Such outputs have
     // k_1 = 0 mod 2^known_log, so they are never computed: pass 1 does not store those rows, the middle passes skip
@@ -66,12 +67,19 @@ struct NttPassParams {
     uint64_t known_poly_stride;
 };
 
-// shared-memory layout: two planes (low/high 16 bytes of every element), [row][C+1] 16-byte slots,
-// second plane offset by 4 extra slots so the planes fall in different bank groups.
-ZKB_HD constexpr uint32_t ntt_plane_slots(int log_r) { return (1u << log_r) * (ZKB_NTT_C + 1) + 4; }
-ZKB_HD constexpr uint32_t ntt_smem_bytes(int log_r) { return 2u * ntt_plane_slots(log_r) * 16u; }
+// shared-memory layout: two planes (low/high 16 bytes of every element), [row][C] 16-byte slots with the column index
+// XOR-swizzled by the row (so that a quarter-warp hits eight distinct 16-byte bank groups whether its eight lanes walk
+// along a row - butterflies, column-contiguous copies - or down a column - row-contiguous copies of the last pass),
+// second plane offset by 4 extra slots so that the two halves of an element fall in complementary bank groups when a
+// quarter-warp copies four elements x two halves.  64 KB + 64 B per 256-row tile (the padded [row][C+1] layout of round 1
+// took 73 KB); after the planes: the tile's R/2 twiddles w_R^e as [e][2] slots (every quarter-warp reads one twiddle:
+// a broadcast), staged once per CTA instead of fetched from global memory in every phase.
+ZKB_HD constexpr uint32_t ntt_plane_slots(int log_r) { return (1u << log_r) * ZKB_NTT_C + 4; }
+ZKB_HD constexpr uint32_t ntt_tw_slots(int log_r) { return log_r >= 1 ? (1u << log_r) : 2u; }      // (R/2) x 2
+ZKB_HD constexpr uint32_t ntt_tw_base(int log_r) { return 2u * ntt_plane_slots(log_r); }
+ZKB_HD constexpr uint32_t ntt_smem_bytes(int log_r) { return (2u * ntt_plane_slots(log_r) + ntt_tw_slots(log_r)) * 16u; }
 ZKB_HD uint32_t ntt_slot(int log_r, int plane, uint32_t r, uint32_t c) {
-    return plane * ntt_plane_slots(log_r) + r * (ZKB_NTT_C + 1) + c;
+    return plane * ntt_plane_slots(log_r) + r * ZKB_NTT_C + (c ^ (r & (ZKB_NTT_C - 1)));
 }
 
 ZKB_HD uint32_t brev(uint32_t v, int bits) {
@@ -242,9 +250,28 @@ ZKB_HD void ntt_phase_premul(const NttPassParams &p, const NttTile &t, u128 *sme
 }
 
 // ------------------------------------------------------------------------------------ butterflies
+// stage the tile's twiddles w_R^e, e < R/2, into shared memory (one 16-byte unit per thread and step)
 template <class F>
-ZKB_HD F ntt_tw(const NttPassParams &p, uint32_t e, int log_size) {
-    // w_{2^log_size}^e from the master table
+ZKB_HD void ntt_phase_stage_tw(const NttPassParams &p, u128 *smem, uint32_t tid, uint32_t nthreads) {
+    const uint32_t units = ntt_tw_slots(p.log_r);
+    const u128 *tab = (const u128 *)p.tw;
+    u128 *dst = smem + ntt_tw_base(p.log_r);
+    for (uint32_t u = tid; u < units; u += nthreads) {
+        const uint32_t e = u >> 1;
+        dst[u] = tab[2 * ((uint64_t)e << (ZKB_NTT_TW_LOG - p.log_r)) + (u & 1)];
+    }
+}
+template <class F>
+ZKB_HD F ntt_tw(const NttPassParams &p, const u128 *smem, uint32_t e, int log_size) {
+    // w_{2^log_size}^e: from the staged copy (log_size = log_r always) or the master table
+    if (p.tw_in_smem) {
+        const u128 *t = smem + ntt_tw_base(p.log_r) + 2 * e;
+        u128 lo = t[0], hi = t[1];
+        F v;
+        v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+        v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+        return v;
+    }
     return ntt_ld_tab<F>(p.tw, (uint64_t)e << (ZKB_NTT_TW_LOG - log_size));
 }
 
@@ -266,7 +293,7 @@ ZKB_HD void ntt_phase_radix2(const NttPassParams &p, u128 *smem, int log_h, uint
         uint32_t j = g & (h - 1), blk = g >> log_h;
         uint32_t i = (blk << (log_h + 1)) + j;
         F a = ntt_ld_elem<F>(smem, p.log_r, i, c), b = ntt_ld_elem<F>(smem, p.log_r, i + h, c);
-        if (blk != 0) b = b * ntt_tw<F>(p, brev(blk, lvl) << log_h, p.log_r);
+        if (blk != 0) b = b * ntt_tw<F>(p, smem, brev(blk, lvl) << log_h, p.log_r);
         ntt_st_elem<F>(smem, p.log_r, i, c, a + b);
         ntt_st_elem<F>(smem, p.log_r, i + h, c, a - b);
     }
@@ -288,13 +315,13 @@ ZKB_HD void ntt_phase_radix4(const NttPassParams &p, u128 *smem, int log_h, uint
         F x1 = ntt_ld_elem<F>(smem, p.log_r, i + q, c), x3 = ntt_ld_elem<F>(smem, p.log_r, i + h + q, c);
         const uint32_t e0 = brev(blk, lvl) << log_q;    // beta q  (< R/4)
         if (blk != 0) {
-            F w = ntt_tw<F>(p, 2 * e0, p.log_r);
+            F w = ntt_tw<F>(p, smem, 2 * e0, p.log_r);
             x2 = x2 * w;
             x3 = x3 * w;
         }
         F y0 = x0 + x2, y2 = x0 - x2, y1 = x1 + x3, y3 = x1 - x3;
-        if (blk != 0) y1 = y1 * ntt_tw<F>(p, e0, p.log_r);
-        y3 = y3 * ntt_tw<F>(p, e0 + (R >> 2), p.log_r);
+        if (blk != 0) y1 = y1 * ntt_tw<F>(p, smem, e0, p.log_r);
+        y3 = y3 * ntt_tw<F>(p, smem, e0 + (R >> 2), p.log_r);
         ntt_st_elem<F>(smem, p.log_r, i, c, y0 + y1);
         ntt_st_elem<F>(smem, p.log_r, i + q, c, y0 - y1);
         ntt_st_elem<F>(smem, p.log_r, i + h, c, y2 + y3);
@@ -362,7 +389,7 @@ __global__ void __launch_bounds__(ZKB_NTT_THREADS, 3) ntt_pass_kernel(const NttP
     u128 *smem = reinterpret_cast<u128 *>(ntt_smem_raw);
     const NttTile t = ntt_tile(p, blockIdx.x);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-#define ZKB_L ntt_phase_load<F>(p, t, smem, tid, nt); __syncthreads()
+#define ZKB_L if (p.tw_in_smem) ntt_phase_stage_tw<F>(p, smem, tid, nt); ntt_phase_load<F>(p, t, smem, tid, nt); __syncthreads()
 #define ZKB_PM ntt_phase_premul<F>(p, t, smem, tid, nt); __syncthreads()
 #define ZKB_R2(lh) ntt_phase_radix2<F>(p, smem, lh, tid, nt); __syncthreads()
 #define ZKB_R4(lh) ntt_phase_radix4<F>(p, smem, lh, tid, nt); __syncthreads()

@@ -59,6 +59,7 @@ inline int ntt_zero_levels(uint64_t in_valid_elems, int log_row_stride, int log_
 // Pointers to the tables one transform needs (device pointers in the runtime, host in the replay).
 struct NttTables {
     const void *tw;                              // master in-tile twiddles for this direction
+    int tw_in_smem;                              // stage every tile's twiddles in shared memory
     const void *inter[ZKB_NTT_MAX_PASSES];       // inter[i] = T_{i+1}, i < n_passes-1
     const void *load_tab;  uint64_t load_mask;   // coset pre-scale (or null)
     const void *store_tab; uint64_t store_mask;  // post-scale of the last pass (or null)
@@ -86,6 +87,7 @@ inline std::vector<NttPassParams> ntt_build_passes(const NttPlan &pl, const NttT
         q.n_passes = p;
         for (int j = 0; j < ZKB_NTT_MAX_PASSES; j++) q.lr[j] = pl.lr[j];
         q.tw = tb.tw;
+        q.tw_in_smem = tb.tw_in_smem;
         q.load_tab = nullptr; q.load_mask = 0;
         q.store_tab = nullptr; q.store_mask = 0;
         q.in_valid_elems = N;
