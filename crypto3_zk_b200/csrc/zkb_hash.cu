@@ -13,6 +13,7 @@
 // consecutive leaves, so every load instruction of a warp covers one contiguous 1 KiB run.
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include "zkb_internal.h"
 
 using namespace zkb;
@@ -537,19 +538,55 @@ int zkb_lpc_commit(zkb_ctx *ctx, int field, int hash, int log_n_in, int log_n_ou
     ZKB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     size_t ib = ((size_t)batch << log_n_in) * 32, ob = ((size_t)batch << log_n_out) * 32;
-    const void *din = polys;
-    if (mem != ZKB_MEM_DEVICE) {
-        void *p;
-        ZKB_TRY(ctx_scratch(ctx, "io_in", ib, &p));
-        ZKB_CUDA_OK(ctx, cudaMemcpyAsync(p, polys, ib, cudaMemcpyHostToDevice, st));
-        din = p;
-    }
     // the extended evaluations are scratch: the reference does not retain them either
     // (precommit takes the container by value, basic_fri.hpp:445; lpc keeps only the tree, lpc.hpp:103)
     void *ext;
     ZKB_TRY(ctx_scratch(ctx, "lpc_ext", ob, &ext));
-    ZKB_TRY(lde_device(ctx, field, log_n_in, log_n_out, batch, din, ext, st));
-    return merkle_build(ctx, hash, log_n_out, fri_step, batch, ext, root_out, tree_out, st);
+    if (mem == ZKB_MEM_DEVICE) {
+        ZKB_TRY(lde_device(ctx, field, log_n_in, log_n_out, batch, polys, ext, st));
+        return merkle_build(ctx, hash, log_n_out, fri_step, batch, ext, root_out, tree_out, st);
+    }
+    // host polynomials: uploaded in chunks on a copy stream, every chunk extended as soon as it has arrived (the upload of
+    // config #2 is 2 GiB = 38 ms at PCIe rate, a quarter of the commit)
+    void *p;
+    ZKB_TRY(ctx_scratch(ctx, "io_in", ib, &p));
+    if (!ctx->copy_in) {
+        ZKB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        ZKB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            ZKB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            ZKB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+            ZKB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t in_poly = (size_t)32 << log_n_in, out_poly = (size_t)32 << log_n_out;
+    uint32_t chunk = (uint32_t)((256ull << 20) / in_poly);
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    const uint32_t nchunks = (batch + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> ev(nchunks, nullptr);
+    int status = ZKB_OK;
+    cudaError_t e = cudaEventRecord(ctx->ev_comp[0], st);            // earlier work on st may still read io_in
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[0], 0);
+    for (uint32_t k = 0; k < nchunks && e == cudaSuccess; k++) {
+        const uint32_t b0 = k * chunk, nb = batch - b0 < chunk ? batch - b0 : chunk;
+        e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char *)p + b0 * in_poly, (const char *)polys + b0 * in_poly, nb * in_poly, cudaMemcpyHostToDevice, ctx->copy_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[k], ctx->copy_in);
+    }
+    for (uint32_t k = 0; k < nchunks && e == cudaSuccess && status == ZKB_OK; k++) {
+        const uint32_t b0 = k * chunk, nb = batch - b0 < chunk ? batch - b0 : chunk;
+        e = cudaStreamWaitEvent(st, ev[k], 0);
+        if (e == cudaSuccess)
+            status = lde_device(ctx, field, log_n_in, log_n_out, nb, (const char *)p + b0 * in_poly, (char *)ext + b0 * out_poly, st);
+    }
+    if (e == cudaSuccess && status == ZKB_OK) status = merkle_build(ctx, hash, log_n_out, fri_step, batch, ext, root_out, tree_out, st);
+    cudaStreamSynchronize(ctx->copy_in);
+    for (auto v : ev)
+        if (v) cudaEventDestroy(v);
+    if (e != cudaSuccess) return ctx_fail(ctx, ZKB_ERR_CUDA, std::string("zkb_lpc_commit: ") + cudaGetErrorString(e));
+    return status;
 }
 
 int zkb_pow_grind(zkb_ctx *ctx, int hash, const uint8_t *state, uint32_t start, uint32_t mask, uint32_t *nonce_out,
