@@ -79,14 +79,14 @@ def degree(expr):
     return a + b if k == "mul" else max(a, b)
 
 
-def compile_expr(expr, p):
-    """nested tuples -> (postfix program for zkb_expr_eval, constants)"""
+def compile_expr(expr, p, column_map=None):
+    """nested tuples -> (postfix program for zkb_expr_eval, constants); column_map renumbers the columns"""
     prog, consts, index = [], [], {}
 
     def visit(e):
         k = e[0]
         if k == "col":
-            prog.append((capi.EXPR_PUSH_COL, e[1], e[2]))
+            prog.append((capi.EXPR_PUSH_COL, e[1] if column_map is None else column_map[e[1]], e[2]))
         elif k == "const":
             v = e[1] % p
             if v not in index:
@@ -104,25 +104,47 @@ def compile_expr(expr, p):
     return prog, consts
 
 
+def used_columns(exprs):
+    """sorted column indices the expressions read"""
+    cols = set()
+
+    def visit(e):
+        if e[0] == "col":
+            cols.add(e[1])
+        elif e[0] != "const":
+            for sub_e in e[1:]:
+                visit(sub_e)
+    for e in exprs:
+        visit(e)
+    return sorted(cols)
+
+
 def evaluate_on_extended_domain(ctx, field, columns, exprs, log_n, log_d, coefficients=None):
     """sum of the expressions as polynomial_dfs on the subgroup of size 2^(log_n + log_d): device tensor [2^(log_n+log_d), 8].
     columns: device tensor [ncols, 2^log_n, 8], evaluation form on the basic domain.  Coset by coset: one batched coset
-    transform of all columns, one zkb_expr_eval launch per expression, results interleaved with stride 2^log_d."""
+    transform of the columns the expressions read, one zkb_expr_eval launch per expression, results interleaved with
+    stride 2^log_d."""
     import torch
     F = FIELD_BY_NAME[field] if isinstance(field, str) else field
     n, D = 1 << log_n, 1 << log_d
+    used = used_columns(exprs)
+    if len(used) < columns.shape[0]:
+        idx = torch.tensor(used, device=columns.device)
+        columns = columns.index_select(0, idx)
+        if coefficients is not None:
+            coefficients = coefficients.index_select(0, idx)
+    cmap = {c: i for i, c in enumerate(used)}
     if coefficients is None:
-        coefficients = ctx.ntt(F.name, columns.clone(), log_n, inverse=True)
+        coefficients = ctx.ntt(F.name, columns, log_n, inverse=True, out=torch.empty_like(columns))
     out = torch.empty((n * D, 8), dtype=torch.int32, device=columns.device)
-    programs = [compile_expr(e, F.p) for e in exprs]
+    programs = [compile_expr(e, F.p, cmap) for e in exprs]
     w_ext = omega(F, log_n + log_d)
     work = torch.empty_like(coefficients)
     for j in range(D):
         if j == 0:
             cos = columns                      # coset 0 is the basic domain itself
         else:
-            work.copy_(coefficients)
-            cos = ctx.ntt(F.name, work, log_n, coset_shift=pow(w_ext, j, F.p))
+            cos = ctx.ntt(F.name, coefficients, log_n, coset_shift=pow(w_ext, j, F.p), out=work)
         for k, (prog, consts) in enumerate(programs):
             ctx.expr_eval(F.name, cos, prog, consts, out, out_stride=D, out_offset=j, accumulate=k > 0)
     return out
@@ -148,8 +170,31 @@ class PlaceholderCircuit:
         self.usable_rows = usable_rows
         self.max_gates_degree = max([degree(c) for _, cs in gates for c in cs] + [0])
         self.max_quotient_chunks = max_quotient_chunks
+        self._identity_ratios = None
         if max_quotient_chunks and max_quotient_chunks <= self.max_gates_degree:
             raise ValueError("max_quotient_chunks must exceed the gates' degree (preprocessor.hpp:559)")
+
+    def identity_ratios(self, ctx):
+        """S_id[i] = ratio_i * S_id[0] as polynomials when the identity polynomials are the preprocessor's
+        (S_id[i][j] = delta^i omega^j, preprocessor.hpp:418-436): then the expressions read ONE identity column and the
+        extended domain needs one transform for all of them.  Returns [ratio_i] (checked on the device once per
+        circuit) or None when the columns are not of that form."""
+        if self._identity_ratios is None:
+            import numpy as np
+            import torch
+            p, npc = self.F.p, len(self.permuted_columns)
+            first = [int.from_bytes(self.s_id[i, 0].cpu().numpy().view(np.uint32).tobytes(), "little") for i in range(npc)]
+            ok = npc > 0 and first[0] % p != 0
+            ratios = []
+            if ok:
+                inv0 = pow(first[0], p - 2, p)
+                ratios = [v * inv0 % p for v in first]
+                for i in range(1, npc):
+                    if not torch.equal(ctx.poly_lincomb(self.F.name, self.s_id[0], self.n, [ratios[i]]), self.s_id[i]):
+                        ok = False
+                        break
+            self._identity_ratios = ratios if ok else False
+        return self._identity_ratios or None
 
     @property
     def table_width(self):
@@ -258,7 +303,11 @@ def placeholder_prove(ctx, circuit, hash_id, fri, witness, public_input, transcr
         cols = base_cols.index_select(0, torch.tensor(circuit.permuted_columns, device=dev))
         v_p = ctx.permutation_grand_product(F.name, cols, circuit.s_id, circuit.s_sigma, beta, gamma)
         perm_polys.append(v_p)
-        g_f = [add(add(mul(const(beta), col(c_sid + i)), const(gamma)), col(circuit.permuted_columns[i])) for i in range(npc)]
+        ratios = circuit.identity_ratios(ctx)
+        if ratios is None:
+            g_f = [add(add(mul(const(beta), col(c_sid + i)), const(gamma)), col(circuit.permuted_columns[i])) for i in range(npc)]
+        else:       # beta S_id[i] = (beta delta^i) S_id[0]: one identity column on the extended domain instead of npc
+            g_f = [add(add(mul(const(beta * ratios[i] % p), col(c_sid)), const(gamma)), col(circuit.permuted_columns[i])) for i in range(npc)]
         h_f = [add(add(mul(const(beta), col(c_ssg + i)), const(gamma)), col(circuit.permuted_columns[i])) for i in range(npc)]
         group = npc if circuit.max_quotient_chunks == 0 else circuit.max_quotient_chunks - 1
         gs = [product(g_f[i:i + group]) for i in range(0, npc, group)]
