@@ -66,6 +66,16 @@ def total(terms):
     return acc
 
 
+def shift_expr(expr, r):
+    """the expression with every column read r rows further (math::polynomial_shift of the polynomial it denotes)"""
+    k = expr[0]
+    if k == "col":
+        return ("col", expr[1], expr[2] + r)
+    if k == "const":
+        return expr
+    return (k,) + tuple(shift_expr(e, r) for e in expr[1:])
+
+
 def degree(expr):
     """degree in units of (n - 1): every column counts 1 (expression_max_degree_visitor, gates_argument.hpp:161)"""
     k = expr[0]
@@ -158,7 +168,8 @@ class PlaceholderCircuit:
     parts of max_quotient_chunks - 1 columns (permutation_partitions_num, preprocessor.hpp:78-87)."""
 
     def __init__(self, field, log_n, n_witness, n_public, n_constant, n_selector, gates, permuted_columns, s_id, s_sigma,
-                 q_last, q_blind, lagrange_0, constants, selectors, usable_rows, max_quotient_chunks=0):
+                 q_last, q_blind, lagrange_0, constants, selectors, usable_rows, max_quotient_chunks=0, lookup_tables=None,
+                 lookup_gates=None):
         self.F = FIELD_BY_NAME[field] if isinstance(field, str) else field
         self.log_n, self.n = log_n, 1 << log_n
         self.n_witness, self.n_public, self.n_constant, self.n_selector = n_witness, n_public, n_constant, n_selector
@@ -170,6 +181,10 @@ class PlaceholderCircuit:
         self.usable_rows = usable_rows
         self.max_gates_degree = max([degree(c) for _, cs in gates for c in cs] + [0])
         self.max_quotient_chunks = max_quotient_chunks
+        # lookup_tables: [(tag selector index, [option: [constant column index, ..], ..]), ..]  (plonk_lookup_table)
+        # lookup_gates:  [(tag selector index, [(table id, 1-based, [input expr, ..]), ..]), ..] (plonk_lookup_gate)
+        self.lookup_tables = list(lookup_tables or [])
+        self.lookup_gates = list(lookup_gates or [])
         self._identity_ratios = None
         if max_quotient_chunks and max_quotient_chunks <= self.max_gates_degree:
             raise ValueError("max_quotient_chunks must exceed the gates' degree (preprocessor.hpp:559)")
@@ -210,6 +225,77 @@ class PlaceholderCircuit:
     def selector_column(self, k):
         return self.n_witness + self.n_public + self.n_constant + k
 
+    def constant_column(self, k):
+        return self.n_witness + self.n_public + k
+
+    # ---- lookup argument (lookup_argument.hpp:411-486, constraint_system.hpp:165-300)
+    def lookup_value_exprs(self, theta, mask):
+        """prepare_lookup_value: per table and option  mask * tag * (table id + sum_i theta^(i+1) constant_i)"""
+        out = []
+        for t_id, (tag, options) in enumerate(self.lookup_tables):
+            tag_c = col(self.selector_column(tag))
+            for option in options:
+                v = mul(const(t_id + 1), tag_c)
+                acc = theta
+                for c in option:
+                    v = add(v, mul(mul(const(acc), tag_c), col(self.constant_column(c))))
+                    acc = acc * theta % self.F.p
+                out.append(mul(v, mask))
+        return out
+
+    def lookup_input_exprs(self, theta):
+        """prepare_lookup_input: per lookup constraint  selector * table id + sum_k theta^(k+1) selector * input_k"""
+        out = []
+        for tag, constraints in self.lookup_gates:
+            sel = col(self.selector_column(tag))
+            for table_id, inputs in constraints:
+                l = mul(sel, const(table_id))
+                acc = theta
+                for e in inputs:
+                    l = add(l, mul(mul(const(acc), sel), e))
+                    acc = acc * theta % self.F.p
+                out.append(l)
+        return out
+
+    def lookup_poly_degree_bound(self):
+        d = 0
+        if self.lookup_gates:
+            for _, constraints in self.lookup_gates:
+                for _, inputs in constraints:
+                    d += max([degree(e) for e in inputs] + [0]) + 1
+            for _, options in self.lookup_tables:
+                d += 3 * len(options)
+        return d
+
+    def lookup_parts(self):
+        """plonk_constraint_system::lookup_parts (constraint_system.hpp:256-300): how many sorted columns (= g / h factors,
+        inputs first, then table options) go into every part of the lookup product"""
+        n_inputs = sum(len(cs) for _, cs in self.lookup_gates)
+        n_options = sum(len(o) for _, o in self.lookup_tables)
+        mqc = self.max_quotient_chunks
+        if mqc == 0:
+            return [n_inputs + n_options]
+        parts, chunk, part = [], 0, 0
+        for _, constraints in self.lookup_gates:
+            for _, inputs in constraints:
+                d = max([degree(e) for e in inputs] + [0])
+                if chunk + d + 1 >= mqc:
+                    parts.append(part)
+                    chunk, part = 0, 0
+                chunk += d + 1
+                part += 1
+        for _, options in self.lookup_tables:
+            for _ in options:
+                if chunk + 3 >= mqc:
+                    parts.append(part)
+                    chunk, part = 0, 0
+                chunk += 3
+                part += 1
+        parts.append(part)
+        if 0 in parts:
+            raise ValueError("max_quotient_chunks is too small for the lookup constraints (an empty lookup part)")
+        return parts
+
     def columns_rotations(self):
         """per table column the sorted rotations the gates use, 0 always included (preprocessor.hpp:363-383, a std::set)"""
         rots = [{0} for _ in range(self.table_width)]
@@ -223,6 +309,16 @@ class PlaceholderCircuit:
         for _, constraints in self.gates:
             for c in constraints:
                 visit(c)
+        if self.lookup_gates:
+            for _, constraints in self.lookup_gates:
+                for _, inputs in constraints:
+                    for e in inputs:
+                        visit(e)
+            for tag, options in self.lookup_tables:          # tag and option columns are also read one row further
+                rots[self.selector_column(tag)].add(1)
+                for option in options:
+                    for c in option:
+                        rots[self.constant_column(c)].add(1)
         return [sorted(r) for r in rots]
 
     def fixed_batch(self):
@@ -236,9 +332,10 @@ class PlaceholderCircuit:
         return torch.cat(parts, dim=0)
 
     def quotient_chunks(self):
-        """split_polynomial_size of prover.hpp:227-246 (no lookups)"""
+        """split_polynomial_size of prover.hpp:227-246"""
         n = self.n
-        size = max((len(self.permuted_columns) + 2) * (n - 1), (self.max_gates_degree + 1) * (n - 1))
+        size = max((len(self.permuted_columns) + 2) * (n - 1), (self.lookup_poly_degree_bound() + 1) * (n - 1),
+                   (self.max_gates_degree + 1) * (n - 1))
         size = (size + n - 1) // n
         if self.max_quotient_chunks and size > self.max_quotient_chunks:
             size = self.max_quotient_chunks
@@ -284,24 +381,73 @@ def placeholder_prove(ctx, circuit, hash_id, fri, witness, public_input, transcr
         table.append(circuit.selectors)
     tw = circuit.table_width
     npc = len(circuit.permuted_columns)
-    # columns the expressions see: the table, then S_id, S_sigma, q_last, q_blind, L_0, V_P and the permutation parts
+    usable = circuit.usable_rows
+    # columns the expressions see: the table, then S_id, S_sigma, q_last, q_blind, L_0 (base_cols), then whatever the
+    # arguments produce (V_P and its parts, V_L and its parts, the sorted lookup columns), numbered as they appear
     c_sid, c_ssg = tw, tw + npc
-    c_qlast, c_qblind, c_l0, c_vp = tw + 2 * npc, tw + 2 * npc + 1, tw + 2 * npc + 2, tw + 2 * npc + 3
+    c_qlast, c_qblind, c_l0 = tw + 2 * npc, tw + 2 * npc + 1, tw + 2 * npc + 2
     base_cols = torch.cat(table + [circuit.s_id, circuit.s_sigma, circuit.q_last.unsqueeze(0), circuit.q_blind.unsqueeze(0),
                                    circuit.lagrange_0.unsqueeze(0)], dim=0)
+    n_base = base_cols.shape[0]
+    extra, col_src = [], {}
+
+    def new_col(t, src):
+        """src = (batch, polynomial index in the batch): where a verifier finds this column's opened values"""
+        extra.append(t)
+        col_src[n_base + len(extra) - 1] = src
+        return n_base + len(extra) - 1
+
+    def column(i):
+        return base_cols[i] if i < n_base else extra[i - n_base]
+
+    def eval_basic(expr, out=None):
+        """the expression on the basic domain (its values there are the reduce_dfs_polynomial_domain of upstream's product)"""
+        used = used_columns([expr])
+        cols = torch.stack([column(i) for i in used]) if used else torch.zeros((1, n, 8), dtype=torch.int32, device=dev)
+        prog, consts = compile_expr(expr, p, {c: i for i, c in enumerate(used)})
+        if out is None:
+            out = torch.empty((n, 8), dtype=torch.int32, device=dev)
+        return ctx.expr_eval(F.name, cols, prog, consts, out)
+
+    gv = torch.empty((n, 8), dtype=torch.int32, device=dev)
+    hv = torch.empty((n, 8), dtype=torch.int32, device=dev)
+
+    def running_products(first_t, first_c, first_index, gs, hs, alphas_, shifted):
+        """the part polynomials of a grand product cut into len(gs) parts (permutation_argument.hpp:194-215,
+        lookup_argument.hpp:262-289): current = previous * g_i / h_i on the usable rows, rows beyond keep the grand
+        product's values; returns (part tensors, the bracket sum alpha_i (prev g_i - cur h_i) + (prev g_last - shifted h_last))"""
+        prev_t, prev_c, terms, made = first_t, first_c, [], []
+        for i in range(len(gs) - 1):
+            eval_basic(gs[i], gv)
+            eval_basic(hs[i], hv)
+            ctx.vec(F.name, capi.VEC_MUL, prev_t, gv, out=gv)
+            ctx.batch_inverse(F.name, hv, out=hv)
+            ctx.vec(F.name, capi.VEC_MUL, gv, hv, out=gv)
+            cur = first_t.clone()
+            cur[:usable] = gv[:usable]
+            cur_c = new_col(cur, (PERMUTATION_BATCH, first_index + 1 + i))
+            made.append(cur)
+            terms.append(mul(const(alphas_[i]), sub(mul(col(prev_c), gs[i]), mul(col(cur_c), hs[i]))))
+            prev_t, prev_c = cur, cur_c
+        terms.append(sub(mul(col(prev_c), gs[-1]), mul(shifted, hs[-1])))
+        return made, total(terms)
+
     # 2. witness and public-input columns
     scheme.append_to_batch(VARIABLE_VALUES_BATCH, base_cols[:circuit.n_witness + circuit.n_public])
     commitments[VARIABLE_VALUES_BATCH] = scheme.commit(VARIABLE_VALUES_BATCH)
     transcript(commitments[VARIABLE_VALUES_BATCH])
     lap("commit_variable_values")
-    # 4. permutation argument (permutation_argument.hpp:95-215)
     f_exprs = {}
     one = const(1)
+    mask = sub(sub(one, col(c_qlast)), col(c_qblind))
+    neg_mask = sub(add(col(c_qlast), col(c_qblind)), one)
     perm_polys = []
+    # 4. permutation argument (permutation_argument.hpp:95-215)
     if npc:
         beta, gamma = transcript.challenge(p), transcript.challenge(p)
         cols = base_cols.index_select(0, torch.tensor(circuit.permuted_columns, device=dev))
         v_p = ctx.permutation_grand_product(F.name, cols, circuit.s_id, circuit.s_sigma, beta, gamma)
+        c_vp = new_col(v_p, (PERMUTATION_BATCH, 0))
         perm_polys.append(v_p)
         ratios = circuit.identity_ratios(ctx)
         if ratios is None:
@@ -317,47 +463,74 @@ def placeholder_prove(ctx, circuit, hash_id, fri, witness, public_input, transcr
         perm_alphas = [transcript.challenge(p) for _ in range(parts - 1)]
         f_exprs[0] = mul(sub(one, col(c_vp)), col(c_l0))
         if parts == 1:
-            f_exprs[1] = mul(sub(sub(one, col(c_qlast)), col(c_qblind)), sub(mul(col(c_vp, 1), hs[0]), mul(col(c_vp), gs[0])))
+            f_exprs[1] = mul(mask, sub(mul(col(c_vp, 1), hs[0]), mul(col(c_vp), gs[0])))
         else:
-            # the running product is committed after every part: current = previous * g_i / h_i on the usable rows
-            # (:194-210), all on the basic domain - two expression launches, one batched inversion, two products per part
-            prev_t, prev_c, terms = v_p, c_vp, []
-            usable = circuit.usable_rows
-            gv = torch.empty((n, 8), dtype=torch.int32, device=dev)
-            hv = torch.empty((n, 8), dtype=torch.int32, device=dev)
-            for i in range(parts - 1):
-                prog, consts = compile_expr(gs[i], p)
-                ctx.expr_eval(F.name, base_cols, prog, consts, gv)
-                prog, consts = compile_expr(hs[i], p)
-                ctx.expr_eval(F.name, base_cols, prog, consts, hv)
-                ctx.vec(F.name, capi.VEC_MUL, prev_t, gv, out=gv)
-                ctx.batch_inverse(F.name, hv, out=hv)
-                ctx.vec(F.name, capi.VEC_MUL, gv, hv, out=gv)
-                cur = v_p.clone()
-                cur[:usable] = gv[:usable]
-                perm_polys.append(cur)
-                cur_c = c_vp + 1 + i
-                terms.append(mul(const(perm_alphas[i]), sub(mul(col(prev_c), gs[i]), mul(col(cur_c), hs[i]))))
-                prev_t, prev_c = cur, cur_c
-            terms.append(sub(mul(col(prev_c), gs[-1]), mul(col(c_vp, 1), hs[-1])))
-            f_exprs[1] = mul(total(terms), sub(add(col(c_qlast), col(c_qblind)), one))
+            made, bracket = running_products(v_p, c_vp, 0, gs, hs, perm_alphas, col(c_vp, 1))
+            perm_polys += made
+            f_exprs[1] = mul(bracket, neg_mask)
         f_exprs[2] = mul(col(c_qlast), sub(mul(col(c_vp), col(c_vp)), col(c_vp)))
         lap("permutation_argument")
+    # 5. lookup argument (lookup_argument.hpp:153-325)
+    lookup = circuit.lookup_gates and circuit.lookup_tables
+    v_l_index = None
+    sorted_cols = []
+    if lookup:
+        theta = transcript.challenge(p)
+        value_exprs, input_exprs = circuit.lookup_value_exprs(theta, mask), circuit.lookup_input_exprs(theta)
+        values = torch.stack([eval_basic(e) for e in value_exprs])          # reduced to the basic domain (:176-186)
+        inputs = torch.stack([eval_basic(e) for e in input_exprs])
+        srt = ctx.lookup_sort(F.name, inputs, values, usable)
+        scheme.append_to_batch(LOOKUP_BATCH, srt)
+        commitments[LOOKUP_BATCH] = scheme.commit(LOOKUP_BATCH)
+        transcript(commitments[LOOKUP_BATCH])
+        sorted_cols = [new_col(srt[i], (LOOKUP_BATCH, i)) for i in range(srt.shape[0])]
+        lbeta, lgamma = transcript.challenge(p), transcript.challenge(p)
+        part_sizes = circuit.lookup_parts()
+        lookup_alphas = [transcript.challenge(p) for _ in range(len(part_sizes) - 1)]
+        v_l = ctx.lookup_grand_product(F.name, inputs, values, srt, lbeta, lgamma, usable)
+        v_l_index = len(perm_polys)
+        c_vl = new_col(v_l, (PERMUTATION_BATCH, v_l_index))
+        perm_polys.append(v_l)
+        one_beta, part1 = (1 + lbeta) % p, (1 + lbeta) * lgamma % p
+        g_f = [mul(const(one_beta), add(const(lgamma), e)) for e in input_exprs]
+        g_f += [add(add(const(part1), e), mul(const(lbeta), shift_expr(e, 1))) for e in value_exprs]
+        h_f = [add(add(const(part1), col(c)), mul(const(lbeta), col(c, 1))) for c in sorted_cols]
+        assert sum(part_sizes) == len(g_f) == len(h_f)
+        gs, hs, o = [], [], 0
+        for sz in part_sizes:
+            gs.append(product(g_f[o:o + sz]))
+            hs.append(product(h_f[o:o + sz]))
+            o += sz
+        f_exprs[3] = mul(col(c_l0), sub(one, col(c_vl)))
+        f_exprs[4] = mul(col(c_qlast), sub(mul(col(c_vl), col(c_vl)), col(c_vl)))
+        if len(part_sizes) == 1:
+            f_exprs[5] = mul(sub(mul(gs[0], col(c_vl)), mul(hs[0], col(c_vl, 1))), neg_mask)
+        else:
+            made, bracket = running_products(v_l, c_vl, v_l_index, gs, hs, lookup_alphas, col(c_vl, 1))
+            perm_polys += made
+            f_exprs[5] = mul(bracket, neg_mask)
+        terms = []
+        for i in range(len(sorted_cols) - 1):          # sorted[i+1](X) = sorted[i](omega^usable X) at the first row (:291-299)
+            a_i = transcript.challenge(p)
+            terms.append(mul(const(a_i), sub(col(sorted_cols[i + 1]), col(sorted_cols[i], usable))))
+        if terms:
+            f_exprs[6] = mul(total(terms), col(c_l0))
+        lap("lookup_argument")
+    if perm_polys:
         scheme.append_to_batch(PERMUTATION_BATCH, torch.stack(perm_polys))
         commitments[PERMUTATION_BATCH] = scheme.commit(PERMUTATION_BATCH)
         transcript(commitments[PERMUTATION_BATCH])
         lap("commit_permutation")
     # 6. circuit satisfiability (gates_argument.hpp:133-217)
     if circuit.gates:
-        theta = transcript.challenge(p)
+        theta_g = transcript.challenge(p)
         theta_acc, terms = 1, []
         for sel, constraints in circuit.gates:
             inner = []
             for c in constraints:
                 inner.append(mul(c, const(theta_acc)))
-                theta_acc = theta_acc * theta % p
+                theta_acc = theta_acc * theta_g % p
             terms.append(mul(total(inner), col(circuit.selector_column(sel))))
-        mask = sub(sub(one, col(c_qlast)), col(c_qblind))
         f_exprs[7] = mul(total(terms), mask)
     # 7. quotient: alphas, F consolidated, division by Z, split, commit (prover.hpp:220-283)
     alphas = [transcript.challenge(p) for _ in range(F_PARTS)]
@@ -366,10 +539,7 @@ def placeholder_prove(ctx, circuit, hash_id, fri, witness, public_input, transcr
     log_d = 1
     while (1 << log_d) * n <= deg * (n - 1):      # the extended domain must hold degree deg (n - 1)
         log_d += 1
-    if perm_polys:
-        all_cols = torch.cat([base_cols, torch.stack(perm_polys)], dim=0)
-    else:
-        all_cols = torch.cat([base_cols, torch.zeros((1, n, 8), dtype=torch.int32, device=dev)], dim=0)
+    all_cols = torch.cat([base_cols] + ([torch.stack(extra)] if extra else [torch.zeros((1, n, 8), dtype=torch.int32, device=dev)]), dim=0)
     f_dfs = evaluate_on_extended_domain(ctx, F, all_cols, parts_exprs, log_n, log_d)
     lap("argument_polynomials_on_extended_domain")
     f_coeff = ctx.ntt(F.name, (f_dfs.clone() if keep is not None else f_dfs).unsqueeze(0), log_n + log_d, inverse=True)[0]   # in place
@@ -391,9 +561,15 @@ def placeholder_prove(ctx, circuit, hash_id, fri, witness, public_input, transcr
     for i in range(nvar):
         for r in rots[i]:
             scheme.append_eval_point(VARIABLE_VALUES_BATCH, rotated(r), poly=i)
-    if npc:
+    if perm_polys:
         scheme.append_eval_point(PERMUTATION_BATCH, y)
-        scheme.append_eval_point(PERMUTATION_BATCH, rotated(1), poly=0)
+        if npc:
+            scheme.append_eval_point(PERMUTATION_BATCH, rotated(1), poly=0)
+        if lookup:
+            scheme.append_eval_point(PERMUTATION_BATCH, rotated(1), poly=v_l_index)
+            scheme.append_eval_point(LOOKUP_BATCH, y)
+            scheme.append_eval_point(LOOKUP_BATCH, rotated(1))
+            scheme.append_eval_point(LOOKUP_BATCH, rotated(usable))
     scheme.append_eval_point(QUOTIENT_BATCH, y)
     if scheme.has_batch(FIXED_VALUES_BATCH):
         start = 2 * npc + 2
@@ -405,8 +581,9 @@ def placeholder_prove(ctx, circuit, hash_id, fri, witness, public_input, transcr
             for r in rots[nvar + ind]:
                 scheme.append_eval_point(FIXED_VALUES_BATCH, rotated(r), poly=start + ind)
     if keep is not None:
-        keep.update(v_p=perm_polys[0] if perm_polys else None, perm_polys=perm_polys, f_dfs=f_dfs, f_coeff=f_coeff, t_chunks=t_chunks,
-                    alphas=alphas, log_d=log_d, f_exprs=f_exprs, all_cols=all_cols)
+        keep.update(v_p=perm_polys[0] if npc else None, perm_polys=perm_polys, f_dfs=f_dfs, f_coeff=f_coeff, t_chunks=t_chunks,
+                    alphas=alphas, log_d=log_d, f_exprs=f_exprs, all_cols=all_cols, n_base=n_base, sorted_cols=sorted_cols,
+                    v_l_index=v_l_index, column_source=dict(col_src))
     eval_proof = scheme.proof_eval(transcript, query=query)
     lap("proof_eval")
     return {"commitments": commitments, "challenge": y, "eval_proof": eval_proof, "quotient_chunks": nchunks, "log_d": log_d,

@@ -137,7 +137,7 @@ def _rand_column(torch, shape, seed, device):
 
 
 def placeholder_chain_circuit(ctx, field, log_n, triples=1, usable_rows=None, seed=1, device="cuda", rotation_gate=True,
-                              max_quotient_chunks=0):
+                              max_quotient_chunks=0, lookup=False):
     """A satisfiable synthetic Placeholder circuit with its assignment, all columns built on the device.
 
     Witness columns (a_k, b_k, c_k) for k < triples, one public-input column, one selector.  On every usable row the gate
@@ -145,7 +145,9 @@ def placeholder_chain_circuit(ctx, field, log_n, triples=1, usable_rows=None, se
     constraints a_k[j+1] = c_k[j] tie the same cells through the permutation argument, and public[0] = a_0[0].  Rows from
     `usable_rows` on hold random blinding values (q_last at usable_rows, q_blind after it: preprocessor.hpp:463-476).
     Identity / sigma polynomials as preprocessor.hpp:418-460 builds them (S_id[i][j] = delta^i omega^j, delta = the
-    multiplicative generator).  Returns (PlaceholderCircuit, witness [3*triples, n, 8], public_input [1, n, 8])."""
+    multiplicative generator).  With `lookup`: two more witness columns (u, v = u^2), a two-column lookup table
+    (t, t^2), t = 1 .. K, in two constant columns with its tag selector, and a lookup gate (u, v) in table 1 on every
+    usable row.  Returns (PlaceholderCircuit, witness [count, n, 8], public_input [1, n, 8])."""
     import torch
     from . import capi
     from .fields import omega
@@ -154,7 +156,7 @@ def placeholder_chain_circuit(ctx, field, log_n, triples=1, usable_rows=None, se
     n = 1 << log_n
     usable = n - 4 if usable_rows is None else usable_rows
     assert 2 <= usable < n
-    nw = 3 * triples
+    nw = 3 * triples + (2 if lookup else 0)
     witness = _rand_column(torch, (nw, n, 8), seed, device)
     for k in range(triples):
         b = witness[3 * k + 1]
@@ -166,10 +168,31 @@ def placeholder_chain_circuit(ctx, field, log_n, triples=1, usable_rows=None, se
     public = torch.zeros((1, n, 8), dtype=torch.int32, device=device)
     public[0, 0] = witness[0, 0]
     # selectors
-    selector = torch.zeros((2 if rotation_gate else 1, n, 8), dtype=torch.int32, device=device)
+    n_gate_sel = 2 if rotation_gate else 1
+    selector = torch.zeros((n_gate_sel + (2 if lookup else 0), n, 8), dtype=torch.int32, device=device)
     selector[0, :usable, 0] = 1
     if rotation_gate:
         selector[1, :usable - 1, 0] = 1
+    constants, lookup_tables, lookup_gates = None, None, None
+    if lookup:
+        K = max(2, min(usable // 2 - 1, 1 << 15))
+        t = torch.arange(1, K + 1, dtype=torch.int32, device=device)
+        constants = torch.zeros((2, n, 8), dtype=torch.int32, device=device)
+        # the table occupies rows 1 .. K: row 0 stays zero, as upstream's table packing leaves it - sort_polynomials starts
+        # its walk from a zero (lookup_argument.hpp:596), so the pair (0, first value) must exist in the table column too
+        constants[0, 1:K + 1, 0] = t
+        constants[1, 1:K + 1, 0] = t * t
+        selector[n_gate_sel, 1:K + 1, 0] = 1                                 # the table's tag
+        selector[n_gate_sel + 1, :usable, 0] = 1                             # the lookup gate's selector
+        g = torch.Generator(device=device).manual_seed(seed + 99)
+        u = torch.randint(1, K + 1, (usable,), dtype=torch.int32, device=device, generator=g)
+        cu, cv = 3 * triples, 3 * triples + 1
+        witness[cu, :usable] = 0
+        witness[cv, :usable] = 0
+        witness[cu, :usable, 0] = u
+        witness[cv, :usable, 0] = u * u
+        lookup_tables = [(n_gate_sel, [[0, 1]])]
+        lookup_gates = [(n_gate_sel + 1, [(1, [col(cu), col(cv)])])]
     q_last = torch.zeros((n, 8), dtype=torch.int32, device=device)
     q_last[usable, 0] = 1
     q_blind = torch.zeros((n, 8), dtype=torch.int32, device=device)
@@ -191,6 +214,7 @@ def placeholder_chain_circuit(ctx, field, log_n, triples=1, usable_rows=None, se
     gates = [(0, [sub(mul(col(3 * k), col(3 * k + 1)), col(3 * k + 2)) for k in range(triples)])]
     if rotation_gate:
         gates.append((1, [sub(col(3 * k, 1), col(3 * k + 2)) for k in range(triples)]))
-    circuit = PlaceholderCircuit(F, log_n, nw, 1, 0, selector.shape[0], gates, list(range(npc)), s_id, s_sigma, q_last, q_blind,
-                                 lagrange_0, None, selector, usable, max_quotient_chunks=max_quotient_chunks)
+    circuit = PlaceholderCircuit(F, log_n, nw, 1, 2 if lookup else 0, selector.shape[0], gates, list(range(npc)), s_id, s_sigma, q_last,
+                                 q_blind, lagrange_0, constants, selector, usable, max_quotient_chunks=max_quotient_chunks,
+                                 lookup_tables=lookup_tables, lookup_gates=lookup_gates)
     return circuit, witness, public

@@ -194,8 +194,9 @@ class _Transcript:
         return self.t.state
 
 
-@pytest.mark.parametrize("log_n,triples,mqc", [(4, 1, 0), (6, 2, 0), (6, 2, 4), (5, 3, 3), (10, 1, 0), (10, 4, 4)])
-def test_placeholder_prove_resident_columns(ctx, log_n, triples, mqc):
+@pytest.mark.parametrize("log_n,triples,mqc,lookup", [(4, 1, 0, False), (6, 2, 0, False), (6, 2, 4, False), (5, 3, 3, False), (10, 1, 0, False),
+                                                     (10, 4, 4, False), (5, 1, 0, True), (6, 1, 5, True), (10, 2, 5, True)])
+def test_placeholder_prove_resident_columns(ctx, log_n, triples, mqc, lookup):
     """placeholder_prover's commitment side with every column resident (prover.hpp:133-217).  Checked three ways:
     (1) V_P closes and the consolidated F equals the oracle's exact polynomial arithmetic (small sizes);
     (2) the quotient is exact (F vanishes on the basic domain) and T's chunks equal the oracle's division + split;
@@ -206,7 +207,7 @@ def test_placeholder_prove_resident_columns(ctx, log_n, triples, mqc):
     from crypto3_zk_b200.lpc import FriParams
     F = fields.PALLAS_FP
     p, n = F.p, 1 << log_n
-    circuit, witness, public = W.placeholder_chain_circuit(ctx, F.name, log_n, triples=triples, seed=log_n, max_quotient_chunks=mqc)
+    circuit, witness, public = W.placeholder_chain_circuit(ctx, F.name, log_n, triples=triples, seed=log_n, max_quotient_chunks=mqc, lookup=lookup)
     fri = FriParams.with_max_step_one(log_n, 4, 3)
     tr = _Transcript(0, b"placeholder-test")
     keep = {}
@@ -240,6 +241,8 @@ def test_placeholder_prove_resident_columns(ctx, log_n, triples, mqc):
 
     rots = res["rotations"]
     assert rots[0] == [0, 1] and rots[1] == [0]          # a_k is read on the next row by the rotation gate
+    src = keep["column_source"]
+    batch_points = {P.PERMUTATION_BATCH: [0, 1], P.LOOKUP_BATCH: [0, 1, usable]}   # rotations in the order they were appended
 
     def value_of(c, rot):
         if c < nvar:                                      # opened at y omega^r for the rotations the gates use, ascending
@@ -247,23 +250,37 @@ def test_placeholder_prove_resident_columns(ctx, log_n, triples, mqc):
         if c < tw:                                        # constants / selectors follow S_id, S_sigma, q_last, q_blind
             return z[P.FIXED_VALUES_BATCH][2 * npc + 2 + (c - nvar)][rots[c].index(rot)]
         k = c - tw
-        if k < 2 * npc + 2:                               # S_id, S_sigma, q_last, q_blind
+        if k < 2 * npc:                                   # S_id, S_sigma
             assert rot == 0
             return z[P.FIXED_VALUES_BATCH][k][0]
+        if k < 2 * npc + 2:                               # q_last, q_blind: opened at y and y omega
+            return z[P.FIXED_VALUES_BATCH][k][rot]
         if k == 2 * npc + 2:                              # L_0(y) = (y^n - 1) / (n (y - 1))
+            assert rot == 0
             return (pow(y, n, p) - 1) * pow(n * (y - 1) % p, p - 2, p) % p
-        part = k - (2 * npc + 3)                          # V_P(y), V_P(y omega), then the committed running products at y
-        assert rot == 0 or part == 0
-        return z[P.PERMUTATION_BATCH][part][rot]
+        batch, poly = src[c]                              # V_P, V_L and their parts; the sorted lookup columns
+        return z[batch][poly][batch_points[batch].index(rot)]
 
-    assert len(z[P.PERMUTATION_BATCH]) == circuit.permutation_parts
-    assert nchunks == (mqc if mqc else npc + 2)
+    assert len(z[P.PERMUTATION_BATCH]) == circuit.permutation_parts + (len(circuit.lookup_parts()) if lookup else 0)
+    if not lookup:
+        assert nchunks == (mqc if mqc else npc + 2)
+    else:
+        assert {3, 4, 5, 6} <= set(keep["f_exprs"]) and len(keep["sorted_cols"]) == 2
+        v_l = from_arr(host(keep["perm_polys"][keep["v_l_index"]]))
+        assert v_l[0] == 1 and v_l[usable] == 1          # the lookup grand product closes (lookup_argument.hpp:224)
 
     lhs = placeholder.expr_at_point(total, value_of, p)
     t_y = sum(pow(y, n * k, p) * z[P.QUOTIENT_BATCH][k][0] for k in range(nchunks)) % p
     assert lhs == t_y * (pow(y, n, p) - 1) % p
     # the evaluation proof itself
     assert all(r == 0 for r in res["eval_proof"]["remainders"])
+    if lookup:
+        # a looked-up pair outside the table: the sort refuses it like upstream's assert
+        from crypto3_zk_b200 import capi
+        bad = witness.clone()
+        bad[3 * triples + 1, 2, 0] += 1                   # v != u^2 on one row
+        with pytest.raises(capi.ZkbInvalidArgument):
+            P.placeholder_prove(ctx, circuit, 0, fri, bad, public, _Transcript(0, b"placeholder-test"), query=False)
     # a violated copy constraint: V_P no longer closes, the quotient has a remainder
     witness2 = witness.clone()
     witness2[2, 1, 0] ^= 1

@@ -164,3 +164,46 @@ def test_sort_polynomials_properties():
     assert V[0] == 1 and V[usable] == 1
     inputs[1][4] = (inputs[1][4] + 1) % p              # an input outside the table: the sorted columns no longer balance it
     assert placeholder.lookup_grand_product(inputs, [value], s, beta, gamma, usable, F)[usable] != 1
+
+
+def test_lookup_argument_relations_hold_row_by_row():
+    """lookup_argument.hpp:153-325 on a two-column table (t, t^2) and one lookup constraint (u, u^2): with the compressed
+    values / inputs of prepare_lookup_value / prepare_lookup_input, the sorted columns of sort_polynomials and V_L of
+    compute_V_L, the four argument polynomials F_3 .. F_6 vanish on every row - when the table leaves row 0 zero, as
+    upstream's table packing does (the sort starts its walk from a zero, :596); a table that starts in row 0 breaks V_L"""
+    F = fields.PALLAS_FP
+    p, n = F.p, 32
+    usable, K = n - 4, 13
+    rnd = random.Random(1)
+
+    def relations(first_row):
+        rows = range(first_row, first_row + K)
+        u = [rnd.randrange(1, K + 1) for _ in range(usable)] + [rnd.randrange(p) for _ in range(n - usable)]
+        v = [x * x % p for x in u[:usable]] + [rnd.randrange(p) for _ in range(n - usable)]
+        c0 = [j - first_row + 1 if j in rows else 0 for j in range(n)]
+        c1 = [x * x for x in c0]
+        tag = [1 if j in rows else 0 for j in range(n)]
+        lsel = [1 if j < usable else 0 for j in range(n)]
+        q_last = [1 if j == usable else 0 for j in range(n)]
+        q_blind = [1 if j > usable else 0 for j in range(n)]
+        theta, beta, gamma = rnd.randrange(p), rnd.randrange(p), rnd.randrange(p)
+        mask = [(1 - q_last[j] - q_blind[j]) % p for j in range(n)]
+        value = [mask[j] * tag[j] * (1 + theta * c0[j] + theta * theta * c1[j]) % p for j in range(n)]
+        inp = [lsel[j] * (1 + theta * u[j] + theta * theta * v[j]) % p for j in range(n)]
+        s = placeholder.sort_polynomials([inp], [value], n, usable)
+        V = placeholder.lookup_grand_product([inp], [value], s, beta, gamma, usable, F)
+        ob, part1 = (1 + beta) % p, (1 + beta) * gamma % p
+        g = [ob * (gamma + inp[j]) % p * ((part1 + value[j] + beta * value[(j + 1) % n]) % p) % p for j in range(n)]
+        h = [1] * n
+        for col in s:
+            h = [h[j] * ((part1 + col[j] + beta * col[(j + 1) % n]) % p) % p for j in range(n)]
+        f3 = [(1 if j == 0 else 0) * (1 - V[j]) % p for j in range(n)]
+        f4 = [q_last[j] * (V[j] * V[j] - V[j]) % p for j in range(n)]
+        f5 = [(g[j] * V[j] - h[j] * V[(j + 1) % n]) % p * ((q_last[j] + q_blind[j] - 1) % p) % p for j in range(n)]
+        f6 = [(1 if j == 0 else 0) * (s[1][j] - s[0][(j + usable) % n]) % p for j in range(n)]
+        return V[usable] == 1, [any(f) for f in (f3, f4, f5, f6)]
+
+    closes, nonzero = relations(first_row=1)
+    assert closes and nonzero == [False] * 4
+    closes, nonzero = relations(first_row=0)
+    assert not closes and nonzero[1]
