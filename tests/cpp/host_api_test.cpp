@@ -598,9 +598,9 @@ static void placeholder_prover_test(std::istream &in) {
     typedef placeholder_prover<F, hash_type, hash_type> prover;
     typedef plonk_expression<V> expr;
     typedef prover::dbuf dbuf;
-    std::size_t log_n, triples, usable, mqc, lambda, expand;
-    in >> log_n >> triples >> usable >> mqc >> lambda >> expand;
-    const std::size_t n = std::size_t(1) << log_n, nw = 3 * triples, npc = nw + 1;
+    std::size_t log_n, triples, usable, mqc, lambda, expand, lookup;
+    in >> log_n >> triples >> usable >> mqc >> lambda >> expand >> lookup;
+    const std::size_t n = std::size_t(1) << log_n, nw = 3 * triples + (lookup ? 2 : 0), npc = nw + 1;
     auto read_cols = [&](std::size_t count) {
         std::vector<std::uint32_t> limbs(count * n * 8);
         std::string t;
@@ -614,10 +614,12 @@ static void placeholder_prover_test(std::istream &in) {
         return d;
     };
     prover::circuit_type c;
-    c.log_n = log_n; c.witness_columns = nw; c.public_input_columns = 1; c.constant_columns = 0; c.selector_columns = 2;
+    c.log_n = log_n; c.witness_columns = nw; c.public_input_columns = 1; c.constant_columns = lookup ? 2 : 0;
+    c.selector_columns = lookup ? 4 : 2;
     c.usable_rows = usable; c.max_quotient_chunks = mqc;
     dbuf witness = read_cols(nw), pub = read_cols(1);
-    c.selectors = read_cols(2);
+    if (lookup) c.constants = read_cols(2);
+    c.selectors = read_cols(c.selector_columns);
     c.s_id = read_cols(npc);
     c.s_sigma = read_cols(npc);
     c.q_last = read_cols(1);
@@ -631,13 +633,20 @@ static void placeholder_prover_test(std::istream &in) {
         g1.constraints.push_back(expr::var(3 * k, 1) - expr::var(3 * k + 2));
     }
     c.gates = {g0, g1};
+    if (lookup) {       // the table (t, t^2) in constants 0, 1 under tag selector 2; (u, v) looked up in table 1 under selector 3
+        c.lookup_tables.push_back({2, {{0, 1}}});
+        plonk_lookup_gate<V> lg;
+        lg.tag_index = 3;
+        lg.constraints.push_back({1, {expr::var((std::uint32_t)(3 * triples)), expr::var((std::uint32_t)(3 * triples + 1))}});
+        c.lookup_gates.push_back(lg);
+    }
     auto fp = zk::commitments::fri_params_type::with_max_step_one(log_n, lambda, expand);
     prover::commitment_scheme_type scheme(fp);
     std::vector<std::uint8_t> init = {'p', 'l', 'a', 'c', 'e', 'h', 'o', 'l', 'd', 'e', 'r', '-', 't', 'e', 's', 't'};
     prover::transcript_type tr(init);
     auto fixed_root = prover::preprocess(c, scheme, tr);
     auto proof = prover::process(c, witness, pub, scheme, tr);
-    CHECK(proof.commitments.size() == 3);
+    CHECK(proof.commitments.size() == (lookup ? 4u : 3u));
     auto hex = [](const std::vector<std::uint8_t> &v) { std::string o; char b[3]; for (auto x : v) { std::snprintf(b, 3, "%02x", x); o += b; } return o; };
     std::printf("PLH fixed %s\n", hex(fixed_root).c_str());
     for (const auto &kv : proof.commitments) std::printf("PLH root%zu %s\n", kv.first, hex(kv.second).c_str());

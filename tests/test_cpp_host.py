@@ -177,8 +177,8 @@ def test_cpp_groth16_prover_vs_oracle(tmp_path, curve, kind, nc, ni):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("log_n,triples,mqc", [(4, 1, 0), (6, 2, 4)])
-def test_cpp_placeholder_prover_vs_python_driver(tmp_path, log_n, triples, mqc):
+@pytest.mark.parametrize("log_n,triples,mqc,lookup", [(4, 1, 0, False), (6, 2, 4, False), (6, 1, 5, True), (7, 1, 0, True)])
+def test_cpp_placeholder_prover_vs_python_driver(tmp_path, log_n, triples, mqc, lookup):
     """C++ placeholder_prover<F, Hash, Hash>::preprocess / process (host/zkb_placeholder.hpp, after placeholder/prover.hpp:
     133-217, permutation_argument.hpp:95-215, gates_argument.hpp:133-217) on the chain circuit: the same commitments,
     challenge, opened values, FRI roots and transcript state as crypto3_zk_b200.placeholder.placeholder_prove, which
@@ -190,15 +190,17 @@ def test_cpp_placeholder_prover_vs_python_driver(tmp_path, log_n, triples, mqc):
     F = fields.PALLAS_FP
     ctx = Context(0)
     try:
-        circuit, witness, public = W.placeholder_chain_circuit(ctx, F.name, log_n, triples=triples, seed=log_n, max_quotient_chunks=mqc)
+        circuit, witness, public = W.placeholder_chain_circuit(ctx, F.name, log_n, triples=triples, seed=log_n, max_quotient_chunks=mqc,
+                                                                lookup=lookup)
 
         def dump(t):
             a = t.cpu().numpy().view(np.uint32).reshape(-1, 8)
             return " ".join("%x" % v for v in fields.u32_array_to_ints(a))
 
         lam, expand = 4, 3
-        lines = ["%d %d %d %d %d %d" % (log_n, triples, circuit.usable_rows, mqc, lam, expand)]
-        lines += [dump(witness), dump(public), dump(circuit.selectors), dump(circuit.s_id), dump(circuit.s_sigma),
+        lines = ["%d %d %d %d %d %d %d" % (log_n, triples, circuit.usable_rows, mqc, lam, expand, int(lookup))]
+        lines += [dump(witness), dump(public)] + ([dump(circuit.constants)] if lookup else [])
+        lines += [dump(circuit.selectors), dump(circuit.s_id), dump(circuit.s_sigma),
                   dump(circuit.q_last), dump(circuit.q_blind), dump(circuit.lagrange_0)]
         path = tmp_path / "placeholder.txt"
         path.write_text("\n".join(lines) + "\n")
@@ -212,12 +214,12 @@ def test_cpp_placeholder_prover_vs_python_driver(tmp_path, log_n, triples, mqc):
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:]
     out = {l.split()[1]: l.split()[2:] for l in r.stdout.splitlines() if l.startswith("PLH ")}
     assert out["fixed"][0] == res["commitments"][0].hex()
-    for k in (1, 2, 3):
+    for k in (1, 2, 3) + ((4,) if lookup else ()):
         assert out["root%d" % k][0] == res["commitments"][k].hex(), k
     assert int(out["y"][0], 16) == res["challenge"]
     assert [int(v) for v in out["chunks"]] == [res["quotient_chunks"], res["log_d"]]
     z = res["eval_proof"]["z"]
-    for k in (0, 1, 2, 3):
+    for k in (0, 1, 2, 3) + ((4,) if lookup else ()):
         got = [[int(v, 16) for v in part.split()] for part in " ".join(out["z%d" % k]).split("|")[1:]]
         assert got == [list(v) for v in z[k]], k
     assert out["fri"] == [rt.hex() for rt in res["eval_proof"]["fri"]["roots"]]
