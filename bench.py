@@ -814,7 +814,7 @@ def placeholder_prover_extra(args, torch, ctx, dev):
     rows_log = args.placeholder_log
     n = 1 << rows_log
     mqc = 4
-    circuit, witness, public = W.placeholder_chain_circuit(ctx, "pallas_fp", rows_log, triples=10, seed=5, max_quotient_chunks=mqc)
+    circuit, witness, public = W.placeholder_chain_circuit(ctx, "pallas_fp", rows_log, triples=10, seed=5, max_quotient_chunks=mqc, lookup=True)
     fri = FriParams.with_max_step_one(rows_log, 40, 3)
     res, best = None, None
     for it in range(3):
@@ -836,10 +836,12 @@ def placeholder_prover_extra(args, torch, ctx, dev):
     p = circuit.F.p
     t_y = sum(pow(y, n * k, p) * z[P.QUOTIENT_BATCH][k][0] for k in range(nchunks)) % p
     best.update({"rows": n, "witness_columns": circuit.n_witness, "public_columns": circuit.n_public, "selectors": circuit.n_selector,
+                 "constant_columns": circuit.n_constant, "lookup_tables": len(circuit.lookup_tables), "lookup_constraints": sum(len(cs) for _, cs in circuit.lookup_gates),
+                 "lookup_parts": circuit.lookup_parts(),
                  "permuted_columns": len(circuit.permuted_columns), "max_quotient_chunks": mqc, "permutation_parts": circuit.permutation_parts,
                  "extended_domain_log_blowup": log_d, "quotient_chunks": nchunks, "evaluation_quotients_exact": exact,
                  "T_at_challenge_nonzero": t_y != 0,
-                 "note": "gates a*b=c and a(next)=c over 10 column triples, copy constraints a[j+1]=c[j]; keccak-256, fri_params(1, rows_log, 40, 3); "
+                 "note": "gates a*b=c and a(next)=c over 10 column triples, copy constraints a[j+1]=c[j], one lookup (u, u^2) into a 2-column table of 2^15 rows; keccak-256, fri_params(1, rows_log, 40, 3); "
                          "the verifier identity F(y) = Z(y) T(y) on the opened values is checked by tests/test_gpu_placeholder.py at small sizes"})
     return best
 
