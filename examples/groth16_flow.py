@@ -29,6 +29,8 @@ def chain(p, log_m, num_inputs, rng):
 
 def main(log_m=10):
     ctx = Context(0)
+    import torch
+    torch.zeros(1, device="cuda:0")        # torch's own CUDA start-up (seconds on a fresh box) stays out of the timings
     G1, G2, F = CURVE_BY_NAME["bls12_381_g1"], CURVE_BY_NAME["bls12_381_g2"], FIELD_BY_NAME["bls12_381_fr"]
     p = F.p
     rng = np.random.Generator(np.random.PCG64(3))
@@ -39,7 +41,8 @@ def main(log_m=10):
     key, vk = groth16.generator(ctx, G1.name, G2.name, cs, t, alpha, beta, gamma, delta)
     t1 = time.perf_counter()
     blob = marshalling.proving_key_to_bytes(key)
-    key2 = marshalling.proving_key_from_bytes(blob)
+    t1b = time.perf_counter()
+    key2 = marshalling.proving_key_from_bytes(blob, ctx=ctx)     # query vectors decompressed on the device
     t2 = time.perf_counter()
     pk = groth16.proving_key_from_dict(ctx, G1.name, G2.name, key2)
     proof = groth16.prove(ctx, pk, primary, aux, r, s)
@@ -55,9 +58,9 @@ def main(log_m=10):
     eb = ctx.batch_exp(G2.name, (G2.gen_x, G2.gen_y), _int_rows([b]))
     assert proof[0] == _affine_from_limbs(np.asarray(ea)[0].reshape(-1), coord_limbs(G1), 1), "g_A"
     assert proof[1] == _affine_from_limbs(np.asarray(eb)[0].reshape(-1), coord_limbs(G2), 2), "g_B"
-    print("Groth16, domain 2^%d: generator %.1f ms, key blob %d bytes (write + read %.1f ms), key upload + proof %.1f ms, "
-          "proof %s...; g_A, g_B match their discrete logs" %
-          (log_m, (t1 - t0) * 1e3, len(blob), (t2 - t1) * 1e3, (t3 - t2) * 1e3, wire[:8].hex()))
+    print("Groth16, domain 2^%d: generator %.1f ms, key blob %d bytes (write %.1f ms on the host, read %.1f ms with the points "
+          "decompressed on the device), key + proof %.1f ms, proof %s...; g_A, g_B match their discrete logs" %
+          (log_m, (t1 - t0) * 1e3, len(blob), (t1b - t1) * 1e3, (t2 - t1b) * 1e3, (t3 - t2) * 1e3, wire[:8].hex()))
     ctx.close()
 
 
