@@ -207,7 +207,8 @@ template <class F>
 ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem, uint32_t tid,
                                   uint32_t nthreads) {
     const uint32_t C = ZKB_NTT_C, R = 1u << p.log_r;
-    const uint32_t L = R >> p.zero_levels;               // live rows (all of them unless zero_levels > 0)
+    const int log_l = p.log_r - p.zero_levels;
+    const uint32_t L = 1u << log_l;                      // live rows (all of them unless zero_levels > 0)
     const uint32_t total = L * C * 2;  // 16-byte units
     const u128 zero = {0, 0, 0, 0};
     // with a coset pre-scale the premul phase writes the replicas (after scaling), otherwise the load does
@@ -216,8 +217,8 @@ ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem,
         uint32_t half, r, c;
         if (t.in_col_stride == 1) {      // runs of C elements along the column axis
             half = u & 1; c = (u >> 1) % C; r = u / (2 * C);
-        } else {                         // runs of L elements along the row axis
-            half = u & 1; r = (u >> 1) % L; c = u / (2 * L);
+        } else {                         // runs of L elements along the row axis (L = 2^log_l: shifts, not divisions)
+            half = u & 1; r = (u >> 1) & (L - 1); c = u >> (log_l + 1);
         }
         u128 v = zero;
         const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
@@ -342,7 +343,7 @@ ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128
             if (t.out_col_stride == 1) {
                 half = u & 1; c = (u >> 1) % C; k = u / (2 * C);
             } else {
-                half = u & 1; k = (u >> 1) % R; c = u / (2 * R);
+                half = u & 1; k = (u >> 1) & (R - 1); c = u >> (p.log_r + 1);
             }
             if (c >= t.ncols) continue;
             const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
@@ -356,7 +357,7 @@ ZKB_HD void ntt_phase_store(const NttPassParams &p, const NttTile &t, const u128
     const uint32_t kmask = kskip ? (1u << p.known_log) - 1 : 0u;
     for (uint32_t e = tid; e < R * C; e += nthreads) {
         uint32_t k, c;
-        if (t.out_col_stride == 1) { c = e % C; k = e / C; } else { k = e % R; c = e / R; }
+        if (t.out_col_stride == 1) { c = e % C; k = e / C; } else { k = e & (R - 1); c = e >> p.log_r; }
         if (c >= t.ncols || (kskip && (k & kmask) == 0)) continue;
         const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
         uint64_t off = k * t.out_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : ce * t.out_col_stride);
