@@ -220,13 +220,29 @@ ZKB_HD void ntt_phase_load(const NttPassParams &p, const NttTile &t, u128 *smem,
         } else {                         // runs of L elements along the row axis (L = 2^log_l: shifts, not divisions)
             half = u & 1; r = (u >> 1) & (L - 1); c = u >> (log_l + 1);
         }
-        u128 v = zero;
         const uint32_t ce = c + (c >= t.col_skip ? 1u : 0u);
         uint64_t widx = t.in_tab_base + r * t.in_row_stride + (p.mode == NTT_MODE_SINGLE ? 0 : ce * t.in_col_stride);
-        if (c < t.ncols && widx < p.in_valid_elems)
-            v = p.in[2 * (t.in_base + r * t.in_row_stride + ce * t.in_col_stride) + half];
+        const bool live = c < t.ncols && widx < p.in_valid_elems;
+#if defined(__CUDA_ARCH__)
+        // cp.async: global -> shared without a register round trip, so the 16 copies of a thread are all in flight at once
+        // (a load followed by its own store serialised 16 DRAM round trips per thread: `long_scoreboard` on the STS was
+        // 7 % of all stall samples, profiles/r3b_source.csv); src-size 0 writes zeros
+        const u128 *src = live ? p.in + 2 * (t.in_base + r * t.in_row_stride + ce * t.in_col_stride) + half : p.in;
+        const uint32_t nbytes = live ? 16u : 0u;
+        for (uint32_t k = 0; k < copies; k++) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + ntt_slot(p.log_r, half, r + k * L, c));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+#else
+        u128 v = zero;
+        if (live) v = p.in[2 * (t.in_base + r * t.in_row_stride + ce * t.in_col_stride) + half];
         for (uint32_t k = 0; k < copies; k++) smem[ntt_slot(p.log_r, half, r + k * L, c)] = v;
+#endif
     }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+    (void)zero;
 }
 
 // optional pre-multiplication (coset shift) - separate phase so that it works on whole elements
